@@ -1,0 +1,142 @@
+"""vsb200 — thin ctypes front-end over the C ABI of libvsb200.so (include/vsb200.h).
+
+The product is the shared library (hand-written sm_100a CUDA behind plain C entry points) plus the C++ host
+programs in host/.  This module only exists so that the tests, bench.py and __graft_entry__ can drive the C ABI
+from Python; it adds no compute of its own and has NO fallback: if the library is missing or no CUDA device is
+present, every call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from . import synth  # noqa: F401  (re-exported: seeded synthetic SIFT-shaped data)
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libvsb200.so")
+
+PREC_AUTO, PREC_3XTF32, PREC_FFMA, PREC_TF32_1X = 0, 1, 2, 3
+PREC_NAMES = {0: "auto", 1: "fp32_3xtf32", 2: "fp32_ffma", 3: "tf32_1x"}
+
+
+class VsbError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"vsb200 error {code}: {msg}")
+        self.code = code
+
+
+def build(verbose: bool = False) -> None:
+    """Compile every CUDA source for sm_100a into libvsb200.so (nvcc cross-compiles without a GPU)."""
+    r = subprocess.run(["make", "-C", HERE, "-j8", "all"], capture_output=not verbose, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("libvsb200 build failed:\n" + (r.stdout or "") + (r.stderr or ""))
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise VsbError(-1, f"{LIB_PATH} is missing: run __graft_entry__.build() (there is no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        L.vs_last_error.restype = C.c_char_p
+        L.vs_exact_size.restype = C.c_int64
+        _lib = L
+    return _lib
+
+
+def _check(rc: int) -> None:
+    if rc != 0:
+        raise VsbError(rc, lib().vs_last_error().decode(errors="replace"))
+
+
+def device_count() -> int:
+    c = C.c_int(0)
+    rc = lib().vs_device_count(C.byref(c))
+    return c.value if rc == 0 else 0
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data_as(C.c_void_p)
+    return C.c_void_p(int(a))  # raw device pointer
+
+
+class ExactIndex:
+    """Exact squared-L2 kNN over a device-resident base; mirrors run_benchmark()'s hot triple
+    (cpu/cpu_baseline.cpp:211-248) for a whole query batch."""
+
+    def __init__(self, base, device: int = 0, id_base: int = 0, n: int | None = None, dim: int = 128):
+        self._h = C.c_void_p()
+        if isinstance(base, np.ndarray):
+            base = np.ascontiguousarray(base, dtype=np.float32)
+            n, dim = base.shape
+            _check(lib().vs_exact_create(C.byref(self._h), _ptr(base), C.c_int64(n), C.c_int(dim), C.c_int(device),
+                                         C.c_int64(id_base)))
+        else:  # device pointer
+            _check(lib().vs_exact_create_dev(C.byref(self._h), _ptr(base), C.c_int64(n), C.c_int(dim), C.c_int(device),
+                                             C.c_int64(id_base)))
+        self.n, self.dim, self.device = int(n), int(dim), device
+
+    def close(self) -> None:
+        if self._h:
+            lib().vs_exact_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def base_is_tf32_exact(self) -> bool:
+        return bool(lib().vs_exact_base_is_tf32_exact(self._h))
+
+    def search(self, queries: np.ndarray, k: int, precision: int = PREC_AUTO, out_ids=None, out_dists=None):
+        """Host buffers in, host buffers out (H2D + search + D2H inside the call)."""
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        nq = q.shape[0]
+        ids = out_ids if out_ids is not None else np.empty((nq, k), dtype=np.int32)
+        d = out_dists if out_dists is not None else np.empty((nq, k), dtype=np.float32)
+        _check(lib().vs_exact_search_f32(self._h, _ptr(q), C.c_int64(nq), C.c_int(k), C.c_int(precision), _ptr(ids),
+                                         _ptr(d)))
+        return ids, d
+
+    def search_dev(self, q_ptr: int, nq: int, k: int, precision: int, ids_ptr: int, dists_ptr: int, stream: int = 0):
+        """Device pointers, asynchronous on `stream` (a raw cudaStream_t value)."""
+        _check(lib().vs_exact_search_dev(self._h, _ptr(q_ptr), C.c_int64(nq), C.c_int(k), C.c_int(precision),
+                                         _ptr(ids_ptr), _ptr(dists_ptr), C.c_void_p(stream)))
+
+    def set_profile(self, enable: bool = True) -> None:
+        _check(lib().vs_exact_set_profile(self._h, C.c_int(int(enable))))
+
+    def last_kernel_ms(self) -> float:
+        ms = C.c_float(0)
+        _check(lib().vs_exact_last_kernel_ms(self._h, C.byref(ms)))
+        return float(ms.value)
+
+    def last_launches(self):
+        a, b = C.c_int(0), C.c_int(0)
+        _check(lib().vs_exact_last_launches(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+
+def merge_topk_dev(ids_ptr: int, keys_ptr: int, n_shards: int, nq: int, k: int, smallest: bool, out_ids_ptr: int,
+                   out_keys_ptr: int, stream: int = 0) -> None:
+    _check(lib().vs_merge_topk_dev(_ptr(ids_ptr), _ptr(keys_ptr), C.c_int(n_shards), C.c_int64(nq), C.c_int(k),
+                                   C.c_int(int(smallest)), _ptr(out_ids_ptr), _ptr(out_keys_ptr), C.c_void_p(stream)))
+
+
+def synth_fill_dev(out_ptr: int, row0: int, nrows: int, dim: int, law: str, seed: int, centre_seed: int = 7,
+                   stream: int = 0) -> None:
+    _check(lib().vs_synth_fill_dev(_ptr(out_ptr), C.c_int64(row0), C.c_int64(nrows), C.c_int(dim),
+                                   C.c_int(synth.LAWS[law]), C.c_uint64(seed), C.c_uint64(centre_seed),
+                                   C.c_void_p(stream)))

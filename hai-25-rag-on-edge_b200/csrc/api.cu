@@ -1,0 +1,441 @@
+// C ABI of libvsb200 (include/vsb200.h): handle management, workspace, TMA descriptors, search orchestration.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+#include "vsb_common.cuh"
+
+namespace vsb {
+
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point query: libvsb200.so then has no link-time
+// dependency on libcuda and still loads (for symbol checks) on machines without a driver.
+typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static encode_tiled_fn get_encode_fn() {
+    static encode_tiled_fn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (encode_tiled_fn)p;
+    });
+    return fn;
+}
+
+// 2D row-major [rows x cols] matrix of `elem_bytes` elements, box = 128 B x box_rows, 128-B swizzle, OOB -> 0
+int make_tmap_2d(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_t cols, int elem_bytes, uint32_t box_rows) {
+    encode_tiled_fn fn = get_encode_fn();
+    if (!fn) return fail(VS_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    const CUtensorMapDataType dt = elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT8;
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstr[1] = {cols * (uint64_t)elem_bytes};
+    cuuint32_t box[2] = {(cuuint32_t)(128 / elem_bytes), box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(out, dt, 2, const_cast<void*>(gptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(VS_ERR_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+    return VS_OK;
+}
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return VS_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        const size_t want = bytes + bytes / 4;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) return fail(VS_ERR_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+        cap = want;
+        return VS_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T>
+    T* as() const { return (T*)p; }
+};
+
+}  // namespace vsb
+
+using namespace vsb;
+
+struct vs_exact {
+    int device = 0;
+    int num_sms = 148;
+    int64_t n = 0;
+    int dim = 0;
+    int64_t id_base = 0;
+    bool owns_base = false;
+    const float* d_base = nullptr;  // [n x dim] fp32
+    float* d_hi = nullptr;          // TF32 split (dim == 128 only); d_hi aliases d_base when the base is TF32-exact
+    float* d_lo = nullptr;
+    float* d_norm = nullptr;        // [n_tiles*128] +inf padded
+    bool base_exact = false;
+    CUtensorMap tmB_hi, tmB_lo;
+    cudaStream_t stream = nullptr;
+    // workspace (grow-only)
+    DevBuf q, qhi, qlo, qnorm, part_key, part_id, lbk, lbi, out_ids, out_keys, flag;
+    int* h_flag = nullptr;  // pinned
+    int last_launches = 0;
+    int last_precision = 0;
+    // optional CUDA-event timing of the dominant kernel (bench.py's roofline line)
+    bool profile = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool ev_valid = false;
+};
+
+static int exact_free(vs_exact* h) {
+    if (!h) return VS_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->owns_base && h->d_base) cudaFree((void*)h->d_base);
+    if (h->d_hi && h->d_hi != h->d_base) cudaFree(h->d_hi);
+    if (h->d_lo) cudaFree(h->d_lo);
+    if (h->d_norm) cudaFree(h->d_norm);
+    for (DevBuf* b : {&h->q, &h->qhi, &h->qlo, &h->qnorm, &h->part_key, &h->part_id, &h->lbk, &h->lbi, &h->out_ids,
+                      &h->out_keys, &h->flag})
+        b->release();
+    if (h->h_flag) cudaFreeHost(h->h_flag);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return VS_OK;
+}
+
+static int exact_build(vs_exact* h) {
+    const int64_t n = h->n;
+    const int dim = h->dim;
+    const int64_t n_pad = ceil_div64(n, 128) * 128;
+    VSB_CUDA(cudaMalloc((void**)&h->d_norm, sizeof(float) * (size_t)n_pad));
+    VSB_TRY(launch_fill_f32(h->d_norm, n_pad, __builtin_inff(), h->stream));
+    VSB_TRY(h->flag.reserve(sizeof(int)));
+    VSB_CUDA(cudaMallocHost((void**)&h->h_flag, sizeof(int)));
+    VSB_CUDA(cudaMemsetAsync(h->flag.p, 0, sizeof(int), h->stream));
+    if (dim == 128) {
+        VSB_CUDA(cudaMalloc((void**)&h->d_hi, sizeof(float) * (size_t)n * dim));
+        VSB_CUDA(cudaMalloc((void**)&h->d_lo, sizeof(float) * (size_t)n * dim));
+        VSB_TRY(launch_prep_rows(h->d_base, n, dim, h->d_norm, h->d_hi, h->d_lo, h->flag.as<int>(), h->stream));
+        VSB_CUDA(cudaMemcpyAsync(h->h_flag, h->flag.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        VSB_CUDA(cudaStreamSynchronize(h->stream));
+        h->base_exact = (*h->h_flag == 0);
+        if (h->base_exact) {  // hi == x and lo == 0: keep one copy
+            cudaFree(h->d_hi);
+            cudaFree(h->d_lo);
+            h->d_hi = const_cast<float*>(h->d_base);
+            h->d_lo = nullptr;
+        }
+        VSB_TRY(make_tmap_2d(&h->tmB_hi, h->d_hi, (uint64_t)n, 128, 4, 128));
+        if (h->d_lo)
+            VSB_TRY(make_tmap_2d(&h->tmB_lo, h->d_lo, (uint64_t)n, 128, 4, 128));
+        else
+            h->tmB_lo = h->tmB_hi;
+        VSB_TRY(tc_set_attributes());
+    } else {
+        VSB_TRY(launch_prep_rows(h->d_base, n, dim, h->d_norm, nullptr, nullptr, nullptr, h->stream));
+        VSB_CUDA(cudaStreamSynchronize(h->stream));
+    }
+    return VS_OK;
+}
+
+static int exact_create_common(vs_exact_t** out, const float* base, bool on_device, int64_t n, int dim, int device,
+                               int64_t id_base) {
+    if (!out) return fail(VS_ERR_INVALID, "out handle is NULL");
+    *out = nullptr;
+    if (!base || n <= 0) return fail(VS_ERR_INVALID, "base is NULL or n <= 0");
+    if (dim != 128) return fail(VS_ERR_UNSUPPORTED, "only dim == 128 (SIFT shape) is implemented");
+    if (id_base < 0 || id_base + n > 0x7fffffffLL) return fail(VS_ERR_INVALID, "ids must fit int32");
+    int cnt = 0;
+    if (cudaGetDeviceCount(&cnt) != cudaSuccess || cnt == 0) {
+        cudaGetLastError();
+        return fail(VS_ERR_CUDA, "no CUDA device available (libvsb200 has no CPU fallback)");
+    }
+    if (device < 0 || device >= cnt) return fail(VS_ERR_INVALID, "bad device ordinal");
+    VSB_CUDA(cudaSetDevice(device));
+    vs_exact* h = new (std::nothrow) vs_exact();
+    if (!h) return fail(VS_ERR_NOMEM, "host allocation failed");
+    h->device = device;
+    h->n = n;
+    h->dim = dim;
+    h->id_base = id_base;
+    cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device);
+    int rc = VS_OK;
+    do {
+        if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+            rc = fail(VS_ERR_CUDA, "cudaStreamCreate failed");
+            break;
+        }
+        if (on_device) {
+            h->d_base = base;
+            h->owns_base = false;
+        } else {
+            float* d = nullptr;
+            cudaError_t e = cudaMalloc((void**)&d, sizeof(float) * (size_t)n * dim);
+            if (e != cudaSuccess) {
+                rc = fail(VS_ERR_NOMEM, std::string("cudaMalloc(base): ") + cudaGetErrorString(e));
+                break;
+            }
+            h->d_base = d;
+            h->owns_base = true;
+            e = cudaMemcpyAsync(d, base, sizeof(float) * (size_t)n * dim, cudaMemcpyHostToDevice, h->stream);
+            if (e != cudaSuccess) {
+                rc = fail(VS_ERR_CUDA, std::string("H2D(base): ") + cudaGetErrorString(e));
+                break;
+            }
+        }
+        rc = exact_build(h);
+    } while (0);
+    if (rc != VS_OK) {
+        std::string keep = g_err;
+        exact_free(h);
+        g_err = keep;
+        return rc;
+    }
+    *out = h;
+    return VS_OK;
+}
+
+// One group of <= 32 results per query: [pass]
+static int exact_search_core(vs_exact* h, const float* q_dev, int64_t nq, int k, int precision, int32_t* out_ids,
+                             float* out_dists, cudaStream_t st) {
+    h->last_launches = 0;
+    if (nq == 0) return VS_OK;
+    const int dim = h->dim;
+    int prec = precision;
+    if (prec != VS_PREC_AUTO && prec != VS_PREC_FP32_3XTF32 && prec != VS_PREC_FP32_FFMA && prec != VS_PREC_TF32_1X)
+        return fail(VS_ERR_INVALID, "unknown precision");
+    if (nq > 0x7fffffff / 128) return fail(VS_ERR_INVALID, "nq too large");
+    const bool want_tc = (prec == VS_PREC_FP32_3XTF32 || prec == VS_PREC_TF32_1X || (prec == VS_PREC_AUTO && nq > 16));
+    if (want_tc && dim != 128) return fail(VS_ERR_UNSUPPORTED, "tensor-core path needs dim == 128");
+
+    VSB_TRY(h->qnorm.reserve(sizeof(float) * (size_t)nq));
+    const int passes = (k + kMaxRegK - 1) / kMaxRegK;
+    const int ktop = passes == 1 ? round_up_ktop(k) : kMaxRegK;
+    if (passes > 1) {
+        VSB_TRY(h->lbk.reserve(sizeof(float) * (size_t)nq));
+        VSB_TRY(h->lbi.reserve(sizeof(int32_t) * (size_t)nq));
+    }
+
+    if (want_tc) {
+        VSB_TRY(h->qhi.reserve(sizeof(float) * (size_t)nq * 128));
+        VSB_TRY(h->qlo.reserve(sizeof(float) * (size_t)nq * 128));
+        VSB_CUDA(cudaMemsetAsync(h->flag.p, 0, sizeof(int), st));
+        VSB_TRY(launch_prep_rows(q_dev, nq, 128, h->qnorm.as<float>(), h->qhi.as<float>(), h->qlo.as<float>(),
+                                 h->flag.as<int>(), st));
+        h->last_launches++;
+        bool split3 = true;
+        if (prec == VS_PREC_TF32_1X) {
+            split3 = false;
+        } else if (prec == VS_PREC_AUTO) {
+            if (h->base_exact) {  // 1xTF32 is bit-identical to 3xTF32 iff the query lo parts are all zero too
+                VSB_CUDA(cudaMemcpyAsync(h->h_flag, h->flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+                VSB_CUDA(cudaStreamSynchronize(st));
+                split3 = (*h->h_flag != 0);
+            }
+        }
+        if (split3 && !h->d_lo && !h->base_exact) return fail(VS_ERR_INVALID, "internal: lo split missing");
+        h->last_precision = split3 ? VS_PREC_FP32_3XTF32 : VS_PREC_TF32_1X;
+        const TcPlan plan = tc_make_plan(h->n, nq, h->num_sms);
+        VSB_TRY(h->part_key.reserve(sizeof(float) * (size_t)plan.n_splits * nq * ktop));
+        VSB_TRY(h->part_id.reserve(sizeof(int32_t) * (size_t)plan.n_splits * nq * ktop));
+        CUtensorMap tmA_hi, tmA_lo;
+        VSB_TRY(make_tmap_2d(&tmA_hi, h->qhi.p, (uint64_t)nq, 128, 4, 128));
+        VSB_TRY(make_tmap_2d(&tmA_lo, h->qlo.p, (uint64_t)nq, 128, 4, 128));
+        // base lo == 0 (TF32-exact base): the q_hi.x_lo product vanishes; the kernel still issues it against
+        // the hi map's zero... no: keep arithmetic honest — with an exact base the lo map aliases hi only when
+        // split3 is false (never read).  A 3x search over an exact base needs a real zero lo operand:
+        if (split3 && !h->d_lo) {
+            VSB_CUDA(cudaMalloc((void**)&h->d_lo, sizeof(float) * (size_t)h->n * 128));
+            VSB_CUDA(cudaMemsetAsync(h->d_lo, 0, sizeof(float) * (size_t)h->n * 128, st));
+            VSB_TRY(make_tmap_2d(&h->tmB_lo, h->d_lo, (uint64_t)h->n, 128, 4, 128));
+        }
+        for (int pass = 0; pass < passes; ++pass) {
+            const int kk = std::min(kMaxRegK, k - pass * kMaxRegK);
+            const bool lb = pass > 0;
+            if (h->profile && pass == 0) VSB_CUDA(cudaEventRecord(h->ev0, st));
+            VSB_TRY(launch_exact_tc(tmA_hi, tmA_lo, h->tmB_hi, h->tmB_lo, h->d_norm, h->qnorm.as<float>(), (int)nq, plan,
+                                    ktop, split3, lb ? h->lbk.as<float>() : nullptr, lb ? h->lbi.as<int32_t>() : nullptr,
+                                    h->part_key.as<float>(), h->part_id.as<int32_t>(), st));
+            if (h->profile && pass == 0) {
+                VSB_CUDA(cudaEventRecord(h->ev1, st));
+                h->ev_valid = true;
+            }
+            VSB_TRY(launch_merge_lists(h->part_key.as<float>(), h->part_id.as<int32_t>(), plan.n_splits, nq, ktop,
+                                       passes == 1 ? k : kk, h->id_base, 0, 0, out_dists, out_ids, k, pass * kMaxRegK,
+                                       passes > 1 ? h->lbk.as<float>() : nullptr,
+                                       passes > 1 ? h->lbi.as<int32_t>() : nullptr, st));
+            h->last_launches += 2;
+        }
+        return VS_OK;
+    }
+
+    // ---- FFMA streaming path: groups of <= 8 queries, one pass over the base per group (and per 32 results)
+    h->last_precision = VS_PREC_FP32_FFMA;
+    VSB_TRY(launch_prep_rows(q_dev, nq, dim, h->qnorm.as<float>(), nullptr, nullptr, nullptr, st));
+    h->last_launches++;
+    const int max_ctas = stream_num_ctas(h->device, 1);
+    VSB_TRY(h->part_key.reserve(sizeof(float) * (size_t)max_ctas * 8 * ktop));
+    VSB_TRY(h->part_id.reserve(sizeof(int32_t) * (size_t)max_ctas * 8 * ktop));
+    for (int64_t q0 = 0; q0 < nq; q0 += 8) {
+        const int g = (int)std::min<int64_t>(8, nq - q0);
+        const int n_ctas = stream_num_ctas(h->device, g);
+        for (int pass = 0; pass < passes; ++pass) {
+            const int kk = std::min(kMaxRegK, k - pass * kMaxRegK);
+            const bool lb = pass > 0;
+            if (h->profile && pass == 0 && q0 == 0) VSB_CUDA(cudaEventRecord(h->ev0, st));
+            VSB_TRY(launch_exact_stream(h->d_base, h->d_norm, h->n, q_dev + q0 * dim, h->qnorm.as<float>() + q0, g, ktop,
+                                        lb ? h->lbk.as<float>() + q0 : nullptr, lb ? h->lbi.as<int32_t>() + q0 : nullptr,
+                                        h->part_key.as<float>(), h->part_id.as<int32_t>(), n_ctas, st));
+            if (h->profile && pass == 0 && q0 == 0) {
+                VSB_CUDA(cudaEventRecord(h->ev1, st));
+                h->ev_valid = true;
+            }
+            VSB_TRY(launch_merge_lists(h->part_key.as<float>(), h->part_id.as<int32_t>(), n_ctas, g, ktop,
+                                       passes == 1 ? k : kk, h->id_base, 0, 0, out_dists + q0 * k, out_ids + q0 * k, k,
+                                       pass * kMaxRegK, passes > 1 ? h->lbk.as<float>() + q0 : nullptr,
+                                       passes > 1 ? h->lbi.as<int32_t>() + q0 : nullptr, st));
+            h->last_launches += 2;
+        }
+    }
+    return VS_OK;
+}
+
+extern "C" {
+
+const char* vs_last_error(void) { return g_err.c_str(); }
+int vs_abi_version(void) { return VSB200_ABI_VERSION; }
+
+int vs_device_count(int* count) {
+    if (!count) return fail(VS_ERR_INVALID, "count is NULL");
+    *count = 0;
+    int c = 0;
+    if (cudaGetDeviceCount(&c) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(VS_ERR_CUDA, "no CUDA device available");
+    }
+    *count = c;
+    return c > 0 ? VS_OK : fail(VS_ERR_CUDA, "no CUDA device available");
+}
+
+int vs_exact_create(vs_exact_t** out, const float* base, int64_t n, int dim, int device, int64_t id_base) {
+    return exact_create_common(out, base, false, n, dim, device, id_base);
+}
+int vs_exact_create_dev(vs_exact_t** out, const float* base_dev, int64_t n, int dim, int device, int64_t id_base) {
+    return exact_create_common(out, base_dev, true, n, dim, device, id_base);
+}
+int vs_exact_destroy(vs_exact_t* h) { return exact_free(h); }
+int64_t vs_exact_size(const vs_exact_t* h) { return h ? h->n : 0; }
+int vs_exact_dim(const vs_exact_t* h) { return h ? h->dim : 0; }
+int vs_exact_base_is_tf32_exact(const vs_exact_t* h) { return h && h->base_exact ? 1 : 0; }
+
+int vs_exact_search_dev(vs_exact_t* h, const float* queries_dev, int64_t nq, int k, int precision, int32_t* out_ids_dev,
+                        float* out_dists_dev, void* stream) {
+    if (!h) return fail(VS_ERR_INVALID, "handle is NULL");
+    if (nq < 0 || k <= 0) return fail(VS_ERR_INVALID, "nq < 0 or k <= 0");
+    if ((int64_t)k > h->n) return fail(VS_ERR_INVALID, "k > n (undefined in the reference, cpu_baseline.cpp:129-131)");
+    if (nq > 0 && (!queries_dev || !out_ids_dev || !out_dists_dev)) return fail(VS_ERR_INVALID, "NULL buffer");
+    VSB_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    return exact_search_core(h, queries_dev, nq, k, precision, out_ids_dev, out_dists_dev, st);
+}
+
+int vs_exact_search_f32(vs_exact_t* h, const float* queries, int64_t nq, int k, int precision, int32_t* out_ids,
+                        float* out_dists) {
+    if (!h) return fail(VS_ERR_INVALID, "handle is NULL");
+    if (nq < 0 || k <= 0) return fail(VS_ERR_INVALID, "nq < 0 or k <= 0");
+    if ((int64_t)k > h->n) return fail(VS_ERR_INVALID, "k > n (undefined in the reference, cpu_baseline.cpp:129-131)");
+    if (nq == 0) return VS_OK;
+    if (!queries || !out_ids || !out_dists) return fail(VS_ERR_INVALID, "NULL buffer");
+    VSB_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    VSB_TRY(h->q.reserve(sizeof(float) * (size_t)nq * h->dim));
+    VSB_TRY(h->out_ids.reserve(sizeof(int32_t) * (size_t)nq * k));
+    VSB_TRY(h->out_keys.reserve(sizeof(float) * (size_t)nq * k));
+    VSB_CUDA(cudaMemcpyAsync(h->q.p, queries, sizeof(float) * (size_t)nq * h->dim, cudaMemcpyHostToDevice, st));
+    VSB_TRY(exact_search_core(h, h->q.as<float>(), nq, k, precision, h->out_ids.as<int32_t>(), h->out_keys.as<float>(), st));
+    VSB_CUDA(cudaMemcpyAsync(out_ids, h->out_ids.p, sizeof(int32_t) * (size_t)nq * k, cudaMemcpyDeviceToHost, st));
+    VSB_CUDA(cudaMemcpyAsync(out_dists, h->out_keys.p, sizeof(float) * (size_t)nq * k, cudaMemcpyDeviceToHost, st));
+    VSB_CUDA(cudaStreamSynchronize(st));
+    return VS_OK;
+}
+
+int vs_exact_last_launches(const vs_exact_t* h, int* n_kernels, int* precision_used) {
+    if (!h) return fail(VS_ERR_INVALID, "handle is NULL");
+    if (n_kernels) *n_kernels = h->last_launches;
+    if (precision_used) *precision_used = h->last_precision;
+    return VS_OK;
+}
+
+int vs_exact_set_profile(vs_exact_t* h, int enable) {
+    if (!h) return fail(VS_ERR_INVALID, "handle is NULL");
+    VSB_CUDA(cudaSetDevice(h->device));
+    if (enable && !h->ev0) {
+        VSB_CUDA(cudaEventCreate(&h->ev0));
+        VSB_CUDA(cudaEventCreate(&h->ev1));
+    }
+    h->profile = enable != 0;
+    h->ev_valid = false;
+    return VS_OK;
+}
+
+int vs_exact_last_kernel_ms(vs_exact_t* h, float* ms) {
+    if (!h || !ms) return fail(VS_ERR_INVALID, "NULL argument");
+    if (!h->ev_valid) return fail(VS_ERR_INVALID, "no profiled search yet (vs_exact_set_profile)");
+    VSB_CUDA(cudaEventSynchronize(h->ev1));
+    VSB_CUDA(cudaEventElapsedTime(ms, h->ev0, h->ev1));
+    return VS_OK;
+}
+
+int vs_merge_topk_dev(const int32_t* ids_dev, const float* keys_dev, int n_shards, int64_t nq, int k, int smallest,
+                      int32_t* out_ids_dev, float* out_keys_dev, void* stream) {
+    if (!ids_dev || !keys_dev || !out_ids_dev || !out_keys_dev) return fail(VS_ERR_INVALID, "NULL buffer");
+    if (n_shards <= 0 || nq < 0 || k <= 0) return fail(VS_ERR_INVALID, "bad sizes");
+    if (k > kMaxRegK) return fail(VS_ERR_UNSUPPORTED, "merge of k > 32 lists is not implemented");
+    return launch_merge_lists(keys_dev, ids_dev, n_shards, nq, k, k, 0, smallest ? 0 : 1, smallest ? 0 : 1, out_keys_dev,
+                              out_ids_dev, k, 0, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+int vs_synth_fill_dev(float* out_dev, int64_t row0, int64_t nrows, int dim, int law, uint64_t seed, uint64_t centre_seed,
+                      void* stream) {
+    if (!out_dev || nrows < 0 || dim <= 0) return fail(VS_ERR_INVALID, "bad arguments");
+    return launch_synth(out_dev, row0, nrows, dim, law, seed, centre_seed, (cudaStream_t)stream);
+}
+
+int vs_host_alloc(void** out, size_t bytes) {
+    if (!out) return fail(VS_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    cudaError_t e = cudaMallocHost(out, bytes ? bytes : 1);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(VS_ERR_CUDA, std::string("cudaMallocHost: ") + cudaGetErrorString(e));
+    }
+    return VS_OK;
+}
+int vs_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+    return VS_OK;
+}
+
+}  // extern "C"

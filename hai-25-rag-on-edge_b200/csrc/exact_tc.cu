@@ -1,0 +1,114 @@
+// Host-side planning and launch of K1 (exact_tc.cuh).
+#include "exact_tc.cuh"
+
+#include <algorithm>
+
+#include "kernels.cuh"
+
+namespace vsb {
+
+// Split the base into n_splits contiguous tile ranges so that n_mtiles * n_splits units fill the grid in an
+// (almost) integral number of rounds.  More splits = better balance but more partial lists and more list
+// warm-up; each split keeps at least 16 tiles unless the problem is tiny.
+TcPlan tc_make_plan(int64_t n, int64_t nq, int num_sms) {
+    TcPlan pl{};
+    pl.n_tiles = (int)ceil_div64(n, TC_BN);
+    pl.n_mtiles = (int)ceil_div64(nq, TC_BM);
+    const int max_splits = std::max(1, std::min(pl.n_tiles / 16, 64));
+    int best_s = 1;
+    double best_cost = 1e30;
+    for (int s = 1; s <= std::max(1, max_splits); ++s) {
+        const int tps = (pl.n_tiles + s - 1) / s;
+        const int s_eff = (pl.n_tiles + tps - 1) / tps;
+        const int64_t units = (int64_t)pl.n_mtiles * s_eff;
+        const int64_t rounds = ceil_div64(units, num_sms);
+        // time ~ rounds * tiles per unit (+ a small per-unit overhead measured in tiles)
+        const double cost = (double)rounds * (tps + 2.0);
+        if (cost < best_cost - 1e-9) {
+            best_cost = cost;
+            best_s = s_eff;
+        }
+    }
+    pl.tiles_per_split = (pl.n_tiles + best_s - 1) / best_s;
+    pl.n_splits = (pl.n_tiles + pl.tiles_per_split - 1) / pl.tiles_per_split;
+    pl.grid = (int)std::min<int64_t>((int64_t)pl.n_mtiles * pl.n_splits, num_sms);
+    return pl;
+}
+
+template <int KTOP, bool SPLIT3, bool HAS_LB>
+static int set_attr_one() {
+    VSB_CUDA(cudaFuncSetAttribute(exact_tc_kernel<KTOP, SPLIT3, HAS_LB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  TcSmem<SPLIT3>::TOTAL));
+    return VS_OK;
+}
+
+int tc_set_attributes() {
+    VSB_TRY((set_attr_one<1, false, false>()));
+    VSB_TRY((set_attr_one<1, true, false>()));
+    VSB_TRY((set_attr_one<5, false, false>()));
+    VSB_TRY((set_attr_one<5, true, false>()));
+    VSB_TRY((set_attr_one<10, false, false>()));
+    VSB_TRY((set_attr_one<10, true, false>()));
+    VSB_TRY((set_attr_one<16, false, false>()));
+    VSB_TRY((set_attr_one<16, true, false>()));
+    VSB_TRY((set_attr_one<32, false, false>()));
+    VSB_TRY((set_attr_one<32, true, false>()));
+    VSB_TRY((set_attr_one<32, false, true>()));
+    VSB_TRY((set_attr_one<32, true, true>()));
+    return VS_OK;
+}
+
+int launch_exact_tc(const CUtensorMap& tmA_hi, const CUtensorMap& tmA_lo, const CUtensorMap& tmB_hi,
+                    const CUtensorMap& tmB_lo, const float* bnorm, const float* qnorm, int nq, const TcPlan& plan,
+                    int ktop, bool split3, const float* lb_key, const int32_t* lb_id, float* part_key,
+                    int32_t* part_id, cudaStream_t st) {
+    TcParams p{};
+    p.bnorm = bnorm;
+    p.qnorm = qnorm;
+    p.lb_key = lb_key;
+    p.lb_id = lb_id;
+    p.part_key = part_key;
+    p.part_id = part_id;
+    p.nq = nq;
+    p.n_tiles = plan.n_tiles;
+    p.n_mtiles = plan.n_mtiles;
+    p.n_splits = plan.n_splits;
+    p.tiles_per_split = plan.tiles_per_split;
+    if (lb_key && ktop != 32) return fail(VS_ERR_INVALID, "tc: lower bound needs the 32-entry list");
+#define VSB_TC_LAUNCH(KT, S3, LB)                                                                               \
+    exact_tc_kernel<KT, S3, LB><<<plan.grid, TC_THREADS, TcSmem<S3>::TOTAL, st>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, p)
+#define VSB_TC_CASE(KT)                         \
+    case KT:                                    \
+        if (split3)                             \
+            VSB_TC_LAUNCH(KT, true, false);     \
+        else                                    \
+            VSB_TC_LAUNCH(KT, false, false);    \
+        break;
+    switch (ktop) {
+        VSB_TC_CASE(1)
+        VSB_TC_CASE(5)
+        VSB_TC_CASE(10)
+        VSB_TC_CASE(16)
+        case 32:
+            if (lb_key) {
+                if (split3)
+                    VSB_TC_LAUNCH(32, true, true);
+                else
+                    VSB_TC_LAUNCH(32, false, true);
+            } else {
+                if (split3)
+                    VSB_TC_LAUNCH(32, true, false);
+                else
+                    VSB_TC_LAUNCH(32, false, false);
+            }
+            break;
+        default:
+            return fail(VS_ERR_INVALID, "tc: unsupported list size");
+    }
+#undef VSB_TC_CASE
+#undef VSB_TC_LAUNCH
+    VSB_CUDA(cudaGetLastError());
+    return VS_OK;
+}
+
+}  // namespace vsb

@@ -1,0 +1,288 @@
+// K1 — fused distance GEMM + top-k on the 5th-generation tensor cores (tcgen05, accumulators in TMEM, operands
+// fed by TMA), replacing the reference's per-query  cblas_sgemm(M=1) -> distance loop -> select_topk
+// (cpu/cpu_baseline.cpp:222-248) for a whole batch of queries.  The Q x N distance matrix never exists in
+// memory: each epilogue thread owns one query row of the accumulator tile and folds it into a register-
+// resident top-k list.
+//
+// Mapping: queries -> M (TMEM lanes, 128 per CTA), base rows -> N (TMEM columns, 128 per tile), K = dim = 128 as
+// 4 k-blocks of 32 fp32 (one 128-byte swizzle row each).  kind::tf32, K = 8 per instruction.
+//   1xTF32 : 16 MMAs per tile (exact when operands are TF32-representable, e.g. integer SIFT data)
+//   3xTF32 : q.x ~= q_lo.x_hi + q_hi.x_hi + q_hi.x_lo per k-block, 48 MMAs per tile, fp32 accumulate
+// Work decomposition: unit = (query tile, base split); units are ordered split-major so that the CTAs resident
+// at any moment sweep the same base panel (it streams from HBM once and is re-read from L2 by the other
+// query tiles).  Each unit writes a sorted partial list [split][query][KTOP]; merge_partials_kernel (K3)
+// combines them.
+//
+// Warp roles (192 threads): warp 0 = TMA producer (one lane), warp 1 = TMEM allocator + MMA issuer (one
+// lane), warps 2..5 = epilogue (TMEM lane quadrant = warp % 4).
+#pragma once
+#include <cuda.h>
+
+#include "vsb_common.cuh"
+
+namespace vsb {
+
+constexpr int TC_BM = 128;        // queries per CTA tile
+constexpr int TC_BN = 128;        // base rows per accumulator tile
+constexpr int TC_NKB = 4;         // k-blocks (dim 128 = 4 x 32 fp32)
+constexpr int TC_KB_BYTES = 128 * 128;  // one k-block of a 128-row operand tile: 128 rows x 128 B
+constexpr int TC_NACC = 4;        // accumulator buffers in TMEM (4 x 128 columns = all 512)
+constexpr int TC_THREADS = 192;
+
+template <bool SPLIT3>
+struct TcSmem {
+    static constexpr int A_BYTES = (SPLIT3 ? 2 : 1) * TC_NKB * TC_KB_BYTES;
+    static constexpr int NSTAGE = SPLIT3 ? 5 : 8;
+    static constexpr int B_BYTES = NSTAGE * TC_KB_BYTES;
+    static constexpr int BAR_BYTES = 1024;
+    static constexpr int TOTAL = A_BYTES + B_BYTES + BAR_BYTES + 1024;  // + slack for 1024-B alignment
+};
+
+struct TcParams {
+    const float* bnorm;  // [n_tiles*128], +inf beyond n
+    const float* qnorm;  // [nq]
+    const float* lb_key; // optional per-query exclusive lower bound (multi-pass k > 32), or nullptr
+    const int32_t* lb_id;
+    float* part_key;     // [n_splits][nq][KTOP]
+    int32_t* part_id;
+    int nq;
+    int n_tiles;         // ceil(n / 128)
+    int n_mtiles;        // ceil(nq / 128)
+    int n_splits;
+    int tiles_per_split;
+};
+
+template <int KTOP, bool SPLIT3, bool HAS_LB>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+                const TcParams p) {
+    using S = TcSmem<SPLIT3>;
+    constexpr int NSTAGE = S::NSTAGE;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + S::A_BYTES;
+    uint64_t* bars = (uint64_t*)(sB + S::B_BYTES);
+    uint64_t* full = bars;                    // [NSTAGE]  TMA -> MMA
+    uint64_t* empty = full + NSTAGE;          // [NSTAGE]  MMA -> TMA
+    uint64_t* acc_full = empty + NSTAGE;      // [TC_NACC] MMA -> epilogue
+    uint64_t* acc_empty = acc_full + TC_NACC; // [TC_NACC] epilogue -> MMA
+    uint64_t* a_full = acc_empty + TC_NACC;   // query tile landed
+    uint64_t* a_empty = a_full + 1;           // query tile no longer read by the tensor core
+    uint32_t* tmem_slot = (uint32_t*)(a_empty + 1);
+
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const int lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NSTAGE; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], 1);
+        }
+        for (int i = 0; i < TC_NACC; ++i) {
+            mbar_init(&acc_full[i], 1);
+            mbar_init(&acc_empty[i], 4);
+        }
+        mbar_init(a_full, 1);
+        mbar_init(a_empty, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, TC_NACC * TC_BN);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int n_units = p.n_mtiles * p.n_splits;
+
+    if (warp == 0) {
+        // ===================================== TMA producer =====================================
+        if (lane == 0) {
+            tma_prefetch_desc(&tmA_hi);
+            tma_prefetch_desc(&tmB_hi);
+            if (SPLIT3) {
+                tma_prefetch_desc(&tmA_lo);
+                tma_prefetch_desc(&tmB_lo);
+            }
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++it) {
+                const int m_tile = unit % p.n_mtiles;
+                const int split = unit / p.n_mtiles;
+                mbar_wait(a_empty, (uint32_t)((it & 1) ^ 1));
+                mbar_expect_tx(a_full, (uint32_t)S::A_BYTES);
+#pragma unroll
+                for (int kb = 0; kb < TC_NKB; ++kb) {
+                    tma_load_2d(sA + kb * TC_KB_BYTES, &tmA_hi, a_full, kb * 32, m_tile * TC_BM);
+                    if (SPLIT3) tma_load_2d(sA + (TC_NKB + kb) * TC_KB_BYTES, &tmA_lo, a_full, kb * 32, m_tile * TC_BM);
+                }
+                const int t0 = split * p.tiles_per_split;
+                const int t1 = min(t0 + p.tiles_per_split, p.n_tiles);
+                for (int t = t0; t < t1; ++t) {
+#pragma unroll
+                    for (int kb = 0; kb < TC_NKB; ++kb) {
+                        mbar_wait(&empty[stage], phase ^ 1);
+                        mbar_expect_tx(&full[stage], (uint32_t)TC_KB_BYTES);
+                        tma_load_2d(sB + stage * TC_KB_BYTES, &tmB_hi, &full[stage], kb * 32, t * TC_BN);
+                        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                        if (SPLIT3) {
+                            mbar_wait(&empty[stage], phase ^ 1);
+                            mbar_expect_tx(&full[stage], (uint32_t)TC_KB_BYTES);
+                            tma_load_2d(sB + stage * TC_KB_BYTES, &tmB_lo, &full[stage], kb * 32, t * TC_BN);
+                            if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================== MMA issuer =======================================
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc(kIdescCF32, kIdescTF32, TC_BM, TC_BN);
+            const uint32_t sA_u = smem_u32(sA);
+            const uint32_t sB_u = smem_u32(sB);
+            int stage = 0, acc = 0;
+            uint32_t phase = 0, acc_phase = 0;
+            int it = 0;
+            for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++it) {
+                const int split = unit / p.n_mtiles;
+                const int t0 = split * p.tiles_per_split;
+                const int t1 = min(t0 + p.tiles_per_split, p.n_tiles);
+                mbar_wait(a_full, (uint32_t)(it & 1));
+                tc_fence_after();
+                for (int t = t0; t < t1; ++t) {
+                    mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TC_BN);
+                    uint32_t accum = 0;
+#pragma unroll
+                    for (int kb = 0; kb < TC_NKB; ++kb) {
+                        const uint64_t a_hi = umma_desc_sw128(sA_u + kb * TC_KB_BYTES);
+                        const uint64_t a_lo = umma_desc_sw128(sA_u + (TC_NKB + kb) * TC_KB_BYTES);
+                        // ---- stage holding x_hi[kb]
+                        mbar_wait(&full[stage], phase);
+                        tc_fence_after();
+                        {
+                            const uint64_t b = umma_desc_sw128(sB_u + stage * TC_KB_BYTES);
+                            if (SPLIT3) {
+#pragma unroll
+                                for (int ks = 0; ks < 4; ++ks) {  // q_lo . x_hi   (small term first)
+                                    tc_mma_tf32(d_tmem, a_lo + 2 * ks, b + 2 * ks, idesc, accum);
+                                    accum = 1;
+                                }
+                            }
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks) {      // q_hi . x_hi
+                                tc_mma_tf32(d_tmem, a_hi + 2 * ks, b + 2 * ks, idesc, accum);
+                                accum = 1;
+                            }
+                        }
+                        tc_commit(&empty[stage]);
+                        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                        if (SPLIT3) {
+                            // ---- stage holding x_lo[kb]
+                            mbar_wait(&full[stage], phase);
+                            tc_fence_after();
+                            const uint64_t b = umma_desc_sw128(sB_u + stage * TC_KB_BYTES);
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks)        // q_hi . x_lo
+                                tc_mma_tf32(d_tmem, a_hi + 2 * ks, b + 2 * ks, idesc, 1u);
+                            tc_commit(&empty[stage]);
+                            if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                        }
+                    }
+                    tc_commit(&acc_full[acc]);
+                    if (++acc == TC_NACC) { acc = 0; acc_phase ^= 1; }
+                }
+                tc_commit(a_empty);
+            }
+        }
+    } else {
+        // ===================================== epilogue ==========================================
+        const int quad = warp & 3;
+        const int row = quad * 32 + lane;
+        const float INF = __int_as_float(0x7f800000);
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+            const int m_tile = unit % p.n_mtiles;
+            const int split = unit / p.n_mtiles;
+            const int t0 = split * p.tiles_per_split;
+            const int t1 = min(t0 + p.tiles_per_split, p.n_tiles);
+            const int q = m_tile * TC_BM + row;
+            const bool valid = q < p.nq;
+            const float qn = valid ? __ldg(p.qnorm + q) : 0.f;
+            float lbk = -INF;
+            int32_t lbi = -1;
+            if (HAS_LB && valid) {
+                lbk = __ldg(p.lb_key + q);
+                lbi = __ldg(p.lb_id + q);
+            }
+            RegTopK<KTOP> top;
+            top.init();
+            for (int t = t0; t < t1; ++t) {
+                mbar_wait(&acc_full[acc], acc_phase);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * TC_BN);
+#pragma unroll 1
+                for (int c = 0; c < TC_BN / 32; ++c) {
+                    uint32_t r[32];
+                    tmem_ld32(taddr + c * 32, r);
+                    float bn[32];
+                    const float4* bn4 = reinterpret_cast<const float4*>(p.bnorm + (size_t)t * TC_BN + c * 32);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 v = __ldg(bn4 + j);
+                        bn[4 * j + 0] = v.x;
+                        bn[4 * j + 1] = v.y;
+                        bn[4 * j + 2] = v.z;
+                        bn[4 * j + 3] = v.w;
+                    }
+                    tc_wait_ld();
+                    const int col0 = t * TC_BN + c * 32;
+                    float d[32];
+                    float mn = INF;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        // (qn + bn) - 2*dot, cpu_baseline.cpp:241 (2*dot is exact, so one rounding either way)
+                        float v = fmaf(-2.0f, __uint_as_float(r[j]), qn + bn[j]);
+                        if (HAS_LB) {
+                            const bool after = v > lbk || (v == lbk && (col0 + j) > lbi);
+                            v = after ? v : INF;
+                        }
+                        d[j] = v;
+                        mn = fminf(mn, v);
+                    }
+                    if (mn < top.threshold()) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (d[j] < top.threshold()) top.insert(d[j], col0 + j);
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[acc]);
+                if (++acc == TC_NACC) { acc = 0; acc_phase ^= 1; }
+            }
+            if (valid) {
+                float* pk = p.part_key + ((size_t)split * p.nq + q) * KTOP;
+                int32_t* pi = p.part_id + ((size_t)split * p.nq + q) * KTOP;
+#pragma unroll
+                for (int i = 0; i < KTOP; ++i) {
+                    pk[i] = top.key[i];
+                    pi[i] = top.id[i];
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, TC_NACC * TC_BN);
+}
+
+}  // namespace vsb

@@ -1,0 +1,245 @@
+// Index-build / query-prep kernels, list merge (K3) and the device-side synthetic data generator.
+#include "kernels.cuh"
+#include "vsb_common.cuh"
+
+namespace vsb {
+
+int round_up_ktop(int k) {
+    if (k <= 1) return 1;
+    if (k <= 5) return 5;
+    if (k <= 10) return 10;
+    if (k <= 16) return 16;
+    if (k <= 32) return 32;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// prep: norms (reference order) + TF32 hi/lo split
+// ------------------------------------------------------------------------------------------------
+// 8 threads per row; thread l accumulates v[l], v[l+8], ... with FMA exactly like lane l of the AVX2 register in
+// compute_norm_avx2 (cpu_baseline.cpp:99-102); lanes are then added in order 0..7 (:106-107), the scalar tail
+// (:109-111, contracted to FMA by g++ -O3 -mfma) follows.  Each step the 8 threads read 32 contiguous bytes.
+__device__ __forceinline__ float round_tf32(float a) {  // round to nearest (ties away), low 13 mantissa bits zero
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(a));
+    return __uint_as_float(r);
+}
+
+__global__ void __launch_bounds__(256) prep_rows_kernel(const float* __restrict__ x, int64_t rows, int dim,
+                                                        float* __restrict__ norms, float* __restrict__ hi,
+                                                        float* __restrict__ lo, int* __restrict__ not_exact) {
+    const int l = threadIdx.x & 7;
+    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    const bool active = row < rows;
+    const float* v = x + (active ? row : 0) * (int64_t)dim;
+    float acc = 0.f;
+    int inexact = 0;
+    const int dim8 = dim & ~7;
+    if (active) {
+        for (int i = l; i < dim8; i += 8) {
+            const float a = __ldg(v + i);
+            acc = fmaf(a, a, acc);
+            if (hi) {
+                const float h = round_tf32(a);
+                const float r = round_tf32(a - h);  // a - h is exact
+                hi[row * (int64_t)dim + i] = h;
+                lo[row * (int64_t)dim + i] = r;
+                inexact |= (r != 0.f);
+            }
+        }
+    }
+    // lanes summed 0..7 in order by the first thread of the group
+    float s = acc;
+#pragma unroll
+    for (int j = 1; j < 8; ++j) {
+        const float o = __shfl_sync(0xffffffffu, acc, (threadIdx.x & 31 & ~7) + j);
+        if (l == 0) s = s + o;
+    }
+    if (active && l == 0) {
+        for (int i = dim8; i < dim; ++i) {
+            const float a = __ldg(v + i);
+            s = fmaf(a, a, s);
+            if (hi) {
+                const float h = round_tf32(a);
+                const float r = round_tf32(a - h);
+                hi[row * (int64_t)dim + i] = h;
+                lo[row * (int64_t)dim + i] = r;
+                inexact |= (r != 0.f);
+            }
+        }
+        if (norms) norms[row] = s;
+    }
+    if (not_exact && __any_sync(0xffffffffu, inexact) && (threadIdx.x & 31) == 0) atomicOr(not_exact, 1);
+}
+
+int launch_prep_rows(const float* x, int64_t rows, int dim, float* norms, float* hi, float* lo, int* not_tf32_exact,
+                     cudaStream_t st) {
+    if (rows <= 0) return VS_OK;
+    const int64_t threads = rows * 8;
+    const int64_t blocks = ceil_div64(threads, 256);
+    prep_rows_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, rows, dim, norms, hi, lo, not_tf32_exact);
+    VSB_CUDA(cudaGetLastError());
+    return VS_OK;
+}
+
+__global__ void fill_f32_kernel(float* p, int64_t n, float v) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+int launch_fill_f32(float* p, int64_t n, float v, cudaStream_t st) {
+    if (n <= 0) return VS_OK;
+    const int64_t blocks = ceil_div64(n, 256);
+    fill_f32_kernel<<<(unsigned)(blocks > 1184 ? 1184 : blocks), 256, 0, st>>>(p, n, v);
+    VSB_CUDA(cudaGetLastError());
+    return VS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3: merge sorted partial lists.  One warp per query; lane j folds lists j, j+32, ... into a register
+// list, then the warp pops the global minimum k times (warp_merge_lists).
+// ------------------------------------------------------------------------------------------------
+template <int KTOP>
+__global__ void __launch_bounds__(128) merge_lists_kernel(const float* __restrict__ part_key,
+                                                          const int32_t* __restrict__ part_id, int n_lists, int64_t nq,
+                                                          int list_len, int k, int64_t id_base, int neg_in, int neg_out, float* __restrict__ out_key,
+                                                          int32_t* __restrict__ out_id, int out_stride, int out_off,
+                                                          float* __restrict__ lb_key_out, int32_t* __restrict__ lb_id_out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t q = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (q >= nq) return;
+    RegTopK<KTOP> L;
+    L.init();
+    bool first = true;
+    for (int l = lane; l < n_lists; l += 32) {
+        const float* pk = part_key + ((size_t)l * nq + q) * list_len;
+        const int32_t* pi = part_id + ((size_t)l * nq + q) * list_len;
+        if (first) {  // lists are already sorted: adopt the first one as is
+#pragma unroll
+            for (int i = 0; i < KTOP; ++i) {
+                if (i < list_len) {
+                    const float kk = pk[i];
+                    L.key[i] = neg_in ? -kk : kk;
+                    L.id[i] = pi[i];
+                }
+            }
+            first = false;
+        } else {
+#pragma unroll 1
+            for (int i = 0; i < list_len; ++i) {
+                const int32_t id = pi[i];
+                if (id < 0) break;
+                const float kk = pk[i];
+                L.insert_any(neg_in ? -kk : kk, id);
+            }
+        }
+    }
+    const float INF = __int_as_float(0x7f800000);
+    float lastk = INF;
+    int32_t lasti = -1;
+    for (int r = 0; r < k; ++r) {
+        float hk = L.key[0];
+        int32_t hi = L.id[0];
+        int src = lane;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ok = __shfl_xor_sync(0xffffffffu, hk, o);
+            const int32_t oi = __shfl_xor_sync(0xffffffffu, hi, o);
+            const int os = __shfl_xor_sync(0xffffffffu, src, o);
+            if (pair_less(ok, oi, hk, hi)) {
+                hk = ok;
+                hi = oi;
+                src = os;
+            }
+        }
+        if (lane == 0) {
+            out_key[q * out_stride + out_off + r] = hi >= 0 ? (neg_out ? -hk : hk) : (neg_out ? -INF : INF);
+            out_id[q * out_stride + out_off + r] = hi >= 0 ? (int32_t)(hi + id_base) : -1;
+        }
+        lastk = hk;
+        lasti = hi;
+        if (src == lane && hi >= 0) {
+#pragma unroll
+            for (int i = 0; i + 1 < KTOP; ++i) {
+                L.key[i] = L.key[i + 1];
+                L.id[i] = L.id[i + 1];
+            }
+            L.key[KTOP - 1] = INF;
+            L.id[KTOP - 1] = -1;
+        }
+    }
+    if (lb_key_out && lane == 0) {  // exclusive lower bound for the next pass (local ids, un-negated search keys)
+        lb_key_out[q] = lasti >= 0 ? lastk : INF;
+        lb_id_out[q] = lasti >= 0 ? lasti : 0x7fffffff;
+    }
+}
+
+int launch_merge_lists(const float* part_key, const int32_t* part_id, int n_lists, int64_t nq, int list_len, int k,
+                       int64_t id_base, int neg_in, int neg_out, float* out_key, int32_t* out_id, int out_stride, int out_off,
+                       float* lb_key_out, int32_t* lb_id_out, cudaStream_t st) {
+    if (nq <= 0) return VS_OK;
+    const unsigned blocks = (unsigned)ceil_div64(nq, 4);
+#define VSB_MERGE_CASE(KT)                                                                                          \
+    case KT:                                                                                                        \
+        merge_lists_kernel<KT><<<blocks, 128, 0, st>>>(part_key, part_id, n_lists, nq, list_len, k, id_base, neg_in, neg_out, out_key, \
+                                                       out_id, out_stride, out_off, lb_key_out, lb_id_out);         \
+        break;
+    if (k > list_len) return fail(VS_ERR_INVALID, "merge: k > list length");
+    switch (round_up_ktop(list_len)) {
+        VSB_MERGE_CASE(1)
+        VSB_MERGE_CASE(5)
+        VSB_MERGE_CASE(10)
+        VSB_MERGE_CASE(16)
+        VSB_MERGE_CASE(32)
+        default:
+            return fail(VS_ERR_INVALID, "merge: unsupported list size");
+    }
+#undef VSB_MERGE_CASE
+    VSB_CUDA(cudaGetLastError());
+    return VS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// synthetic data (must stay bit-identical to hai-25-rag-on-edge_b200/synth.py)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__device__ __forceinline__ uint64_t hash_idx(uint64_t seed, uint64_t idx) { return mix64(idx + seed * 0x9E3779B97F4A7C15ull); }
+__device__ __forceinline__ int sift_from_hash(uint64_t h) { return (int)(((h & 0xFF) * ((h >> 8) & 0xFF)) >> 9); }
+
+__global__ void synth_kernel(float* __restrict__ out, int64_t row0, int64_t nrows, int dim, int law, uint64_t seed,
+                             uint64_t centre_seed) {
+    const int64_t total = nrows * dim;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const uint64_t r = (uint64_t)(row0 + e / dim);
+        const uint64_t c = (uint64_t)(e % dim);
+        const uint64_t h = hash_idx(seed, r * (uint64_t)dim + c);
+        float v;
+        if (law == 0) {
+            v = (float)sift_from_hash(h);
+        } else if (law == 1) {
+            const float frac = (float)((h >> 16) & 0xFFFF) / 65536.0f;
+            v = (float)sift_from_hash(h) + (frac - 0.5f);
+        } else {
+            const uint64_t cid = hash_idx(seed ^ 0x5BD1E995ull, r) % 4096ull;
+            const int centre = sift_from_hash(hash_idx(centre_seed, cid * (uint64_t)dim + c));
+            const int s = (int)((h >> 16) & 0xFF) + (int)((h >> 24) & 0xFF) + (int)((h >> 32) & 0xFF) + (int)((h >> 40) & 0xFF);
+            int val = centre + s / 12 - 42;
+            val = val < 0 ? 0 : (val > 218 ? 218 : val);
+            v = (float)val;
+        }
+        out[e] = v;
+    }
+}
+
+int launch_synth(float* out, int64_t row0, int64_t nrows, int dim, int law, uint64_t seed, uint64_t centre_seed,
+                 cudaStream_t st) {
+    if (nrows <= 0) return VS_OK;
+    if (law < 0 || law > 2) return fail(VS_ERR_INVALID, "synth: unknown law");
+    synth_kernel<<<148 * 8, 256, 0, st>>>(out, row0, nrows, dim, law, seed, centre_seed);
+    VSB_CUDA(cudaGetLastError());
+    return VS_OK;
+}
+
+}  // namespace vsb

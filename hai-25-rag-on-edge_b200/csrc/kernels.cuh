@@ -1,0 +1,51 @@
+// Launch wrappers implemented in the .cu files of libvsb200 (internal interface between api.cu and the kernels).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace vsb {
+
+// prep.cu ---------------------------------------------------------------------------------------
+// ||x||^2 per row in the reference's summation order (cpu_baseline.cpp:95-114) and, when hi/lo are non-null,
+// the TF32 split x = hi + lo (hi = rna_tf32(x), lo = rna_tf32(x - hi)).  *not_tf32_exact is OR-ed with 1 when
+// some lo != 0.  norms may be null.
+int launch_prep_rows(const float* x, int64_t rows, int dim, float* norms, float* hi, float* lo, int* not_tf32_exact,
+                     cudaStream_t st);
+int launch_fill_f32(float* p, int64_t n, float v, cudaStream_t st);
+
+// exact_stream.cu -------------------------------------------------------------------------------
+// K2: HBM-streaming FFMA scan for up to 8 queries at a time. Writes sorted partial lists
+// part[(cta*nq + q)*ktop + i]; returns the number of partial lists per query in *n_parts.
+int stream_num_ctas(int device, int nq);
+int launch_exact_stream(const float* base, const float* bnorm, int64_t n, const float* q, const float* qnorm, int nq,
+                        int ktop, const float* lb_key, const int32_t* lb_id, float* part_key, int32_t* part_id,
+                        int n_ctas, cudaStream_t st);
+
+// exact_tc.cu -----------------------------------------------------------------------------------
+struct TcPlan {
+    int n_tiles, n_mtiles, n_splits, tiles_per_split, grid;
+};
+TcPlan tc_make_plan(int64_t n, int64_t nq, int num_sms);
+int launch_exact_tc(const CUtensorMap& tmA_hi, const CUtensorMap& tmA_lo, const CUtensorMap& tmB_hi,
+                    const CUtensorMap& tmB_lo, const float* bnorm, const float* qnorm, int nq, const TcPlan& plan,
+                    int ktop, bool split3, const float* lb_key, const int32_t* lb_id, float* part_key,
+                    int32_t* part_id, cudaStream_t st);
+int tc_set_attributes();  // opt-in to > 48 KB dynamic shared memory for every instantiation
+
+// merge.cu --------------------------------------------------------------------------------------
+// Merges n_lists sorted lists of `list_len` (<= 32) entries per query (layout [list][nq][list_len]) into out[nq][k],
+// canonical (key asc, id asc); adds id_base to valid ids; neg_in / neg_out flip the key sign on load / store
+// (descending scores are handled as ascending negated keys).  Optionally appends to an existing result prefix (multi-pass k > 32): out_off entries
+// per query are already final.
+int launch_merge_lists(const float* part_key, const int32_t* part_id, int n_lists, int64_t nq, int list_len, int k,
+                       int64_t id_base, int neg_in, int neg_out, float* out_key, int32_t* out_id, int out_stride, int out_off,
+                       float* lb_key_out, int32_t* lb_id_out, cudaStream_t st);
+
+// synth.cu --------------------------------------------------------------------------------------
+int launch_synth(float* out, int64_t row0, int64_t nrows, int dim, int law, uint64_t seed, uint64_t centre_seed,
+                 cudaStream_t st);
+
+int round_up_ktop(int k);  // smallest supported register-list size >= k (1,5,10,16,32), 0 if k > 32
+
+}  // namespace vsb

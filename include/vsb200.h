@@ -1,0 +1,120 @@
+/* vsb200 — C ABI of the B200-native vector-search hot paths (libvsb200.so).
+ *
+ * Drop-in boundary for the two data-parallel hot paths of zyx7k/HAI-25-RAG-on-Edge (file:line relative
+ * to the reference tree):
+ *
+ *   exact L2 kNN   replaces the triple  compute_norms -> cblas_sgemm(M=1) -> select_topk  inside
+ *                  run_benchmark()                     cpu/cpu_baseline.cpp:116-153, 211-248
+ *   IVF search     replaces IVFIndex::IVFIndex / search / searchBatch and the QNN coarse MatMul
+ *                  qidk_ivf/android/app/main/jni/IVFIndex.h:19-54, IVFIndex.cpp:154-267, 572-859
+ *                  and the builder build_ivf_index()   qidk_ivf/prepare/create_ivf_model.py:86-175
+ *   INT8 brute     replaces QnnRunner::executeRaw/executeBatchRaw + find_top_k_int8
+ *                  qidk_bruteforce/android/app/main/jni/QnnRunner.h:20-52, QnnRunner.cpp:13-55,529-638,
+ *                  main.cpp:36-71
+ *
+ * Conventions: plain pointers and sizes, no C++ or torch types; every function returns a vs_status
+ * (0 = ok) and never throws; vs_last_error() gives the message of the last failure on the calling thread.
+ * Host buffers are owned by the caller; *_dev entry points take device pointers valid on the handle's
+ * device and enqueue on the given CUDA stream (cudaStream_t passed as void*, NULL = the handle's own
+ * stream) without synchronising.  A handle is not thread-safe (one in-flight search per handle);
+ * different handles are independent.  There is NO CPU fallback: without a CUDA device every compute
+ * entry point fails with VS_ERR_CUDA.
+ *
+ * Result order is canonical and deterministic: exact L2 -> (distance ascending, id ascending);
+ * IVF / INT8 -> (score descending, id ascending).  Ids are global row ids (shard id_base added).
+ */
+#ifndef VSB200_H
+#define VSB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VSB200_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define VSB_API __attribute__((visibility("default")))
+#else
+#define VSB_API
+#endif
+
+typedef enum vs_status {
+    VS_OK = 0,
+    VS_ERR_INVALID = 1,     /* bad argument (NULL, k<=0, k>n, dim mismatch, ...) */
+    VS_ERR_CUDA = 2,        /* CUDA runtime/driver failure or no device */
+    VS_ERR_IO = 3,          /* index directory / file problem */
+    VS_ERR_NOMEM = 4,
+    VS_ERR_UNSUPPORTED = 5  /* shape outside what the kernels implement */
+} vs_status;
+
+/* Arithmetic of the exact path's dot products (distances are always combined in fp32 as
+ * (qn + bn) - 2*dot, cpu_baseline.cpp:241). */
+typedef enum vs_precision {
+    VS_PREC_AUTO = 0,        /* small batches -> FFMA stream; otherwise 1xTF32 when every operand is exactly
+                                representable in TF32 (integer SIFT data: bit-identical to fp32), else 3xTF32 */
+    VS_PREC_FP32_3XTF32 = 1, /* tcgen05 kind::tf32, hi/lo split, 3 products, fp32 accumulate in TMEM */
+    VS_PREC_FP32_FFMA = 2,   /* CUDA-core FFMA streaming kernel (HBM-bound; any batch, slow for large ones) */
+    VS_PREC_TF32_1X = 3      /* single TF32 product; exact only for TF32-representable data */
+} vs_precision;
+
+VSB_API const char* vs_last_error(void);
+VSB_API int vs_abi_version(void);
+/* number of visible CUDA devices (0 and VS_ERR_CUDA when there is none) */
+VSB_API int vs_device_count(int* count);
+
+/* ---------------------------------------------------------------------------------------------- */
+/* Exact L2 kNN                                                                                    */
+/* ---------------------------------------------------------------------------------------------- */
+typedef struct vs_exact vs_exact_t;
+
+/* Builds the device-resident index for base[n x dim] (row-major fp32, host memory): copies the rows,
+ * precomputes ||x||^2 in the reference's summation order (cpu_baseline.cpp:95-114) and the TF32 hi/lo split.
+ * device = CUDA ordinal; id_base is added to every returned id (row-sharded multi-GPU use). dim must be 128
+ * for the tensor-core path (any dim multiple of 4 up to 1024 for FFMA). */
+VSB_API int vs_exact_create(vs_exact_t** out, const float* base, int64_t n, int dim, int device, int64_t id_base);
+/* Same, base already resident on `device` (not copied; must outlive the handle). */
+VSB_API int vs_exact_create_dev(vs_exact_t** out, const float* base_dev, int64_t n, int dim, int device, int64_t id_base);
+VSB_API int vs_exact_destroy(vs_exact_t* h);
+VSB_API int64_t vs_exact_size(const vs_exact_t* h);
+VSB_API int vs_exact_dim(const vs_exact_t* h);
+/* 1 if every base component is exactly representable in TF32 (then 1xTF32 == 3xTF32 == fp32 bit for bit) */
+VSB_API int vs_exact_base_is_tf32_exact(const vs_exact_t* h);
+
+/* queries[nq x dim] host -> out_ids[nq x k] (int32), out_dists[nq x k] (squared L2, ascending).
+ * Timed span equivalent to the reference's (cpu_baseline.cpp:220-257): query upload + search + download. */
+VSB_API int vs_exact_search_f32(vs_exact_t* h, const float* queries, int64_t nq, int k, int precision,
+                        int32_t* out_ids, float* out_dists);
+/* Device-pointer variant; asynchronous on `stream`. */
+VSB_API int vs_exact_search_dev(vs_exact_t* h, const float* queries_dev, int64_t nq, int k, int precision,
+                        int32_t* out_ids_dev, float* out_dists_dev, void* stream);
+/* Introspection for benchmarks: kernels launched / tensor-core or streaming kernel device time of the last
+ * search is measured by the caller with CUDA events on the stream; this returns how many kernels the last
+ * search launched and which precision path AUTO resolved to. */
+VSB_API int vs_exact_last_launches(const vs_exact_t* h, int* n_kernels, int* precision_used);
+/* When enabled, every search brackets its dominant kernel (the fused distance+top-k kernel: tcgen05 or FFMA
+ * stream) with CUDA events on the launching stream; vs_exact_last_kernel_ms waits for and returns that duration. */
+VSB_API int vs_exact_set_profile(vs_exact_t* h, int enable);
+VSB_API int vs_exact_last_kernel_ms(vs_exact_t* h, float* ms);
+
+/* Merge per-shard results gathered from G shards (layout [G][nq][k], as produced by an all-gather of every
+ * rank's out_ids/out_dists) into the global top-k per query, canonical order. smallest!=0: keys ascending
+ * (L2); smallest==0: keys descending (inner product). Device pointers, asynchronous on `stream`. */
+VSB_API int vs_merge_topk_dev(const int32_t* ids_dev, const float* keys_dev, int n_shards, int64_t nq, int k,
+                      int smallest, int32_t* out_ids_dev, float* out_keys_dev, void* stream);
+
+/* Seeded synthetic SIFT-shaped rows generated on the device (bit-identical to the numpy generator in
+ * hai-25-rag-on-edge_b200/synth.py). law: 0 "sift", 1 "cont", 2 "mix". */
+VSB_API int vs_synth_fill_dev(float* out_dev, int64_t row0, int64_t nrows, int dim, int law, uint64_t seed,
+                      uint64_t centre_seed, void* stream);
+
+/* Pinned host memory helpers (so that host<->device copies inside the timed span run at full PCIe rate). */
+VSB_API int vs_host_alloc(void** out, size_t bytes);
+VSB_API int vs_host_free(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VSB200_H */

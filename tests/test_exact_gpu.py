@@ -1,0 +1,159 @@
+"""GPU parity tests for the exact-L2 path, through the C ABI (ctypes), against the golden vectors of the
+unmodified reference and against the CPU oracle on the same seeded inputs."""
+import numpy as np
+import pytest
+
+from util import RTOL, assert_topk_matches, golden_cases, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _precisions(vsb, law):
+    p = [vsb.PREC_3XTF32, vsb.PREC_FFMA, vsb.PREC_AUTO]
+    if law == "sift":
+        p.append(vsb.PREC_TF32_1X)  # exact on TF32-representable (integer) data
+    return p
+
+
+@pytest.mark.parametrize("path", golden_cases(), ids=lambda p: p.split("/")[-1][:-4])
+def test_golden_reference_vectors(path, gpu_vsb, oracle):
+    vsb = gpu_vsb
+    g, law, base, qry, k = load_golden(path, vsb.synth)
+    exact = law == "sift"
+    idx = vsb.ExactIndex(base)
+    try:
+        assert idx.base_is_tf32_exact == exact
+        for prec in _precisions(vsb, law):
+            ids, d = idx.search(qry, k, prec)
+            rec = oracle.exact_distances_at(base, qry, ids)
+            assert_topk_matches(ids, d, g["ids"], g["dists"], rec, exact=exact,
+                                what=f"{path} prec={vsb.PREC_NAMES[prec]}")
+            # canonical order: equal to the oracle's canonical mode bit for bit on integer data
+            if exact:
+                oi, od = oracle.exact_search(base, qry, k, mode=1)
+                assert np.array_equal(ids, oi) and np.array_equal(d, od)
+    finally:
+        idx.close()
+
+
+@pytest.mark.parametrize("nb,nq,k", [(1, 1, 1), (127, 1, 5), (129, 3, 10), (1000, 129, 10), (4097, 257, 16),
+                                     (20000, 17, 32), (3001, 40, 33), (2000, 9, 70)])
+@pytest.mark.parametrize("law", ["sift", "cont"])
+def test_ragged_shapes_vs_oracle(nb, nq, k, law, gpu_vsb, oracle):
+    vsb = gpu_vsb
+    k = min(k, nb)
+    base = vsb.synth.make(law, 1000 + nb, nb)
+    qry = vsb.synth.make(law, 2000 + nq, nq)
+    oi, od = oracle.exact_search(base, qry, k, mode=1)
+    idx = vsb.ExactIndex(base)
+    try:
+        for prec in _precisions(vsb, law):
+            ids, d = idx.search(qry, k, prec)
+            rec = oracle.exact_distances_at(base, qry, ids)
+            assert_topk_matches(ids, d, oi, od, rec, exact=(law == "sift"),
+                                what=f"nb={nb} nq={nq} k={k} {law} {vsb.PREC_NAMES[prec]}")
+    finally:
+        idx.close()
+
+
+def test_mid_size_vs_oracle(gpu_vsb, oracle):
+    """300K x 128, 300 queries: several query tiles, several base splits, every SM busy."""
+    vsb = gpu_vsb
+    for law in ("sift", "cont"):
+        base = vsb.synth.make(law, 77, 300_000)
+        qry = vsb.synth.make(law, 78, 300)
+        oi, od = oracle.exact_search(base, qry, 10, mode=1)
+        idx = vsb.ExactIndex(base)
+        try:
+            for prec in _precisions(vsb, law):
+                nq = 300 if prec != vsb.PREC_FFMA else 24
+                ids, d = idx.search(qry[:nq], 10, prec)
+                rec = oracle.exact_distances_at(base, qry[:nq], ids)
+                assert_topk_matches(ids, d, oi[:nq], od[:nq], rec, exact=(law == "sift"),
+                                    what=f"mid {law} {vsb.PREC_NAMES[prec]}")
+        finally:
+            idx.close()
+
+
+def test_3xtf32_is_fp32_faithful(gpu_vsb):
+    """Continuous data: 3xTF32 distances within 1e-5 relative of a float64 evaluation, and far closer than 1xTF32."""
+    vsb = gpu_vsb
+    base = vsb.synth.make("cont", 5, 50_000)
+    qry = vsb.synth.make("cont", 6, 256)
+    idx = vsb.ExactIndex(base)
+    try:
+        ids3, d3 = idx.search(qry, 10, vsb.PREC_3XTF32)
+        ids1, d1 = idx.search(qry, 10, vsb.PREC_TF32_1X)
+    finally:
+        idx.close()
+    b64, q64 = base.astype(np.float64), qry.astype(np.float64)
+    true3 = ((q64[:, None, :] - b64[ids3]) ** 2).sum(-1)
+    true1 = ((q64[:, None, :] - b64[ids1]) ** 2).sum(-1)
+    e3 = np.abs(d3 - true3) / true3
+    e1 = np.abs(d1 - true1) / true1
+    assert e3.max() < RTOL, e3.max()
+    assert e3.max() < e1.max()  # the split buys real accuracy
+
+
+def test_properties_full_size(gpu_vsb):
+    """BASELINE configs[1] shape (1M x 128): size-independent properties instead of a full oracle run —
+    sorted output, self-query returns itself at distance ~0, FFMA and tensor-core paths agree, and the answer
+    is independent of how the base is sharded (merge of two half-indexes == one index)."""
+    import torch
+
+    vsb = gpu_vsb
+    n, nq, k = 1_000_000, 512, 10
+    dev = torch.device("cuda:0")
+    base_d = torch.empty((n, 128), dtype=torch.float32, device=dev)
+    vsb.synth_fill_dev(base_d.data_ptr(), 0, n, 128, "cont", 4242)
+    torch.cuda.synchronize()
+    # device generator == numpy generator
+    assert np.array_equal(base_d[123456:123456 + 64].cpu().numpy(), vsb.synth.rows("cont", 4242, 123456, 64))
+    qry = vsb.synth.rows("cont", 4242, 500_000, nq).copy()  # queries are base rows 500000..500511
+    qry[nq // 2:] += 0.25
+    idx = vsb.ExactIndex(base_d.data_ptr(), n=n)
+    try:
+        ids, d = idx.search(qry, k, vsb.PREC_3XTF32)
+        assert (np.diff(d, axis=1) >= 0).all()
+        half = nq // 2
+        assert np.array_equal(ids[:half, 0], np.arange(500_000, 500_000 + half))
+        qn = (qry[:half].astype(np.float64) ** 2).sum(1)
+        assert (np.abs(d[:half, 0]) <= 2e-5 * qn).all()  # cancellation of ~1e6-sized terms
+        ids_f, d_f = idx.search(qry[:16], k, vsb.PREC_FFMA)
+        assert np.allclose(d_f[:, 1:], d[:16, 1:], rtol=RTOL)
+        assert (ids_f[:, 1:] == ids[:16, 1:]).mean() > 0.99
+    finally:
+        idx.close()
+    # sharding invariance
+    h = n // 2
+    a = vsb.ExactIndex(base_d.data_ptr(), n=h, id_base=0)
+    b = vsb.ExactIndex(base_d.data_ptr() + h * 128 * 4, n=n - h, id_base=h)
+    try:
+        ia, da = a.search(qry, k, vsb.PREC_3XTF32)
+        ib, db = b.search(qry, k, vsb.PREC_3XTF32)
+    finally:
+        a.close()
+        b.close()
+    gi = torch.from_numpy(np.stack([ia, ib])).to(dev)
+    gd = torch.from_numpy(np.stack([da, db])).to(dev)
+    oi = torch.empty((nq, k), dtype=torch.int32, device=dev)
+    od = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    vsb.merge_topk_dev(gi.data_ptr(), gd.data_ptr(), 2, nq, k, True, oi.data_ptr(), od.data_ptr(),
+                       torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(oi.cpu().numpy(), ids) and np.array_equal(od.cpu().numpy(), d)
+
+
+def test_argument_errors(gpu_vsb):
+    vsb = gpu_vsb
+    base = vsb.synth.make("sift", 1, 100)
+    idx = vsb.ExactIndex(base)
+    try:
+        with pytest.raises(vsb.VsbError):
+            idx.search(base[:2], 101)  # k > n is UB in the reference (cpu_baseline.cpp:129-131): rejected here
+        with pytest.raises(vsb.VsbError):
+            idx.search(base[:2], 0)
+        ids, d = idx.search(base[:0], 5)  # empty batch
+        assert ids.shape == (0, 5)
+    finally:
+        idx.close()

@@ -1,0 +1,54 @@
+"""Helpers shared by the parity tests."""
+import glob
+import os
+
+import numpy as np
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+RTOL = 1e-5  # BASELINE.json north_star: fp32 distances within 1e-5 relative; ids bit-exact except ties within 1e-5
+
+
+def golden_cases(prefix="hp1_"):
+    return sorted(glob.glob(os.path.join(GOLDEN_DIR, prefix + "*.npz")))
+
+
+def load_golden(path, synth):
+    g = np.load(path)
+    law = str(g["law"])
+    base = synth.make(law, int(g["base_seed"]), int(g["nb"]))
+    qry = synth.make(law, int(g["query_seed"]), int(g["nq"]))
+    return g, law, base, qry, int(g["k"])
+
+
+def assert_topk_matches(ids, keys, ref_ids, ref_keys, recomputed, *, exact: bool, what=""):
+    """Tie-aware comparison.
+      1. key vectors equal position by position (bit-exact when `exact`, else within RTOL);
+      2. every returned id's key, recomputed by the oracle, equals the reported key;
+      3. ids identical wherever the reference key is not part of a tie group (a neighbour within RTOL in the same
+         row) and is not the last position (whose tie partner may be the excluded (k+1)-th element).
+    """
+    ids, ref_ids = np.asarray(ids), np.asarray(ref_ids)
+    keys, ref_keys, recomputed = (np.asarray(x, dtype=np.float32) for x in (keys, ref_keys, recomputed))
+    assert ids.shape == ref_ids.shape, what
+    if exact:
+        assert np.array_equal(keys, ref_keys), f"{what}: keys not bit-exact (max abs diff {np.abs(keys - ref_keys).max()})"
+        assert np.array_equal(recomputed, keys), f"{what}: reported key != oracle key of the returned id"
+    else:
+        assert np.allclose(keys, ref_keys, rtol=RTOL, atol=0), f"{what}: keys differ beyond {RTOL}"
+        assert np.allclose(recomputed, keys, rtol=RTOL, atol=0), f"{what}: reported key != oracle key of the returned id"
+    mism = ids != ref_ids
+    if not mism.any():
+        return
+    tol = RTOL * np.abs(ref_keys) if not exact else np.zeros_like(ref_keys)
+    k = ids.shape[1]
+    tied = np.zeros_like(mism)
+    if k > 1:
+        close_next = np.abs(ref_keys[:, 1:] - ref_keys[:, :-1]) <= np.maximum(tol[:, 1:], tol[:, :-1])
+        tied[:, 1:] |= close_next
+        tied[:, :-1] |= close_next
+    tied[:, -1] = True
+    bad = mism & ~tied
+    assert not bad.any(), f"{what}: {int(bad.sum())} id mismatches outside tie groups, first at {np.argwhere(bad)[0]}"
+    # a mismatching id must not appear twice in a row
+    for r in np.unique(np.argwhere(mism)[:, 0]):
+        assert len(set(ids[r].tolist())) == k, f"{what}: duplicate ids in row {r}"
