@@ -1,0 +1,363 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark: QPS of exact L2 top-10 on a 1M x 128 fp32 base (BASELINE.json configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one pass of the hot path over one batch: 10 000 queries against the whole base, top-10,
+fp32-faithful (3xTF32 tcgen05 kernel + exact fp32 refine of the candidates).
+N > 1 (torchrun, one rank per GPU): base rows sharded across ranks, queries replicated, per-rank local top-k,
+one NCCL all-gather of [nq x k] (ids, dists) + merge kernel — strong scaling on the fixed 1M x 128 problem.
+
+Prints ONE JSON line (rank 0):
+  value        whole-job QPS, queries already resident in HBM when the timed region starts
+  e2e          the same through the host-buffer C-ABI call (H2D of queries + D2H of results inside the timing)
+  roofline     dominant kernel (fused distance+top-k) timed live with CUDA events on its launching stream
+  cpu_baseline the UNMODIFIED reference (oracle/_ref) timed on this box's host cores on a bounded query sample
+--impl reference times that reference as the main metric (rank 0 only).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_BASE = 1_000_000
+N_QUERY = 10_000
+DIM = 128
+TOPK = 10
+LAW = "cont"  # continuous-valued SIFT-shaped synthetic data: exercises the real 3xTF32 split (lo != 0)
+BASE_SEED, QUERY_SEED = 2025, 2026
+METRIC = "QPS exact top-10 on 1Mx128"
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        busy = [s for s, p in zip(sm, pw) if p >= 0.5 * max(pw)] or sm
+        return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16": d["bf16_tflops"], "bf16_sustained": d.get("bf16_tflops_sustained"),
+                "src": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16": 1590.0, "bf16_sustained": 1400.0, "src": "fallback"}
+
+
+# ----------------------------------------------------------------------------------------------------------
+# reference arm: the UNMODIFIED cpu_baseline.cpp (oracle/_ref/ref_driver -> run_benchmark), bounded sample
+# ----------------------------------------------------------------------------------------------------------
+def reference_run(vsb, n_queries, repeats, threads, keep_dir=None):
+    """Times run_benchmark() (its own timed span: the query loop, cpu_baseline.cpp:220-257) on the bench base
+    and `n_queries` of the bench queries. Returns list of QPS values (one per repeat)."""
+    from oracle import oracle
+
+    if not oracle.have_ref():
+        return None
+    td = keep_dir or tempfile.mkdtemp(prefix="vsb_ref_")
+    bf, qf, rt = (os.path.join(td, x) for x in ("base.fvecs", "query.fvecs", "results.txt"))
+    if not os.path.exists(bf):
+        out = np.empty((N_BASE, DIM + 1), dtype=np.float32)
+        out[:, 0] = np.array([DIM], dtype=np.int32).view(np.float32)[0]
+        for r0 in range(0, N_BASE, 1 << 16):
+            n = min(1 << 16, N_BASE - r0)
+            out[r0:r0 + n, 1:] = vsb.synth.rows(LAW, BASE_SEED, r0, n)
+        out.tofile(bf)
+        del out
+    vsb.synth.write_fvecs(qf, vsb.synth.rows(LAW, QUERY_SEED, 0, n_queries))
+    res = []
+    for _ in range(repeats):
+        r = oracle.ref_bench(bf, qf, TOPK, rt, threads=threads)
+        res.append(r["qps"])
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="3xtf32", choices=["3xtf32", "auto", "1xtf32", "ffma"])
+    ap.add_argument("--nq", type=int, default=N_QUERY)
+    ap.add_argument("--cpu-sample", type=int, default=128, help="queries timed on the CPU reference (bounded sample)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = env_int("RANK", 0)
+    world = env_int("WORLD_SIZE", 1)
+    local_rank = env_int("LOCAL_RANK", 0)
+    ncores = os.cpu_count() or 1
+
+    import vsb200_loader
+    vsb = vsb200_loader.load()
+
+    # ------------------------------------------------------------------ reference arm
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        sample = min(args.cpu_sample, args.nq)
+        qps = reference_run(vsb, sample, args.warmup + args.steps, ncores)
+        if qps is None:
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ref_driver was not built"}))
+            return 0
+        qps = qps[args.warmup:]
+        v = float(np.mean(qps))
+        line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "queries/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sample / v,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic",
+                "config": {"workload": f"{N_BASE}x{DIM} fp32 base, exact L2 top-{TOPK}, law={LAW}",
+                           "queries_per_step": sample},
+                "cpu_baseline": {"value": v, "unit": "queries/s", "cores": ncores, "kind": "reference",
+                                 "sample": f"{sample} of the {args.nq} bench queries per step against the full "
+                                           f"{N_BASE}x{DIM} base; the reference's own timed span "
+                                           f"(cpu_baseline.cpp:220-257)"},
+                "e2e": {"value": v, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ our arm
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available() or vsb.device_count() < 1:
+        raise SystemExit("bench.py needs a CUDA device: libvsb200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    prec = {"3xtf32": vsb.PREC_3XTF32, "auto": vsb.PREC_AUTO, "1xtf32": vsb.PREC_TF32_1X, "ffma": vsb.PREC_FFMA}[args.precision]
+    nq, k = args.nq, TOPK
+
+    # base shard of this rank, generated on the device (bit-identical to the numpy generator)
+    r0 = (N_BASE * rank) // world
+    r1 = (N_BASE * (rank + 1)) // world
+    base_d = torch.empty((r1 - r0, DIM), dtype=torch.float32, device=dev)
+    vsb.synth_fill_dev(base_d.data_ptr(), r0, r1 - r0, DIM, LAW, BASE_SEED)
+    torch.cuda.synchronize()
+    index = vsb.ExactIndex(base_d.data_ptr(), device=local_rank, id_base=r0, n=r1 - r0)
+    index.set_profile(True)
+
+    q_host = torch.from_numpy(vsb.synth.make(LAW, QUERY_SEED, nq)).pin_memory()
+    q_dev = q_host.to(dev)
+    ids_loc = torch.empty((nq, k), dtype=torch.int32, device=dev)
+    d_loc = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    ids_all = torch.empty((world, nq, k), dtype=torch.int32, device=dev)
+    d_all = torch.empty((world, nq, k), dtype=torch.float32, device=dev)
+    ids_out = torch.empty((nq, k), dtype=torch.int32, device=dev)
+    d_out = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    ids_h = torch.empty((nq, k), dtype=torch.int32).pin_memory()
+    d_h = torch.empty((nq, k), dtype=torch.float32).pin_memory()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    stream = torch.cuda.current_stream()
+    sptr = stream.cuda_stream
+
+    def device_step(q_ptr):
+        index.search_dev(q_ptr, nq, k, prec, ids_loc.data_ptr(), d_loc.data_ptr(), sptr)
+        if world > 1:
+            dist.all_gather_into_tensor(ids_all, ids_loc)
+            dist.all_gather_into_tensor(d_all, d_loc)
+            vsb.merge_topk_dev(ids_all.data_ptr(), d_all.data_ptr(), world, nq, k, True, ids_out.data_ptr(),
+                               d_out.data_ptr(), sptr)
+            return ids_out, d_out
+        return ids_loc, d_loc
+
+    q_stage = torch.empty_like(q_dev)
+
+    def e2e_step():
+        if world == 1:
+            # the reference-facing C-ABI call with HOST buffers: H2D + search + D2H inside
+            index.search(q_host.numpy(), k, prec, out_ids=ids_h.numpy(), out_dists=d_h.numpy())
+        else:
+            q_stage.copy_(q_host, non_blocking=True)
+            oi, od = device_step(q_stage.data_ptr())
+            if rank == 0:
+                ids_h.copy_(oi, non_blocking=True)
+                d_h.copy_(od, non_blocking=True)
+            stream.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, use_events=True):
+        """per-step timing with an L2 flush between steps; returns list of ms"""
+        out = []
+        for _ in range(steps):
+            flush.fill_(1)
+            barrier()
+            if use_events:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                fn()
+                e1.record(stream)
+                e1.synchronize()
+                out.append(e0.elapsed_time(e1))
+            else:
+                t0 = time.perf_counter()
+                fn()
+                torch.cuda.synchronize()
+                out.append(1e3 * (time.perf_counter() - t0))
+        return out
+
+    for _ in range(args.warmup):
+        device_step(q_dev.data_ptr())
+        e2e_step()
+    barrier()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    kernel_ms = []
+
+    def dev_fn():
+        device_step(q_dev.data_ptr())
+
+    t_dev = []
+    for _ in range(args.steps):
+        t_dev += timed(dev_fn, 1)
+        kernel_ms.append(index.last_kernel_ms())
+    launches, prec_used = index.last_launches()
+    t_e2e = timed(e2e_step, args.steps, use_events=False)  # wall clock: the host-buffer call blocks the host
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    ms_dev = max_over_ranks(float(np.sum(t_dev))) / args.steps
+    ms_e2e = max_over_ranks(float(np.sum(t_e2e))) / args.steps
+    ms_kernel = max_over_ranks(float(np.mean(kernel_ms)))
+
+    # sanity: the timed path produced a plausible answer (ascending distances, ids in range)
+    oi, od = device_step(q_dev.data_ptr())
+    torch.cuda.synchronize()
+    assert bool((od[:, 1:] >= od[:, :-1]).all()) and int(oi.min()) >= 0 and int(oi.max()) < N_BASE
+
+    if rank == 0:
+        pk = peaks()
+        split = 3 if prec_used == vsb.PREC_3XTF32 else 1
+        n_local = (N_BASE + world - 1) // world
+        if prec_used == vsb.PREC_FFMA:
+            passes = (nq + 7) // 8
+            alg_bytes = n_local * (DIM * 4 + 4)  # first launch: one pass over the shard
+            roof = {"bound": "hbm", "achieved": alg_bytes / (ms_kernel * 1e-3) / 1e9, "peak": pk["hbm_gbs"],
+                    "unit": "GB/s", "traffic": None, "kernel": "exact_stream_kernel (first of %d passes)" % passes}
+        else:
+            # tensor work issued by the fused kernel for this rank's shard: 2*Q*N*128 flop per TF32 product, 3
+            # products for the fp32-faithful split (DESIGN.md "Roofline")
+            flops = 2.0 * nq * n_local * DIM * split
+            tf32_peak = pk["bf16"] / 2.0
+            roof = {"bound": "tensor", "achieved": flops / (ms_kernel * 1e-3) / 1e12, "peak": tf32_peak,
+                    "unit": "TFLOP/s", "traffic": None, "kernel": "exact_tc_kernel",
+                    "tf32_products": split, "algorithmic_fp32_tflops": 2.0 * nq * n_local * DIM / (ms_kernel * 1e-3) / 1e12,
+                    "peak_note": f"TF32 dense = MEASURED_PEAKS bf16 burst / 2 ({pk['src']})"}
+        roof["frac"] = roof["achieved"] / roof["peak"]
+        roof["kernel_ms"] = ms_kernel
+        line = {
+            "metric": METRIC, "value": nq / (ms_dev * 1e-3), "unit": "queries/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{N_BASE}x{DIM} fp32 base, {nq} queries/step, exact L2 top-{k}, law={LAW}",
+                       "precision": vsb.PREC_NAMES[prec_used], "base_rows_per_gpu": n_local,
+                       "parallelism": f"base rows sharded x{world}, queries replicated, all-gather + merge" if world > 1 else "single GPU",
+                       "cache": "L2 flushed (256 MB write) between timed steps; operands (0.5-1 GB) exceed the 126 MB L2"},
+            "e2e": {"value": nq / (ms_e2e * 1e-3), "unit": "queries/s", "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": int(q_host.numel() * 4) * world,
+                    "d2h_bytes_per_step": int(nq * k * 8),
+                    "api": "vs_exact_search_f32 (host buffers)" if world == 1 else "H2D + vs_exact_search_dev + NCCL all-gather + vs_merge_topk_dev + D2H"},
+            "gpu_launches": int(launches + (1 if world > 1 else 0)) * args.steps,
+            "roofline": roof,
+            "clocks": clocks,
+        }
+        if not args.no_cpu and world == 1:
+            t0 = time.time()
+            sample = min(args.cpu_sample, nq)
+            qps = reference_run(vsb, sample, 1, ncores)
+            if qps is not None:
+                line["cpu_baseline"] = {"value": float(qps[0]), "unit": "queries/s", "cores": ncores, "kind": "reference",
+                                        "sample": f"unmodified cpu_baseline.cpp run_benchmark(): {sample} of the {nq} bench "
+                                                  f"queries against the full {N_BASE}x{DIM} base, its own timed span "
+                                                  f"(query loop only); wall {time.time() - t0:.0f}s incl. file I/O"}
+            else:
+                line["cpu_baseline"] = {"value": None, "unit": "queries/s", "cores": ncores, "kind": "reference",
+                                        "sample": "oracle/_ref/ref_driver missing"}
+        print(json.dumps(line))
+    index.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

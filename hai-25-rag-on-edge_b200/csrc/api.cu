@@ -232,7 +232,9 @@ static int exact_search_core(vs_exact* h, const float* q_dev, int64_t nq, int k,
 
     VSB_TRY(h->qnorm.reserve(sizeof(float) * (size_t)nq));
     const int passes = (k + kMaxRegK - 1) / kMaxRegK;
-    const int ktop = passes == 1 ? round_up_ktop(k) : kMaxRegK;
+    // single pass: keep a couple of spare candidates beyond k so that the exact refine can repair a k-th/k+1-th
+    // swap caused by the tensor-core rounding bias
+    const int ktop = passes == 1 ? round_up_ktop(std::min(k + 2, kMaxRegK)) : kMaxRegK;
     if (passes > 1) {
         VSB_TRY(h->lbk.reserve(sizeof(float) * (size_t)nq));
         VSB_TRY(h->lbi.reserve(sizeof(int32_t) * (size_t)nq));
@@ -283,10 +285,15 @@ static int exact_search_core(vs_exact* h, const float* q_dev, int64_t nq, int k,
                 h->ev_valid = true;
             }
             VSB_TRY(launch_merge_lists(h->part_key.as<float>(), h->part_id.as<int32_t>(), plan.n_splits, nq, ktop,
-                                       passes == 1 ? k : kk, h->id_base, 0, 0, out_dists, out_ids, k, pass * kMaxRegK,
-                                       passes > 1 ? h->lbk.as<float>() : nullptr,
-                                       passes > 1 ? h->lbi.as<int32_t>() : nullptr, st));
+                                       passes == 1 ? ktop : kk, passes == 1 ? k : kk, h->id_base, 0, 0, out_dists,
+                                       out_ids, k, pass * kMaxRegK, passes > 1 ? h->lbk.as<float>() : nullptr,
+                                       passes > 1 ? h->lbi.as<int32_t>() : nullptr, h->d_base, h->d_norm, q_dev,
+                                       h->qnorm.as<float>(), st));
             h->last_launches += 2;
+        }
+        if (passes > 1) {
+            VSB_TRY(launch_sort_rows(out_dists, out_ids, nq, k, st));
+            h->last_launches++;
         }
         return VS_OK;
     }
@@ -313,11 +320,17 @@ static int exact_search_core(vs_exact* h, const float* q_dev, int64_t nq, int k,
                 h->ev_valid = true;
             }
             VSB_TRY(launch_merge_lists(h->part_key.as<float>(), h->part_id.as<int32_t>(), n_ctas, g, ktop,
-                                       passes == 1 ? k : kk, h->id_base, 0, 0, out_dists + q0 * k, out_ids + q0 * k, k,
-                                       pass * kMaxRegK, passes > 1 ? h->lbk.as<float>() + q0 : nullptr,
-                                       passes > 1 ? h->lbi.as<int32_t>() + q0 : nullptr, st));
+                                       passes == 1 ? ktop : kk, passes == 1 ? k : kk, h->id_base, 0, 0,
+                                       out_dists + q0 * k, out_ids + q0 * k, k, pass * kMaxRegK,
+                                       passes > 1 ? h->lbk.as<float>() + q0 : nullptr,
+                                       passes > 1 ? h->lbi.as<int32_t>() + q0 : nullptr, h->d_base, h->d_norm,
+                                       q_dev + q0 * dim, h->qnorm.as<float>() + q0, st));
             h->last_launches += 2;
         }
+    }
+    if (passes > 1) {
+        VSB_TRY(launch_sort_rows(out_dists, out_ids, nq, k, st));
+        h->last_launches++;
     }
     return VS_OK;
 }
@@ -413,8 +426,9 @@ int vs_merge_topk_dev(const int32_t* ids_dev, const float* keys_dev, int n_shard
     if (!ids_dev || !keys_dev || !out_ids_dev || !out_keys_dev) return fail(VS_ERR_INVALID, "NULL buffer");
     if (n_shards <= 0 || nq < 0 || k <= 0) return fail(VS_ERR_INVALID, "bad sizes");
     if (k > kMaxRegK) return fail(VS_ERR_UNSUPPORTED, "merge of k > 32 lists is not implemented");
-    return launch_merge_lists(keys_dev, ids_dev, n_shards, nq, k, k, 0, smallest ? 0 : 1, smallest ? 0 : 1, out_keys_dev,
-                              out_ids_dev, k, 0, nullptr, nullptr, (cudaStream_t)stream);
+    return launch_merge_lists(keys_dev, ids_dev, n_shards, nq, k, k, k, 0, smallest ? 0 : 1, smallest ? 0 : 1,
+                              out_keys_dev, out_ids_dev, k, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                              (cudaStream_t)stream);
 }
 
 int vs_synth_fill_dev(float* out_dev, int64_t row0, int64_t nrows, int dim, int law, uint64_t seed, uint64_t centre_seed,

@@ -94,17 +94,59 @@ int launch_fill_f32(float* p, int64_t n, float v, cudaStream_t st) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// K3: merge sorted partial lists.  One warp per query; lane j folds lists j, j+32, ... into a register
-// list, then the warp pops the global minimum k times (warp_merge_lists).
+// K3: merge sorted partial lists (+ optional exact fp32 refine).  One warp per query; lane j folds lists
+// j, j+32, ... into a register list, then the warp pops the global minimum `nsel` times.
+//
+// Refine (rf.base != nullptr): the tensor-core accumulator does not round to nearest (measured on B200: a
+// systematic ~2e-6 relative truncation bias of the dot product on continuous data), so the fused kernel's keys
+// are treated as a candidate ranking; the nsel selected candidates get their distance recomputed in plain fp32
+// — 16 accumulators by (d mod 16) with FMA, pairwise lane tree, then (qn + bn) - 2*dot (cpu_baseline.cpp:241)
+// — and are re-sorted by (distance, id).  Reported distances are then fp32-faithful regardless of which
+// kernel generated the candidates.
 // ------------------------------------------------------------------------------------------------
+struct RefineArgs {
+    const float* base;   // [n x 128] fp32, or nullptr = no refine
+    const float* bnorm;
+    const float* q;      // [nq x 128]
+    const float* qnorm;
+};
+
+__device__ __forceinline__ float dot16_128(const float* __restrict__ a, const float* __restrict__ b) {
+    float lane[16];
+#pragma unroll
+    for (int l = 0; l < 16; ++l) lane[l] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 128; i += 16) {
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            const float4 x = __ldg(reinterpret_cast<const float4*>(a + i) + v);
+            const float4 y = __ldg(reinterpret_cast<const float4*>(b + i) + v);
+            lane[4 * v + 0] = fmaf(x.x, y.x, lane[4 * v + 0]);
+            lane[4 * v + 1] = fmaf(x.y, y.y, lane[4 * v + 1]);
+            lane[4 * v + 2] = fmaf(x.z, y.z, lane[4 * v + 2]);
+            lane[4 * v + 3] = fmaf(x.w, y.w, lane[4 * v + 3]);
+        }
+    }
+#pragma unroll
+    for (int w = 8; w >= 1; w >>= 1)
+#pragma unroll
+        for (int l = 0; l < w; ++l) lane[l] = __fadd_rn(lane[l], lane[l + w]);
+    return lane[0];
+}
+
 template <int KTOP>
 __global__ void __launch_bounds__(128) merge_lists_kernel(const float* __restrict__ part_key,
                                                           const int32_t* __restrict__ part_id, int n_lists, int64_t nq,
-                                                          int list_len, int k, int64_t id_base, int neg_in, int neg_out, float* __restrict__ out_key,
+                                                          int list_len, int nsel, int k, int64_t id_base, int neg_in,
+                                                          int neg_out, float* __restrict__ out_key,
                                                           int32_t* __restrict__ out_id, int out_stride, int out_off,
-                                                          float* __restrict__ lb_key_out, int32_t* __restrict__ lb_id_out) {
+                                                          float* __restrict__ lb_key_out, int32_t* __restrict__ lb_id_out,
+                                                          RefineArgs rf) {
+    __shared__ float s_key[4][32];
+    __shared__ int32_t s_id[4][32];
     const int lane = threadIdx.x & 31;
-    const int64_t q = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int wib = threadIdx.x >> 5;
+    const int64_t q = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
     if (q >= nq) return;
     RegTopK<KTOP> L;
     L.init();
@@ -135,28 +177,28 @@ __global__ void __launch_bounds__(128) merge_lists_kernel(const float* __restric
     const float INF = __int_as_float(0x7f800000);
     float lastk = INF;
     int32_t lasti = -1;
-    for (int r = 0; r < k; ++r) {
+    for (int r = 0; r < nsel; ++r) {
         float hk = L.key[0];
-        int32_t hi = L.id[0];
+        int32_t hid = L.id[0];
         int src = lane;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             const float ok = __shfl_xor_sync(0xffffffffu, hk, o);
-            const int32_t oi = __shfl_xor_sync(0xffffffffu, hi, o);
+            const int32_t oi = __shfl_xor_sync(0xffffffffu, hid, o);
             const int os = __shfl_xor_sync(0xffffffffu, src, o);
-            if (pair_less(ok, oi, hk, hi)) {
+            if (pair_less(ok, oi, hk, hid)) {
                 hk = ok;
-                hi = oi;
+                hid = oi;
                 src = os;
             }
         }
         if (lane == 0) {
-            out_key[q * out_stride + out_off + r] = hi >= 0 ? (neg_out ? -hk : hk) : (neg_out ? -INF : INF);
-            out_id[q * out_stride + out_off + r] = hi >= 0 ? (int32_t)(hi + id_base) : -1;
+            s_key[wib][r] = hid >= 0 ? hk : INF;
+            s_id[wib][r] = hid;
         }
         lastk = hk;
-        lasti = hi;
-        if (src == lane && hi >= 0) {
+        lasti = hid;
+        if (src == lane && hid >= 0) {
 #pragma unroll
             for (int i = 0; i + 1 < KTOP; ++i) {
                 L.key[i] = L.key[i + 1];
@@ -166,23 +208,57 @@ __global__ void __launch_bounds__(128) merge_lists_kernel(const float* __restric
             L.id[KTOP - 1] = -1;
         }
     }
-    if (lb_key_out && lane == 0) {  // exclusive lower bound for the next pass (local ids, un-negated search keys)
+    if (lb_key_out && lane == 0) {  // exclusive lower bound for the next pass (local ids, candidate-ranking keys)
         lb_key_out[q] = lasti >= 0 ? lastk : INF;
         lb_id_out[q] = lasti >= 0 ? lasti : 0x7fffffff;
     }
+    __syncwarp();
+    // ---- this lane's candidate (nsel <= 32), refined when requested
+    float myk = INF;
+    int32_t myid = -1;
+    if (lane < nsel) {
+        myk = s_key[wib][lane];
+        myid = s_id[wib][lane];
+        if (rf.base && myid >= 0) {
+            const float dot = dot16_128(rf.q + (size_t)q * 128, rf.base + (size_t)myid * 128);
+            myk = fmaf(-2.0f, dot, __fadd_rn(__ldg(rf.qnorm + q), __ldg(rf.bnorm + myid)));
+        }
+    }
+    // rank by counting (ids are unique; padding sorts last and is never written)
+    int rank = 0;
+#pragma unroll 1
+    for (int j = 0; j < nsel; ++j) {
+        const float ok = __shfl_sync(0xffffffffu, myk, j);
+        const int32_t oi = __shfl_sync(0xffffffffu, myid, j);
+        rank += (oi >= 0 && pair_less(ok, oi, myk, myid)) ? 1 : 0;
+    }
+    const int n_valid = __popc(__ballot_sync(0xffffffffu, myid >= 0));
+    float* ok_row = out_key + q * out_stride + out_off;
+    int32_t* oi_row = out_id + q * out_stride + out_off;
+    if (myid >= 0 && rank < k) {
+        ok_row[rank] = neg_out ? -myk : myk;
+        oi_row[rank] = (int32_t)(myid + id_base);
+    }
+    for (int r = n_valid + lane; r < k; r += 32) {
+        ok_row[r] = neg_out ? -INF : INF;
+        oi_row[r] = -1;
+    }
 }
 
-int launch_merge_lists(const float* part_key, const int32_t* part_id, int n_lists, int64_t nq, int list_len, int k,
-                       int64_t id_base, int neg_in, int neg_out, float* out_key, int32_t* out_id, int out_stride, int out_off,
-                       float* lb_key_out, int32_t* lb_id_out, cudaStream_t st) {
+int launch_merge_lists(const float* part_key, const int32_t* part_id, int n_lists, int64_t nq, int list_len, int nsel,
+                       int k, int64_t id_base, int neg_in, int neg_out, float* out_key, int32_t* out_id, int out_stride,
+                       int out_off, float* lb_key_out, int32_t* lb_id_out, const float* rf_base, const float* rf_bnorm,
+                       const float* rf_q, const float* rf_qnorm, cudaStream_t st) {
     if (nq <= 0) return VS_OK;
+    if (nsel > list_len || k > nsel || nsel > 32) return fail(VS_ERR_INVALID, "merge: need k <= nsel <= list length <= 32");
     const unsigned blocks = (unsigned)ceil_div64(nq, 4);
-#define VSB_MERGE_CASE(KT)                                                                                          \
-    case KT:                                                                                                        \
-        merge_lists_kernel<KT><<<blocks, 128, 0, st>>>(part_key, part_id, n_lists, nq, list_len, k, id_base, neg_in, neg_out, out_key, \
-                                                       out_id, out_stride, out_off, lb_key_out, lb_id_out);         \
+    RefineArgs rf{rf_base, rf_bnorm, rf_q, rf_qnorm};
+#define VSB_MERGE_CASE(KT)                                                                                            \
+    case KT:                                                                                                          \
+        merge_lists_kernel<KT><<<blocks, 128, 0, st>>>(part_key, part_id, n_lists, nq, list_len, nsel, k, id_base,    \
+                                                       neg_in, neg_out, out_key, out_id, out_stride, out_off,         \
+                                                       lb_key_out, lb_id_out, rf);                                    \
         break;
-    if (k > list_len) return fail(VS_ERR_INVALID, "merge: k > list length");
     switch (round_up_ktop(list_len)) {
         VSB_MERGE_CASE(1)
         VSB_MERGE_CASE(5)
@@ -193,6 +269,41 @@ int launch_merge_lists(const float* part_key, const int32_t* part_id, int n_list
             return fail(VS_ERR_INVALID, "merge: unsupported list size");
     }
 #undef VSB_MERGE_CASE
+    VSB_CUDA(cudaGetLastError());
+    return VS_OK;
+}
+
+// Final (key, id) sort of each row of out[nq][k] for multi-pass results (k > 32): passes are ordered by the
+// candidate ranking, refined keys may reorder neighbours across a pass boundary.  One warp per row.
+__global__ void __launch_bounds__(128) sort_rows_kernel(float* __restrict__ key, int32_t* __restrict__ id, int64_t nq, int k) {
+    extern __shared__ uint8_t sm[];
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    const int64_t q = (int64_t)blockIdx.x * 4 + wib;
+    if (q >= nq) return;
+    float* sk = reinterpret_cast<float*>(sm) + (size_t)wib * k;
+    int32_t* si = reinterpret_cast<int32_t*>(sm + (size_t)4 * k * sizeof(float)) + (size_t)wib * k;
+    for (int c = lane; c < k; c += 32) {
+        sk[c] = key[q * k + c];
+        si[c] = id[q * k + c];
+    }
+    __syncwarp();
+    for (int c = lane; c < k; c += 32) {
+        const float mk = sk[c];
+        const int32_t mi = si[c];
+        if (mi < 0) continue;  // padding already sits at the end
+        int rank = 0;
+        for (int j = 0; j < k; ++j) rank += (si[j] >= 0 && pair_less(sk[j], si[j], mk, mi)) ? 1 : 0;
+        key[q * k + rank] = mk;
+        id[q * k + rank] = mi;
+    }
+}
+
+int launch_sort_rows(float* key, int32_t* id, int64_t nq, int k, cudaStream_t st) {
+    if (nq <= 0) return VS_OK;
+    const size_t smem = (size_t)4 * k * 8;
+    if (smem > 48 * 1024) return fail(VS_ERR_UNSUPPORTED, "k too large for the final sort");
+    sort_rows_kernel<<<(unsigned)ceil_div64(nq, 4), 128, smem, st>>>(key, id, nq, k);
     VSB_CUDA(cudaGetLastError());
     return VS_OK;
 }

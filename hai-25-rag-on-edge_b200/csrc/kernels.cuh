@@ -33,14 +33,17 @@ int launch_exact_tc(const CUtensorMap& tmA_hi, const CUtensorMap& tmA_lo, const 
                     int32_t* part_id, cudaStream_t st);
 int tc_set_attributes();  // opt-in to > 48 KB dynamic shared memory for every instantiation
 
-// merge.cu --------------------------------------------------------------------------------------
-// Merges n_lists sorted lists of `list_len` (<= 32) entries per query (layout [list][nq][list_len]) into out[nq][k],
-// canonical (key asc, id asc); adds id_base to valid ids; neg_in / neg_out flip the key sign on load / store
-// (descending scores are handled as ascending negated keys).  Optionally appends to an existing result prefix (multi-pass k > 32): out_off entries
-// per query are already final.
-int launch_merge_lists(const float* part_key, const int32_t* part_id, int n_lists, int64_t nq, int list_len, int k,
-                       int64_t id_base, int neg_in, int neg_out, float* out_key, int32_t* out_id, int out_stride, int out_off,
-                       float* lb_key_out, int32_t* lb_id_out, cudaStream_t st);
+// kernels.cu (K3) ----------------------------------------------------------------------------
+// Merges n_lists sorted lists of `list_len` (<= 32) entries per query (layout [list][nq][list_len]): selects the
+// `nsel` best by the candidate keys, optionally recomputes their distances in exact fp32 (rf_* non-null; local
+// ids), orders them by (key asc, id asc) and writes the first k to out[q*out_stride + out_off ...]; adds id_base
+// to valid ids; neg_in / neg_out flip the key sign on load / store (descending scores are handled as ascending
+// negated keys).  lb_*_out receive the last selected candidate (exclusive lower bound of the next pass, k > 32).
+int launch_merge_lists(const float* part_key, const int32_t* part_id, int n_lists, int64_t nq, int list_len, int nsel,
+                       int k, int64_t id_base, int neg_in, int neg_out, float* out_key, int32_t* out_id, int out_stride,
+                       int out_off, float* lb_key_out, int32_t* lb_id_out, const float* rf_base, const float* rf_bnorm,
+                       const float* rf_q, const float* rf_qnorm, cudaStream_t st);
+int launch_sort_rows(float* key, int32_t* id, int64_t nq, int k, cudaStream_t st);
 
 // synth.cu --------------------------------------------------------------------------------------
 int launch_synth(float* out, int64_t row0, int64_t nrows, int dim, int law, uint64_t seed, uint64_t centre_seed,
