@@ -215,8 +215,11 @@ def main():
     ids_h = torch.empty((nq, k), dtype=torch.int32).pin_memory()
     d_h = torch.empty((nq, k), dtype=torch.float32).pin_memory()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
-    stream = torch.cuda.current_stream()
+    # a non-default stream: its handle is what the C ABI launches on and what the CUDA events are recorded on
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
     sptr = stream.cuda_stream
+    assert sptr != 0
 
     def device_step(q_ptr):
         index.search_dev(q_ptr, nq, k, prec, ids_loc.data_ptr(), d_loc.data_ptr(), sptr)

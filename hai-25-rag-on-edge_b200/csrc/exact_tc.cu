@@ -2,6 +2,7 @@
 #include "exact_tc.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "kernels.cuh"
 
@@ -74,6 +75,10 @@ int launch_exact_tc(const CUtensorMap& tmA_hi, const CUtensorMap& tmA_lo, const 
     p.n_mtiles = plan.n_mtiles;
     p.n_splits = plan.n_splits;
     p.tiles_per_split = plan.tiles_per_split;
+    {
+        const char* e = getenv("VSB_TC_DBG");
+        p.dbg = e ? atoi(e) : 0;
+    }
     if (lb_key && ktop != 32) return fail(VS_ERR_INVALID, "tc: lower bound needs the 32-entry list");
 #define VSB_TC_LAUNCH(KT, S3, LB)                                                                               \
     exact_tc_kernel<KT, S3, LB><<<plan.grid, TC_THREADS, TcSmem<S3>::TOTAL, st>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, p)

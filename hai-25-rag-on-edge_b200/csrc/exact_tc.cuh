@@ -50,6 +50,7 @@ struct TcParams {
     int n_mtiles;        // ceil(nq / 128)
     int n_splits;
     int tiles_per_split;
+    int dbg;             // timing experiments only (VSB_TC_DBG): 1 no epilogue work, 2 no inserts, 4 no MMA, 8 no B loads
 };
 
 template <int KTOP, bool SPLIT3, bool HAS_LB>
@@ -127,13 +128,21 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
 #pragma unroll
                     for (int kb = 0; kb < TC_NKB; ++kb) {
                         mbar_wait(&empty[stage], phase ^ 1);
-                        mbar_expect_tx(&full[stage], (uint32_t)TC_KB_BYTES);
-                        tma_load_2d(sB + stage * TC_KB_BYTES, &tmB_hi, &full[stage], kb * 32, t * TC_BN);
+                        if (p.dbg & 8) {
+                            mbar_arrive(&full[stage]);
+                        } else {
+                            mbar_expect_tx(&full[stage], (uint32_t)TC_KB_BYTES);
+                            tma_load_2d(sB + stage * TC_KB_BYTES, &tmB_hi, &full[stage], kb * 32, t * TC_BN);
+                        }
                         if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
                         if (SPLIT3) {
                             mbar_wait(&empty[stage], phase ^ 1);
-                            mbar_expect_tx(&full[stage], (uint32_t)TC_KB_BYTES);
-                            tma_load_2d(sB + stage * TC_KB_BYTES, &tmB_lo, &full[stage], kb * 32, t * TC_BN);
+                            if (p.dbg & 8) {
+                                mbar_arrive(&full[stage]);
+                            } else {
+                                mbar_expect_tx(&full[stage], (uint32_t)TC_KB_BYTES);
+                                tma_load_2d(sB + stage * TC_KB_BYTES, &tmB_lo, &full[stage], kb * 32, t * TC_BN);
+                            }
                             if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
                         }
                     }
@@ -169,17 +178,19 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
                         tc_fence_after();
                         {
                             const uint64_t b = umma_desc_sw128(sB_u + stage * TC_KB_BYTES);
-                            if (SPLIT3) {
+                            if (SPLIT3 && !(p.dbg & 4)) {
 #pragma unroll
                                 for (int ks = 0; ks < 4; ++ks) {  // q_lo . x_hi   (small term first)
                                     tc_mma_tf32(d_tmem, a_lo + 2 * ks, b + 2 * ks, idesc, accum);
                                     accum = 1;
                                 }
                             }
+                            if (!(p.dbg & 4)) {
 #pragma unroll
-                            for (int ks = 0; ks < 4; ++ks) {      // q_hi . x_hi
-                                tc_mma_tf32(d_tmem, a_hi + 2 * ks, b + 2 * ks, idesc, accum);
-                                accum = 1;
+                                for (int ks = 0; ks < 4; ++ks) {  // q_hi . x_hi
+                                    tc_mma_tf32(d_tmem, a_hi + 2 * ks, b + 2 * ks, idesc, accum);
+                                    accum = 1;
+                                }
                             }
                         }
                         tc_commit(&empty[stage]);
@@ -189,9 +200,11 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
                             mbar_wait(&full[stage], phase);
                             tc_fence_after();
                             const uint64_t b = umma_desc_sw128(sB_u + stage * TC_KB_BYTES);
+                            if (!(p.dbg & 4)) {
 #pragma unroll
-                            for (int ks = 0; ks < 4; ++ks)        // q_hi . x_lo
-                                tc_mma_tf32(d_tmem, a_hi + 2 * ks, b + 2 * ks, idesc, 1u);
+                                for (int ks = 0; ks < 4; ++ks)    // q_hi . x_lo
+                                    tc_mma_tf32(d_tmem, a_hi + 2 * ks, b + 2 * ks, idesc, 1u);
+                            }
                             tc_commit(&empty[stage]);
                             if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
                         }
@@ -230,7 +243,7 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * TC_BN);
 #pragma unroll 1
-                for (int c = 0; c < TC_BN / 32; ++c) {
+                for (int c = 0; c < ((p.dbg & 1) ? 0 : TC_BN / 32); ++c) {
                     uint32_t r[32];
                     tmem_ld32(taddr + c * 32, r);
                     float bn[32];
@@ -258,7 +271,7 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
                         d[j] = v;
                         mn = fminf(mn, v);
                     }
-                    if (mn < top.threshold()) {
+                    if (mn < top.threshold() && !(p.dbg & 2)) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j)
                             if (d[j] < top.threshold()) top.insert(d[j], col0 + j);

@@ -76,7 +76,8 @@ def test_mid_size_vs_oracle(gpu_vsb, oracle):
 
 
 def test_3xtf32_is_fp32_faithful(gpu_vsb):
-    """Continuous data: 3xTF32 distances within 1e-5 relative of a float64 evaluation, and far closer than 1xTF32."""
+    """Continuous data: the 3xTF32 path returns the float64-exact neighbour set and fp32-faithful distances
+    (far inside the 1e-5 budget); the single-product TF32 ranking is visibly worse."""
     vsb = gpu_vsb
     base = vsb.synth.make("cont", 5, 50_000)
     qry = vsb.synth.make("cont", 6, 256)
@@ -88,11 +89,12 @@ def test_3xtf32_is_fp32_faithful(gpu_vsb):
         idx.close()
     b64, q64 = base.astype(np.float64), qry.astype(np.float64)
     true3 = ((q64[:, None, :] - b64[ids3]) ** 2).sum(-1)
-    true1 = ((q64[:, None, :] - b64[ids1]) ** 2).sum(-1)
     e3 = np.abs(d3 - true3) / true3
-    e1 = np.abs(d1 - true1) / true1
-    assert e3.max() < RTOL, e3.max()
-    assert e3.max() < e1.max()  # the split buys real accuracy
+    assert e3.max() < 2e-6, e3.max()
+    full = (q64 ** 2).sum(1)[:, None] + (b64 ** 2).sum(1)[None, :] - 2.0 * (q64 @ b64.T)
+    want = np.argsort(full, axis=1, kind="stable")[:, :10]
+    assert (ids3 == want).mean() > 0.9995          # only float64-vs-fp32 near-ties may differ
+    assert (ids1 == want).mean() <= (ids3 == want).mean()
 
 
 def test_properties_full_size(gpu_vsb):
