@@ -96,7 +96,7 @@ struct vs_exact {
     CUtensorMap tmB_hi, tmB_lo;
     cudaStream_t stream = nullptr;
     // workspace (grow-only)
-    DevBuf q, qhi, qlo, qnorm, part_key, part_id, lbk, lbi, out_ids, out_keys, flag;
+    DevBuf q, qhi, qlo, qnorm, part_key, part_id, lbk, lbi, out_ids, out_keys, flag, gthr;
     int* h_flag = nullptr;  // pinned
     int last_launches = 0;
     int last_precision = 0;
@@ -115,7 +115,7 @@ static int exact_free(vs_exact* h) {
     if (h->d_lo) cudaFree(h->d_lo);
     if (h->d_norm) cudaFree(h->d_norm);
     for (DevBuf* b : {&h->q, &h->qhi, &h->qlo, &h->qnorm, &h->part_key, &h->part_id, &h->lbk, &h->lbi, &h->out_ids,
-                      &h->out_keys, &h->flag})
+                      &h->out_keys, &h->flag, &h->gthr})
         b->release();
     if (h->h_flag) cudaFreeHost(h->h_flag);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -260,8 +260,10 @@ static int exact_search_core(vs_exact* h, const float* q_dev, int64_t nq, int k,
         if (split3 && !h->d_lo && !h->base_exact) return fail(VS_ERR_INVALID, "internal: lo split missing");
         h->last_precision = split3 ? VS_PREC_FP32_3XTF32 : VS_PREC_TF32_1X;
         const TcPlan plan = tc_make_plan(h->n, nq, h->num_sms);
-        VSB_TRY(h->part_key.reserve(sizeof(float) * (size_t)plan.n_splits * nq * ktop));
-        VSB_TRY(h->part_id.reserve(sizeof(int32_t) * (size_t)plan.n_splits * nq * ktop));
+        const int n_lists = plan.n_splits * tc_lists_per_split();
+        VSB_TRY(h->part_key.reserve(sizeof(float) * (size_t)n_lists * nq * ktop));
+        VSB_TRY(h->part_id.reserve(sizeof(int32_t) * (size_t)n_lists * nq * ktop));
+        VSB_TRY(h->gthr.reserve(sizeof(int32_t) * (size_t)nq));
         CUtensorMap tmA_hi, tmA_lo;
         VSB_TRY(make_tmap_2d(&tmA_hi, h->qhi.p, (uint64_t)nq, 128, 4, 128));
         VSB_TRY(make_tmap_2d(&tmA_lo, h->qlo.p, (uint64_t)nq, 128, 4, 128));
@@ -276,15 +278,17 @@ static int exact_search_core(vs_exact* h, const float* q_dev, int64_t nq, int k,
         for (int pass = 0; pass < passes; ++pass) {
             const int kk = std::min(kMaxRegK, k - pass * kMaxRegK);
             const bool lb = pass > 0;
+            // shared per-query thresholds start at a huge finite value (0x7f7f7f7f in the ordered-int encoding)
+            VSB_CUDA(cudaMemsetAsync(h->gthr.p, 0x7f, sizeof(int32_t) * (size_t)nq, st));
             if (h->profile && pass == 0) VSB_CUDA(cudaEventRecord(h->ev0, st));
-            VSB_TRY(launch_exact_tc(tmA_hi, tmA_lo, h->tmB_hi, h->tmB_lo, h->d_norm, h->qnorm.as<float>(), (int)nq, plan,
+            VSB_TRY(launch_exact_tc(tmA_hi, tmA_lo, h->tmB_hi, h->tmB_lo, h->d_norm, h->gthr.as<int32_t>(), (int)nq, plan,
                                     ktop, split3, lb ? h->lbk.as<float>() : nullptr, lb ? h->lbi.as<int32_t>() : nullptr,
                                     h->part_key.as<float>(), h->part_id.as<int32_t>(), st));
             if (h->profile && pass == 0) {
                 VSB_CUDA(cudaEventRecord(h->ev1, st));
                 h->ev_valid = true;
             }
-            VSB_TRY(launch_merge_lists(h->part_key.as<float>(), h->part_id.as<int32_t>(), plan.n_splits, nq, ktop,
+            VSB_TRY(launch_merge_lists(h->part_key.as<float>(), h->part_id.as<int32_t>(), n_lists, nq, ktop,
                                        passes == 1 ? ktop : kk, passes == 1 ? k : kk, h->id_base, 0, 0, out_dists,
                                        out_ids, k, pass * kMaxRegK, passes > 1 ? h->lbk.as<float>() : nullptr,
                                        passes > 1 ? h->lbi.as<int32_t>() : nullptr, h->d_base, h->d_norm, q_dev,

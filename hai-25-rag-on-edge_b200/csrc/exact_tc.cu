@@ -43,6 +43,8 @@ static int set_attr_one() {
     return VS_OK;
 }
 
+int tc_lists_per_split() { return TC_EPI_GROUPS; }
+
 int tc_set_attributes() {
     VSB_TRY((set_attr_one<1, false, false>()));
     VSB_TRY((set_attr_one<1, true, false>()));
@@ -60,12 +62,12 @@ int tc_set_attributes() {
 }
 
 int launch_exact_tc(const CUtensorMap& tmA_hi, const CUtensorMap& tmA_lo, const CUtensorMap& tmB_hi,
-                    const CUtensorMap& tmB_lo, const float* bnorm, const float* qnorm, int nq, const TcPlan& plan,
+                    const CUtensorMap& tmB_lo, const float* bnorm, int32_t* gthr, int nq, const TcPlan& plan,
                     int ktop, bool split3, const float* lb_key, const int32_t* lb_id, float* part_key,
                     int32_t* part_id, cudaStream_t st) {
     TcParams p{};
     p.bnorm = bnorm;
-    p.qnorm = qnorm;
+    p.gthr = gthr;
     p.lb_key = lb_key;
     p.lb_id = lb_id;
     p.part_key = part_key;

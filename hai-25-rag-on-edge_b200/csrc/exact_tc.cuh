@@ -2,19 +2,24 @@
 // fed by TMA), replacing the reference's per-query  cblas_sgemm(M=1) -> distance loop -> select_topk
 // (cpu/cpu_baseline.cpp:222-248) for a whole batch of queries.  The Q x N distance matrix never exists in
 // memory: each epilogue thread owns one query row of the accumulator tile and folds it into a register-
-// resident top-k list.
+// resident candidate list.
 //
 // Mapping: queries -> M (TMEM lanes, 128 per CTA), base rows -> N (TMEM columns, 128 per tile), K = dim = 128 as
 // 4 k-blocks of 32 fp32 (one 128-byte swizzle row each).  kind::tf32, K = 8 per instruction.
 //   1xTF32 : 16 MMAs per tile (exact when operands are TF32-representable, e.g. integer SIFT data)
 //   3xTF32 : q.x ~= q_lo.x_hi + q_hi.x_hi + q_hi.x_lo per k-block, 48 MMAs per tile, fp32 accumulate
+// Ranking key per (query, base row): bn - 2*dot (the query norm is constant per row of the tile); the merge
+// kernel recomputes the reported distance of the surviving candidates in exact fp32 (kernels.cu, K3).
+//
 // Work decomposition: unit = (query tile, base split); units are ordered split-major so that the CTAs resident
 // at any moment sweep the same base panel (it streams from HBM once and is re-read from L2 by the other
-// query tiles).  Each unit writes a sorted partial list [split][query][KTOP]; merge_partials_kernel (K3)
-// combines them.
+// query tiles).  Every unit writes two sorted partial lists per query (one per epilogue warpgroup).
+// Per-query thresholds are shared between CTAs through a global array (atomicMin of each full list's worst kept
+// key — an upper bound of the query's KTOP-th best key), so later units start with a tight filter.
 //
-// Warp roles (192 threads): warp 0 = TMA producer (one lane), warp 1 = TMEM allocator + MMA issuer (one
-// lane), warps 2..5 = epilogue (TMEM lane quadrant = warp % 4).
+// Warp roles (320 threads): warp 0 = TMA producer (one lane), warp 1 = TMEM allocator + MMA issuer (one
+// lane), warps 2..9 = epilogue: warpgroup g = (warp-2)/4 handles columns [64g, 64g+64) of every tile, TMEM
+// lane quadrant = warp % 4.
 #pragma once
 #include <cuda.h>
 
@@ -27,23 +32,27 @@ constexpr int TC_BN = 128;        // base rows per accumulator tile
 constexpr int TC_NKB = 4;         // k-blocks (dim 128 = 4 x 32 fp32)
 constexpr int TC_KB_BYTES = 128 * 128;  // one k-block of a 128-row operand tile: 128 rows x 128 B
 constexpr int TC_NACC = 4;        // accumulator buffers in TMEM (4 x 128 columns = all 512)
-constexpr int TC_THREADS = 192;
+constexpr int TC_EPI_GROUPS = 2;  // epilogue warpgroups (column halves)
+constexpr int TC_GCOLS = TC_BN / TC_EPI_GROUPS;
+constexpr int TC_THREADS = 64 + 128 * TC_EPI_GROUPS;
+constexpr int TC_THR_REFRESH = 8; // tiles between reads of the shared threshold (power of two)
 
 template <bool SPLIT3>
 struct TcSmem {
     static constexpr int A_BYTES = (SPLIT3 ? 2 : 1) * TC_NKB * TC_KB_BYTES;
     static constexpr int NSTAGE = SPLIT3 ? 5 : 8;
     static constexpr int B_BYTES = NSTAGE * TC_KB_BYTES;
+    static constexpr int NORM_BYTES = TC_NACC * TC_BN * 4;
     static constexpr int BAR_BYTES = 1024;
-    static constexpr int TOTAL = A_BYTES + B_BYTES + BAR_BYTES + 1024;  // + slack for 1024-B alignment
+    static constexpr int TOTAL = A_BYTES + B_BYTES + NORM_BYTES + BAR_BYTES + 1024;  // + slack for 1024-B alignment
 };
 
 struct TcParams {
     const float* bnorm;  // [n_tiles*128], +inf beyond n
-    const float* qnorm;  // [nq]
     const float* lb_key; // optional per-query exclusive lower bound (multi-pass k > 32), or nullptr
     const int32_t* lb_id;
-    float* part_key;     // [n_splits][nq][KTOP]
+    int32_t* gthr;       // [nq] shared thresholds (order-preserving int encoding), preset to a huge value
+    float* part_key;     // [n_splits*TC_EPI_GROUPS][nq][KTOP]
     int32_t* part_id;
     int nq;
     int n_tiles;         // ceil(n / 128)
@@ -52,6 +61,14 @@ struct TcParams {
     int tiles_per_split;
     int dbg;             // timing experiments only (VSB_TC_DBG): 1 no epilogue work, 2 no inserts, 4 no MMA, 8 no B loads
 };
+
+// smallest float strictly greater than x (x finite or +inf; +inf maps to itself)
+__device__ __forceinline__ float next_up(float x) {
+    if (x == 0.f) return __int_as_float(1);
+    if (!(x < __int_as_float(0x7f800000))) return x;
+    const int32_t i = __float_as_int(x);
+    return __int_as_float(i > 0 ? i + 1 : i - 1);
+}
 
 template <int KTOP, bool SPLIT3, bool HAS_LB>
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -64,12 +81,14 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* sA = smem;
     uint8_t* sB = smem + S::A_BYTES;
-    uint64_t* bars = (uint64_t*)(sB + S::B_BYTES);
+    float* sN = (float*)(sB + S::B_BYTES);      // [TC_NACC][128] base norms of the tile in accumulator slot i
+    uint64_t* bars = (uint64_t*)((uint8_t*)sN + S::NORM_BYTES);
     uint64_t* full = bars;                    // [NSTAGE]  TMA -> MMA
     uint64_t* empty = full + NSTAGE;          // [NSTAGE]  MMA -> TMA
     uint64_t* acc_full = empty + NSTAGE;      // [TC_NACC] MMA -> epilogue
-    uint64_t* acc_empty = acc_full + TC_NACC; // [TC_NACC] epilogue -> MMA
-    uint64_t* a_full = acc_empty + TC_NACC;   // query tile landed
+    uint64_t* acc_empty = acc_full + TC_NACC; // [TC_NACC] epilogue -> MMA, and -> producer (norm slot free)
+    uint64_t* n_full = acc_empty + TC_NACC;   // [TC_NACC] norms landed
+    uint64_t* a_full = n_full + TC_NACC;      // query tile landed
     uint64_t* a_empty = a_full + 1;           // query tile no longer read by the tensor core
     uint32_t* tmem_slot = (uint32_t*)(a_empty + 1);
 
@@ -83,7 +102,8 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         }
         for (int i = 0; i < TC_NACC; ++i) {
             mbar_init(&acc_full[i], 1);
-            mbar_init(&acc_empty[i], 4);
+            mbar_init(&acc_empty[i], 4 * TC_EPI_GROUPS);
+            mbar_init(&n_full[i], 1);
         }
         mbar_init(a_full, 1);
         mbar_init(a_empty, 1);
@@ -109,8 +129,8 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
                 tma_prefetch_desc(&tmA_lo);
                 tma_prefetch_desc(&tmB_lo);
             }
-            int stage = 0;
-            uint32_t phase = 0;
+            int stage = 0, acc = 0;
+            uint32_t phase = 0, acc_phase = 0;
             int it = 0;
             for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++it) {
                 const int m_tile = unit % p.n_mtiles;
@@ -125,6 +145,11 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
                 const int t0 = split * p.tiles_per_split;
                 const int t1 = min(t0 + p.tiles_per_split, p.n_tiles);
                 for (int t = t0; t < t1; ++t) {
+                    // norms of this tile go to the slot of the accumulator the tile will use
+                    mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+                    mbar_expect_tx(&n_full[acc], (uint32_t)(TC_BN * 4));
+                    bulk_load_1d(sN + acc * TC_BN, p.bnorm + (size_t)t * TC_BN, TC_BN * 4, &n_full[acc]);
+                    if (++acc == TC_NACC) { acc = 0; acc_phase ^= 1; }
 #pragma unroll
                     for (int kb = 0; kb < TC_NKB; ++kb) {
                         mbar_wait(&empty[stage], phase ^ 1);
@@ -218,8 +243,10 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
     } else {
         // ===================================== epilogue ==========================================
         const int quad = warp & 3;
+        const int grp = (warp - 2) >> 2;  // column half handled by this warpgroup
         const int row = quad * 32 + lane;
         const float INF = __int_as_float(0x7f800000);
+        constexpr int CH = TC_GCOLS / 32;  // 32-column chunks per thread per tile
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
@@ -229,7 +256,6 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
             const int t1 = min(t0 + p.tiles_per_split, p.n_tiles);
             const int q = m_tile * TC_BM + row;
             const bool valid = q < p.nq;
-            const float qn = valid ? __ldg(p.qnorm + q) : 0.f;
             float lbk = -INF;
             int32_t lbi = -1;
             if (HAS_LB && valid) {
@@ -238,53 +264,83 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
             }
             RegTopK<KTOP> top;
             top.init();
+            // cap = smallest "worst kept key" published by any full list of this query so far.  Keys equal to it
+            // may still belong to the canonical answer (smaller id), hence the strict test against next_up(cap).
+            float cap = INF;
+            float thr = INF;  // invariant: thr == min(top.threshold(), next_up(cap))
             for (int t = t0; t < t1; ++t) {
+                const int rel = (t - t0) & (TC_THR_REFRESH - 1);
+                if (rel == 0 && valid) {
+                    cap = fminf(cap, ordered_to_float(__ldcg(p.gthr + q)));
+                    thr = fminf(top.threshold(), next_up(cap));
+                }
+                mbar_wait(&n_full[acc], acc_phase);
                 mbar_wait(&acc_full[acc], acc_phase);
                 tc_fence_after();
-                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * TC_BN);
-#pragma unroll 1
-                for (int c = 0; c < ((p.dbg & 1) ? 0 : TC_BN / 32); ++c) {
-                    uint32_t r[32];
-                    tmem_ld32(taddr + c * 32, r);
-                    float bn[32];
-                    const float4* bn4 = reinterpret_cast<const float4*>(p.bnorm + (size_t)t * TC_BN + c * 32);
+                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * TC_BN + grp * TC_GCOLS);
+                const float* bn_s = sN + acc * TC_BN + grp * TC_GCOLS;
+                uint32_t r[2][32];
+                if (!(p.dbg & 1)) tmem_ld32(taddr, r[0]);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float4 v = __ldg(bn4 + j);
-                        bn[4 * j + 0] = v.x;
-                        bn[4 * j + 1] = v.y;
-                        bn[4 * j + 2] = v.z;
-                        bn[4 * j + 3] = v.w;
-                    }
+                for (int c = 0; c < CH; ++c) {
+                    if (p.dbg & 1) break;
                     tc_wait_ld();
-                    const int col0 = t * TC_BN + c * 32;
+                    if (c + 1 < CH) tmem_ld32(taddr + (c + 1) * 32, r[(c + 1) & 1]);
+                    const int col0 = t * TC_BN + grp * TC_GCOLS + c * 32;
                     float d[32];
-                    float mn = INF;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        // (qn + bn) - 2*dot, cpu_baseline.cpp:241 (2*dot is exact, so one rounding either way)
-                        float v = fmaf(-2.0f, __uint_as_float(r[j]), qn + bn[j]);
-                        if (HAS_LB) {
-                            const bool after = v > lbk || (v == lbk && (col0 + j) > lbi);
-                            v = after ? v : INF;
-                        }
-                        d[j] = v;
-                        mn = fminf(mn, v);
+                    for (int j4 = 0; j4 < 8; ++j4) {
+                        const float4 bn = *reinterpret_cast<const float4*>(bn_s + c * 32 + 4 * j4);  // smem broadcast
+                        d[4 * j4 + 0] = fmaf(-2.0f, __uint_as_float(r[c & 1][4 * j4 + 0]), bn.x);
+                        d[4 * j4 + 1] = fmaf(-2.0f, __uint_as_float(r[c & 1][4 * j4 + 1]), bn.y);
+                        d[4 * j4 + 2] = fmaf(-2.0f, __uint_as_float(r[c & 1][4 * j4 + 2]), bn.z);
+                        d[4 * j4 + 3] = fmaf(-2.0f, __uint_as_float(r[c & 1][4 * j4 + 3]), bn.w);
                     }
-                    if (mn < top.threshold() && !(p.dbg & 2)) {
+                    if (HAS_LB) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (d[j] < top.threshold()) top.insert(d[j], col0 + j);
+                        for (int j = 0; j < 32; ++j) {
+                            const bool after = d[j] > lbk || (d[j] == lbk && (col0 + j) > lbi);
+                            d[j] = after ? d[j] : INF;
+                        }
+                    }
+                    float m[16];  // pairwise min tree (depth 5)
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) m[j] = fminf(d[j], d[j + 16]);
+#pragma unroll
+                    for (int w = 8; w >= 1; w >>= 1)
+#pragma unroll
+                        for (int j = 0; j < w; ++j) m[j] = fminf(m[j], m[j + w]);
+                    if (m[0] < thr && !(p.dbg & 2)) {
+                        // rare path: bit mask of the qualifying columns, then one insertion per set bit
+                        uint32_t mask = 0;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) mask |= (d[j] < thr) ? (1u << j) : 0u;
+                        while (mask) {
+                            const int j = __ffs(mask) - 1;
+                            mask &= mask - 1;
+                            const float v = select32(d, j);
+                            if (v < thr) {
+                                top.insert(v, col0 + j);
+                                thr = fminf(thr, top.threshold());
+                            }
+                        }
                     }
                 }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&acc_empty[acc]);
                 if (++acc == TC_NACC) { acc = 0; acc_phase ^= 1; }
+                // publish this list's worst kept key: a valid upper bound of the query's KTOP-th best key
+                if (valid && rel == TC_THR_REFRESH - 1 && top.threshold() < cap) {
+                    atomicMin(p.gthr + q, float_to_ordered(top.threshold()));
+                    cap = top.threshold();
+                }
             }
             if (valid) {
-                float* pk = p.part_key + ((size_t)split * p.nq + q) * KTOP;
-                int32_t* pi = p.part_id + ((size_t)split * p.nq + q) * KTOP;
+                if (top.threshold() < cap) atomicMin(p.gthr + q, float_to_ordered(top.threshold()));
+                const size_t list = (size_t)split * TC_EPI_GROUPS + grp;
+                float* pk = p.part_key + (list * p.nq + q) * KTOP;
+                int32_t* pi = p.part_id + (list * p.nq + q) * KTOP;
 #pragma unroll
                 for (int i = 0; i < KTOP; ++i) {
                     pk[i] = top.key[i];

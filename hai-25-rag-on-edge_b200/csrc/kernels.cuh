@@ -28,9 +28,10 @@ struct TcPlan {
 };
 TcPlan tc_make_plan(int64_t n, int64_t nq, int num_sms);
 int launch_exact_tc(const CUtensorMap& tmA_hi, const CUtensorMap& tmA_lo, const CUtensorMap& tmB_hi,
-                    const CUtensorMap& tmB_lo, const float* bnorm, const float* qnorm, int nq, const TcPlan& plan,
+                    const CUtensorMap& tmB_lo, const float* bnorm, int32_t* gthr, int nq, const TcPlan& plan,
                     int ktop, bool split3, const float* lb_key, const int32_t* lb_id, float* part_key,
                     int32_t* part_id, cudaStream_t st);
+int tc_lists_per_split();  // partial lists written per (split, query)
 int tc_set_attributes();  // opt-in to > 48 KB dynamic shared memory for every instantiation
 
 // kernels.cu (K3) ----------------------------------------------------------------------------

@@ -168,19 +168,22 @@ struct RegTopK {
         }
     }
     __device__ __forceinline__ float threshold() const { return key[K - 1]; }
-    // precondition for a useful call: v < threshold()
+    // precondition: v < threshold().  Every slot is computed independently (no serial bubble chain):
+    // entries with key <= v stay, the first slot whose key > v receives v, later slots shift down by one.
     __device__ __forceinline__ void insert(float v, int32_t i) {
-        key[K - 1] = v;
-        id[K - 1] = i;
+        bool keep[K];
+#pragma unroll
+        for (int s = 0; s < K; ++s) keep[s] = key[s] <= v;
 #pragma unroll
         for (int s = K - 1; s > 0; --s) {
-            const bool sw = key[s] < key[s - 1];
-            const float a = key[s], b = key[s - 1];
-            const int32_t ia = id[s], ib = id[s - 1];
-            key[s] = sw ? b : a;
-            key[s - 1] = sw ? a : b;
-            id[s] = sw ? ib : ia;
-            id[s - 1] = sw ? ia : ib;
+            const float nk = keep[s - 1] ? v : key[s - 1];
+            const int32_t ni = keep[s - 1] ? i : id[s - 1];
+            key[s] = keep[s] ? key[s] : nk;
+            id[s] = keep[s] ? id[s] : ni;
+        }
+        if (!keep[0]) {
+            key[0] = v;
+            id[0] = i;
         }
     }
     // general insert honouring (key, id) order for arbitrary arrival order
@@ -200,6 +203,27 @@ struct RegTopK {
         }
     }
 };
+
+// value d[j] for a run-time j without dynamic register indexing: 5-level multiplexer (31 selects)
+__device__ __forceinline__ float select32(const float (&d)[32], int j) {
+    float a[16], b[8], c[4];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = (j & 16) ? d[i + 16] : d[i];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) b[i] = (j & 8) ? a[i + 8] : a[i];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) c[i] = (j & 4) ? b[i + 4] : b[i];
+    const float e0 = (j & 2) ? c[2] : c[0];
+    const float e1 = (j & 2) ? c[3] : c[1];
+    return (j & 1) ? e1 : e0;
+}
+
+// order-preserving float <-> int mapping (so that atomicMin on int orders floats, negatives included)
+__device__ __forceinline__ int32_t float_to_ordered(float f) {
+    const int32_t i = __float_as_int(f);
+    return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__device__ __forceinline__ float ordered_to_float(int32_t i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
 
 // (key, id) lexicographic "a before b"; id compared unsigned so that the -1 padding sorts last
 __device__ __forceinline__ bool pair_less(float ka, int32_t ia, float kb, int32_t ib) {
