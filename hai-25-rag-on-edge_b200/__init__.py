@@ -140,3 +140,82 @@ def synth_fill_dev(out_ptr: int, row0: int, nrows: int, dim: int, law: str, seed
     _check(lib().vs_synth_fill_dev(_ptr(out_ptr), C.c_int64(row0), C.c_int64(nrows), C.c_int(dim),
                                    C.c_int(synth.LAWS[law]), C.c_uint64(seed), C.c_uint64(centre_seed),
                                    C.c_void_p(stream)))
+
+
+class IvfIndex:
+    """Two-stage IVF search (inner product, largest first); mirrors the reference's IVFIndex class surface
+    (qidk_ivf/android/app/main/jni/IVFIndex.h:14-54) over the C ABI."""
+
+    def __init__(self, index_dir: str | None = None, *, vectors=None, offsets=None, id_map=None, centroids=None,
+                 device: int = 0):
+        self._h = C.c_void_p()
+        L = lib()
+        L.vs_ivf_num_vectors.restype = C.c_int64
+        L.vs_ivf_avg_cluster_size.restype = C.c_float
+        if index_dir is not None:
+            _check(L.vs_ivf_open(C.byref(self._h), index_dir.encode(), C.c_int(device)))
+        else:
+            v = np.ascontiguousarray(vectors, dtype=np.float32)
+            o = np.ascontiguousarray(offsets, dtype=np.int32)
+            m = np.ascontiguousarray(id_map, dtype=np.int32)
+            c = np.ascontiguousarray(centroids, dtype=np.float32)
+            _check(L.vs_ivf_create(C.byref(self._h), _ptr(v), C.c_int64(v.shape[0]), C.c_int(v.shape[1]), _ptr(o),
+                                   C.c_int(o.shape[0] - 1), _ptr(m), _ptr(c), C.c_int(device)))
+        self.num_vectors = int(L.vs_ivf_num_vectors(self._h))
+        self.num_clusters = int(L.vs_ivf_num_clusters(self._h))
+        self.dim = int(L.vs_ivf_dim(self._h))
+        self.avg_cluster_size = float(L.vs_ivf_avg_cluster_size(self._h))
+
+    def close(self) -> None:
+        if self._h:
+            lib().vs_ivf_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def search_batch(self, queries, k: int, nprobe: int):
+        """-> (ids [nq,k] int32 (-1 padded), scores [nq,k] f32 descending, counts [nq], total candidates)."""
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        nq = q.shape[0]
+        ids = np.empty((nq, k), dtype=np.int32)
+        sc = np.empty((nq, k), dtype=np.float32)
+        cnt = np.empty(nq, dtype=np.int32)
+        total = C.c_uint64(0)
+        _check(lib().vs_ivf_search(self._h, _ptr(q), C.c_int64(nq), C.c_int(k), C.c_int(nprobe), _ptr(ids), _ptr(sc),
+                                   _ptr(cnt), C.byref(total)))
+        return ids, sc, cnt, int(total.value)
+
+    def search_dev(self, q_ptr: int, nq: int, k: int, nprobe: int, ids_ptr: int, scores_ptr: int, counts_ptr: int,
+                   stream: int = 0) -> None:
+        _check(lib().vs_ivf_search_dev(self._h, _ptr(q_ptr), C.c_int64(nq), C.c_int(k), C.c_int(nprobe), _ptr(ids_ptr),
+                                       _ptr(scores_ptr), _ptr(counts_ptr), C.c_void_p(stream)))
+
+    def coarse_scores(self, queries) -> np.ndarray:
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        out = np.empty((q.shape[0], self.num_clusters), dtype=np.float32)
+        _check(lib().vs_ivf_coarse_scores(self._h, _ptr(q), C.c_int64(q.shape[0]), _ptr(out)))
+        return out
+
+    def set_profile(self, enable: bool = True) -> None:
+        _check(lib().vs_ivf_set_profile(self._h, C.c_int(int(enable))))
+
+    def last_kernel_ms(self) -> float:
+        ms = C.c_float(0)
+        _check(lib().vs_ivf_last_kernel_ms(self._h, C.byref(ms)))
+        return float(ms.value)
+
+
+def ivf_build(base, nlist: int, out_dir: str, *, max_iter: int = 100, seed: int = 42, reordered: bool = True,
+              device: int = 0, init_centroids=None):
+    """build_ivf_index() of the reference (create_ivf_model*.py) on the GPU -> {'nlist','iters','inertia'}."""
+    b = np.ascontiguousarray(base, dtype=np.float32)
+    ic = None if init_centroids is None else np.ascontiguousarray(init_centroids, dtype=np.float32)
+    nl, it, inertia = C.c_int(0), C.c_int(0), C.c_double(0)
+    _check(lib().vs_ivf_build(_ptr(b), C.c_int64(b.shape[0]), C.c_int(b.shape[1]), C.c_int(nlist), C.c_int(max_iter),
+                              C.c_uint64(seed), out_dir.encode(), C.c_int(int(reordered)), C.c_int(device), _ptr(ic),
+                              C.byref(nl), C.byref(it), C.byref(inertia)))
+    return {"nlist": nl.value, "iters": it.value, "inertia": inertia.value}

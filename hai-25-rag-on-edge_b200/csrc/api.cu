@@ -54,29 +54,6 @@ int make_tmap_2d(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_t col
     return VS_OK;
 }
 
-struct DevBuf {
-    void* p = nullptr;
-    size_t cap = 0;
-    int reserve(size_t bytes) {
-        if (bytes <= cap) return VS_OK;
-        if (p) cudaFree(p);
-        p = nullptr;
-        cap = 0;
-        const size_t want = bytes + bytes / 4;
-        cudaError_t e = cudaMalloc(&p, want);
-        if (e != cudaSuccess) return fail(VS_ERR_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
-        cap = want;
-        return VS_OK;
-    }
-    void release() {
-        if (p) cudaFree(p);
-        p = nullptr;
-        cap = 0;
-    }
-    template <class T>
-    T* as() const { return (T*)p; }
-};
-
 }  // namespace vsb
 
 using namespace vsb;
@@ -363,6 +340,19 @@ int vs_exact_create_dev(vs_exact_t** out, const float* base_dev, int64_t n, int 
     return exact_create_common(out, base_dev, true, n, dim, device, id_base);
 }
 int vs_exact_destroy(vs_exact_t* h) { return exact_free(h); }
+
+int vs_exact_refresh(vs_exact_t* h) {
+    if (!h) return fail(VS_ERR_INVALID, "handle is NULL");
+    VSB_CUDA(cudaSetDevice(h->device));
+    VSB_CUDA(cudaStreamSynchronize(h->stream));
+    if (h->d_hi && h->d_hi != h->d_base) cudaFree(h->d_hi);
+    if (h->d_lo) cudaFree(h->d_lo);
+    if (h->d_norm) cudaFree(h->d_norm);
+    if (h->h_flag) cudaFreeHost(h->h_flag);
+    h->d_hi = h->d_lo = h->d_norm = nullptr;
+    h->h_flag = nullptr;
+    return exact_build(h);
+}
 int64_t vs_exact_size(const vs_exact_t* h) { return h ? h->n : 0; }
 int vs_exact_dim(const vs_exact_t* h) { return h ? h->dim : 0; }
 int vs_exact_base_is_tf32_exact(const vs_exact_t* h) { return h && h->base_exact ? 1 : 0; }

@@ -29,42 +29,6 @@ __device__ __forceinline__ float4 ldg_stream(const float4* p) {
     return v;
 }
 
-// pop-min merge of the lists held by the lanes of a warp; `mine` = this lane takes part. Lane 0 writes k entries.
-template <int KTOP>
-__device__ __forceinline__ void warp_merge_lists(RegTopK<KTOP>& L, int k, float* out_key, int32_t* out_id) {
-    const int lane = threadIdx.x & 31;
-    const float INF = __int_as_float(0x7f800000);
-    for (int r = 0; r < k; ++r) {
-        float hk = L.key[0];
-        int32_t hid = L.id[0];
-        int src = lane;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const float ok = __shfl_xor_sync(0xffffffffu, hk, o);
-            const int32_t oi = __shfl_xor_sync(0xffffffffu, hid, o);
-            const int os = __shfl_xor_sync(0xffffffffu, src, o);
-            if (pair_less(ok, oi, hk, hid)) {
-                hk = ok;
-                hid = oi;
-                src = os;
-            }
-        }
-        if (lane == 0) {
-            out_key[r] = hid >= 0 ? hk : INF;
-            out_id[r] = hid;
-        }
-        if (src == lane && hid >= 0) {
-#pragma unroll
-            for (int i = 0; i + 1 < KTOP; ++i) {
-                L.key[i] = L.key[i + 1];
-                L.id[i] = L.id[i + 1];
-            }
-            L.key[KTOP - 1] = INF;
-            L.id[KTOP - 1] = -1;
-        }
-    }
-}
-
 template <int KTOP, int ST_QB, bool HAS_LB>
 __global__ void __launch_bounds__(ST_THREADS, st_ctas_per_sm(ST_QB))
 exact_stream_kernel(const float* __restrict__ base, const float* __restrict__ bnorm, int64_t n,

@@ -50,6 +50,18 @@ int launch_sort_rows(float* key, int32_t* id, int64_t nq, int k, cudaStream_t st
 int launch_synth(float* out, int64_t row0, int64_t nrows, int dim, int law, uint64_t seed, uint64_t centre_seed,
                  cudaStream_t st);
 
+// ivf.cu ----------------------------------------------------------------------------------------
+int launch_ivf_coarse(const float* q, int64_t nq, const float* cent, int nlist, float* scores, cudaStream_t st);
+int launch_ivf_probes(const float* scores, int64_t nq, int nlist, int nprobe, int32_t* probes, cudaStream_t st);
+int launch_ivf_scan(const CUtensorMap& tmV, const float* q, const int32_t* probes, const int32_t* offsets,
+                    const int32_t* id_map, int64_t nq, int nprobe, int k, float* out_scores, int32_t* out_ids,
+                    int32_t* out_counts, unsigned long long* total, cudaStream_t st);
+int ivf_set_attributes();
+int ivf_scan_rows_per_chunk();
+
+// api.cu helpers shared with api_ivf.cu
+int make_tmap_2d(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_t cols, int elem_bytes, uint32_t box_rows);
+
 int round_up_ktop(int k);  // smallest supported register-list size >= k (1,5,10,16,32), 0 if k > 32
 
 }  // namespace vsb

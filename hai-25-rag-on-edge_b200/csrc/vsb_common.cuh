@@ -33,6 +33,31 @@ static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b;
 
 constexpr int kMaxRegK = 32;  // largest k kept in a per-thread register list
 
+// grow-only device buffer
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return VS_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        const size_t want = bytes + bytes / 4;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) return fail(VS_ERR_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+        cap = want;
+        return VS_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T>
+    T* as() const { return (T*)p; }
+};
+
+
 #if defined(__CUDACC__)
 // ------------------------------------------------------------------------------------------------
 // PTX wrappers (sm_100a)
@@ -228,6 +253,42 @@ __device__ __forceinline__ float ordered_to_float(int32_t i) { return __int_as_f
 // (key, id) lexicographic "a before b"; id compared unsigned so that the -1 padding sorts last
 __device__ __forceinline__ bool pair_less(float ka, int32_t ia, float kb, int32_t ib) {
     return ka < kb || (ka == kb && (uint32_t)ia < (uint32_t)ib);
+}
+
+// pop-min merge of the lists held by the lanes of a warp; `mine` = this lane takes part. Lane 0 writes k entries.
+template <int KTOP>
+__device__ __forceinline__ void warp_merge_lists(RegTopK<KTOP>& L, int k, float* out_key, int32_t* out_id) {
+    const int lane = threadIdx.x & 31;
+    const float INF = __int_as_float(0x7f800000);
+    for (int r = 0; r < k; ++r) {
+        float hk = L.key[0];
+        int32_t hid = L.id[0];
+        int src = lane;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ok = __shfl_xor_sync(0xffffffffu, hk, o);
+            const int32_t oi = __shfl_xor_sync(0xffffffffu, hid, o);
+            const int os = __shfl_xor_sync(0xffffffffu, src, o);
+            if (pair_less(ok, oi, hk, hid)) {
+                hk = ok;
+                hid = oi;
+                src = os;
+            }
+        }
+        if (lane == 0) {
+            out_key[r] = hid >= 0 ? hk : INF;
+            out_id[r] = hid;
+        }
+        if (src == lane && hid >= 0) {
+#pragma unroll
+            for (int i = 0; i + 1 < KTOP; ++i) {
+                L.key[i] = L.key[i + 1];
+                L.id[i] = L.id[i + 1];
+            }
+            L.key[KTOP - 1] = INF;
+            L.id[KTOP - 1] = -1;
+        }
+    }
 }
 
 // One warp selects the k smallest (key, id) pairs out of C candidates living in shared or global memory

@@ -78,6 +78,9 @@ VSB_API int vs_exact_create(vs_exact_t** out, const float* base, int64_t n, int 
 /* Same, base already resident on `device` (not copied; must outlive the handle). */
 VSB_API int vs_exact_create_dev(vs_exact_t** out, const float* base_dev, int64_t n, int dim, int device, int64_t id_base);
 VSB_API int vs_exact_destroy(vs_exact_t* h);
+/* The rows behind a vs_exact_create_dev handle were modified in place (same pointer, same shape): recompute the
+ * norms and the TF32 split.  Used by the k-means builder, whose centroids move every iteration. */
+VSB_API int vs_exact_refresh(vs_exact_t* h);
 VSB_API int64_t vs_exact_size(const vs_exact_t* h);
 VSB_API int vs_exact_dim(const vs_exact_t* h);
 /* 1 if every base component is exactly representable in TF32 (then 1xTF32 == 3xTF32 == fp32 bit for bit) */
@@ -104,6 +107,51 @@ VSB_API int vs_exact_last_kernel_ms(vs_exact_t* h, float* ms);
  * (L2); smallest==0: keys descending (inner product). Device pointers, asynchronous on `stream`. */
 VSB_API int vs_merge_topk_dev(const int32_t* ids_dev, const float* keys_dev, int n_shards, int64_t nq, int k,
                       int smallest, int32_t* out_ids_dev, float* out_keys_dev, void* stream);
+
+/* ---------------------------------------------------------------------------------------------- */
+/* IVF two-stage search (inner-product metric, like the reference)                                 */
+/* ---------------------------------------------------------------------------------------------- */
+typedef struct vs_ivf vs_ivf_t;
+
+/* Index from host arrays: vectors in list-contiguous order [n x dim] (the reference's "reordered" layout,
+ * vectors_reordered.npy), CSR cluster_offsets [nlist+1], position_to_id [n] (reorder_to_original.npy) and
+ * centroids [nlist x dim].  Replaces IVFIndex::IVFIndex's loaders (IVFIndex.cpp:154-267). */
+VSB_API int vs_ivf_create(vs_ivf_t** out, const float* vectors_list_order, int64_t n, int dim,
+                          const int32_t* cluster_offsets, int nlist, const int32_t* position_to_id,
+                          const float* centroids, int device);
+/* Index from the reference's on-disk directory (ivf_config.json + .npy files); both the
+ * "reordered" and the scattered (cluster_indices.npy + vectors.npy|vectors.bin) layouts; centroids come from
+ * centroids.npy (the reference loads the same numbers as a QNN context binary, centroids.bin). */
+VSB_API int vs_ivf_open(vs_ivf_t** out, const char* index_dir, int device);
+VSB_API int vs_ivf_destroy(vs_ivf_t* h);
+VSB_API int64_t vs_ivf_num_vectors(const vs_ivf_t* h);   /* IVFIndex::getNumVectors  (IVFIndex.h:51) */
+VSB_API int vs_ivf_num_clusters(const vs_ivf_t* h);      /* IVFIndex::getNumClusters (IVFIndex.h:52) */
+VSB_API int vs_ivf_dim(const vs_ivf_t* h);               /* IVFIndex::getDim         (IVFIndex.h:53) */
+VSB_API float vs_ivf_avg_cluster_size(const vs_ivf_t* h);/* IVFIndex::getAvgClusterSize (IVFIndex.h:54) */
+
+/* IVFIndex::searchBatch (IVFIndex.h:45-48, IVFIndex.cpp:640-859): coarse query x centroid scores, top-nprobe
+ * lists (nprobe clamped to nlist), fine scan, top-k by inner product.  out_ids[nq x k] original ids (-1 padded),
+ * out_scores[nq x k] descending (-inf padded), out_counts[nq] = min(k, candidates) (may be NULL),
+ * *total_candidates = rows scanned over the whole batch (the reference's return value). k <= 32. */
+VSB_API int vs_ivf_search(vs_ivf_t* h, const float* queries, int64_t nq, int k, int nprobe, int32_t* out_ids,
+                          float* out_scores, int32_t* out_counts, uint64_t* total_candidates);
+VSB_API int vs_ivf_search_dev(vs_ivf_t* h, const float* queries_dev, int64_t nq, int k, int nprobe,
+                              int32_t* out_ids_dev, float* out_scores_dev, int32_t* out_counts_dev, void* stream);
+/* Raw coarse scores [nq x nlist] (what QnnRunner::getRawOutputBuffer holds after executeBatchRaw on the float
+ * centroid model, IVFIndex.cpp:657-663). */
+VSB_API int vs_ivf_coarse_scores(vs_ivf_t* h, const float* queries, int64_t nq, float* out_scores);
+VSB_API int vs_ivf_set_profile(vs_ivf_t* h, int enable);       /* CUDA-event timing of the list-scan kernel */
+VSB_API int vs_ivf_last_kernel_ms(vs_ivf_t* h, float* ms);
+
+/* build_ivf_index (qidk_ivf/prepare/create_ivf_model.py:86-175, create_ivf_model_reordered.py:82-177): Lloyd
+ * k-means (L2) — assignment = the fused tensor-core distance + arg-min kernel, update = per-list means — then the
+ * inverted lists and the index directory (same file names, dtypes and ivf_config.json keys; no ONNX/QNN
+ * artefacts).  nlist is adjusted like the reference (nlist > n/10 -> max(16, n/100)).  init_centroids
+ * [nlist x dim] may be NULL (seeded sample of rows); with init_centroids and max_iter = 0 the given centroids are
+ * used unchanged (parity mode). reordered != 0 writes the list-contiguous layout. */
+VSB_API int vs_ivf_build(const float* base, int64_t n, int dim, int nlist, int max_iter, uint64_t seed,
+                         const char* out_dir, int reordered, int device, const float* init_centroids,
+                         int* out_nlist, int* out_iters, double* out_inertia);
 
 /* Seeded synthetic SIFT-shaped rows generated on the device (bit-identical to the numpy generator in
  * hai-25-rag-on-edge_b200/synth.py). law: 0 "sift", 1 "cont", 2 "mix". */
