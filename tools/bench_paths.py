@@ -1,0 +1,101 @@
+"""Secondary measurements (BASELINE.json configs 2-3): batch-1 exact scan (HBM-bound), IVF nlist=1024 nprobe 8/32
+list scan (HBM-bound), the GPU k-means builder.  One JSON line per path; kernel times are CUDA-event times of the
+dominant kernel on its launching stream, L2 flushed between repetitions."""
+import json
+import os
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+import torch
+
+import vsb200_loader
+
+vsb = vsb200_loader.load()
+peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"hbm_gbs": 6650.0}
+HBM = peaks["hbm_gbs"]
+dev = torch.device("cuda:0")
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+what = sys.argv[1:] or ["batch1", "ivf"]
+N, NQ, K = 1_000_000, 10_000, 10
+
+if "batch1" in what:
+    base = torch.empty((N, 128), dtype=torch.float32, device=dev)
+    vsb.synth_fill_dev(base.data_ptr(), 0, N, 128, "cont", 2025)
+    q = torch.from_numpy(vsb.synth.make("cont", 2026, 64)).to(dev)
+    qh = vsb.synth.make("cont", 2026, 64)
+    ids = torch.empty((64, K), dtype=torch.int32, device=dev)
+    d = torch.empty((64, K), dtype=torch.float32, device=dev)
+    torch.cuda.synchronize()
+    idx = vsb.ExactIndex(base.data_ptr(), n=N)
+    idx.set_profile(True)
+    st = torch.cuda.Stream()
+    for nq in (1, 2, 4, 8):
+        ts, lat = [], []
+        for it in range(12):
+            flush.fill_(1)
+            torch.cuda.synchronize()
+            idx.search_dev(q.data_ptr(), nq, K, vsb.PREC_FFMA, ids.data_ptr(), d.data_ptr(), st.cuda_stream)
+            st.synchronize()
+            ts.append(idx.last_kernel_ms())
+        for it in range(30):  # host-buffer latency of the C-ABI call (H2D + 3 kernels + D2H + sync)
+            t0 = time.perf_counter()
+            idx.search(qh[:nq], K, vsb.PREC_FFMA)
+            lat.append(1e3 * (time.perf_counter() - t0))
+        ms = float(np.median(ts[2:]))
+        gb = N * (128 * 4 + 4) / 1e9
+        print(json.dumps({"path": "exact batch-%d (exact_stream_kernel)" % nq, "kernel_ms": ms,
+                          "roofline": {"bound": "hbm", "achieved": gb / (ms * 1e-3), "peak": HBM, "unit": "GB/s",
+                                       "frac": gb / (ms * 1e-3) / HBM},
+                          "e2e_call_ms_median": float(np.median(lat[5:])), "e2e_qps": nq / (np.median(lat[5:]) * 1e-3)}))
+    idx.close()
+    del base
+
+if "ivf" in what:
+    nlist = 1024
+    t0 = time.time()
+    base_h = vsb.synth.make("mix", 2025, N)
+    t_gen = time.time() - t0
+    d_ = tempfile.mkdtemp(prefix="vsb_ivf_")
+    t0 = time.time()
+    info = vsb.ivf_build(base_h, nlist, d_, max_iter=10, seed=42, reordered=True)
+    t_build = time.time() - t0
+    off = np.load(os.path.join(d_, "cluster_offsets.npy"))
+    sizes = np.diff(off)
+    print(json.dumps({"path": "ivf build (k-means 1Mx128, nlist 1024)", "iters": info["iters"], "inertia": info["inertia"],
+                      "build_s_incl_io": t_build, "list_len_min_avg_max": [int(sizes.min()), float(sizes.mean()), int(sizes.max())]}))
+    idx = vsb.IvfIndex(d_)
+    idx.set_profile(True)
+    qh = vsb.synth.make("mix", 2026, NQ)
+    q = torch.from_numpy(qh).to(dev)
+    ids = torch.empty((NQ, K), dtype=torch.int32, device=dev)
+    sc = torch.empty((NQ, K), dtype=torch.float32, device=dev)
+    cnt = torch.empty((NQ,), dtype=torch.int32, device=dev)
+    st = torch.cuda.Stream()
+    for nprobe in (8, 32):
+        _, _, _, total = idx.search_batch(qh, K, nprobe)
+        ts, tot = [], []
+        for it in range(8):
+            flush.fill_(1)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(st)
+            idx.search_dev(q.data_ptr(), NQ, K, nprobe, ids.data_ptr(), sc.data_ptr(), cnt.data_ptr(), st.cuda_stream)
+            e1.record(st)
+            st.synchronize()
+            ts.append(idx.last_kernel_ms())
+            tot.append(e0.elapsed_time(e1))
+        t0 = time.perf_counter()
+        idx.search_batch(qh, K, nprobe)
+        e2e = time.perf_counter() - t0
+        ms = float(np.median(ts[2:]))
+        gb = total * 512 / 1e9
+        print(json.dumps({"path": "ivf nlist=1024 nprobe=%d top-10, 10K queries (ivf_scan_kernel)" % nprobe, "kernel_ms": ms,
+                          "search_ms_all_kernels": float(np.median(tot[2:])), "qps_device": NQ / (np.median(tot[2:]) * 1e-3),
+                          "qps_e2e_host_buffers": NQ / e2e, "rows_scanned": total,
+                          "roofline": {"bound": "hbm", "achieved": gb / (ms * 1e-3), "peak": HBM, "unit": "GB/s",
+                                       "frac": gb / (ms * 1e-3) / HBM, "algorithmic_bytes": total * 512}}))
+    idx.close()
