@@ -219,3 +219,78 @@ def ivf_build(base, nlist: int, out_dir: str, *, max_iter: int = 100, seed: int 
                               C.c_uint64(seed), out_dir.encode(), C.c_int(int(reordered)), C.c_int(device), _ptr(ic),
                               C.byref(nl), C.byref(it), C.byref(inertia)))
     return {"nlist": nl.value, "iters": it.value, "inertia": inertia.value}
+
+
+QNN_INPUT_SCALE = 0.6627451    # QnnRunner.cpp:70 default u8 encoding of the query tensor (169/255)
+QNN_OUTPUT_SCALE = 1013.4312   # QnnRunner.cpp:71 default u8 encoding of the score tensor
+
+
+class Int8Index:
+    """INT8 brute force (u8 x u8 -> s32 MatMul + requantisation + largest-k); mirrors the QnnRunner surface of the
+    reference's qidk_rag_demo (qidk_bruteforce/android/app/main/jni/QnnRunner.h:20-52) plus find_top_k_int8
+    (main.cpp:36-71) over the C ABI."""
+
+    def __init__(self, base, in_scale: float = QNN_INPUT_SCALE, w_scale: float = 0.0, out_scale: float = QNN_OUTPUT_SCALE,
+                 device: int = 0, id_base: int = 0, n: int | None = None, dim: int = 128):
+        self._h = C.c_void_p()
+        L = lib()
+        L.vs_int8_num_docs.restype = C.c_int64
+        L.vs_int8_output_scale.restype = C.c_float
+        args = (C.c_float(in_scale), C.c_float(w_scale), C.c_float(out_scale), C.c_int(device), C.c_int64(id_base))
+        if isinstance(base, np.ndarray):
+            base = np.ascontiguousarray(base, dtype=np.float32)
+            n, dim = base.shape
+            _check(L.vs_int8_create(C.byref(self._h), _ptr(base), C.c_int64(n), C.c_int(dim), *args))
+        else:
+            _check(L.vs_int8_create_dev(C.byref(self._h), _ptr(base), C.c_int64(n), C.c_int(dim), *args))
+        self.num_docs = int(L.vs_int8_num_docs(self._h))
+        self.dim = int(L.vs_int8_dim(self._h))
+        a, b, c, m = C.c_float(0), C.c_float(0), C.c_float(0), C.c_float(0)
+        _check(L.vs_int8_scales(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(m)))
+        self.in_scale, self.w_scale, self.out_scale, self.multiplier = a.value, b.value, c.value, m.value
+
+    def close(self) -> None:
+        if self._h:
+            lib().vs_int8_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def search(self, queries, k: int):
+        """fp32 queries (raw SIFT values) -> (ids [nq,k] int32, raw u8 scores [nq,k]), (score desc, id asc)."""
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        nq = q.shape[0]
+        ids = np.empty((nq, k), dtype=np.int32)
+        sc = np.empty((nq, k), dtype=np.uint8)
+        _check(lib().vs_int8_search(self._h, _ptr(q), C.c_int64(nq), C.c_int(k), _ptr(ids), _ptr(sc)))
+        return ids, sc
+
+    def search_dev(self, q_ptr: int, nq: int, k: int, ids_ptr: int, scores_ptr: int, stream: int = 0) -> None:
+        _check(lib().vs_int8_search_dev(self._h, _ptr(q_ptr), C.c_int64(nq), C.c_int(k), _ptr(ids_ptr), _ptr(scores_ptr),
+                                        C.c_void_p(stream)))
+
+    def scores_raw(self, queries) -> np.ndarray:
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        out = np.empty((q.shape[0], self.num_docs), dtype=np.uint8)
+        _check(lib().vs_int8_scores_raw(self._h, _ptr(q), C.c_int64(q.shape[0]), _ptr(out)))
+        return out
+
+    def set_profile(self, enable: bool = True) -> None:
+        _check(lib().vs_int8_set_profile(self._h, C.c_int(int(enable))))
+
+    def last_kernel_ms(self) -> float:
+        ms = C.c_float(0)
+        _check(lib().vs_int8_last_kernel_ms(self._h, C.byref(ms)))
+        return float(ms.value)
+
+
+def int8_quantize(x, scale: float, device: int = 0) -> np.ndarray:
+    """quantize_buffer_neon (QnnRunner.cpp:13-55) on the device."""
+    a = np.ascontiguousarray(x, dtype=np.float32)
+    out = np.empty(a.shape, dtype=np.uint8)
+    _check(lib().vs_int8_quantize(_ptr(a), C.c_int64(a.size), C.c_float(scale), _ptr(out), C.c_int(device)))
+    return out

@@ -15,7 +15,10 @@ TcPlan tc_make_plan(int64_t n, int64_t nq, int num_sms) {
     TcPlan pl{};
     pl.n_tiles = (int)ceil_div64(n, TC_BN);
     pl.n_mtiles = (int)ceil_div64(nq, TC_BM);
-    const int max_splits = std::max(1, std::min(pl.n_tiles / 16, 64));
+    // few query tiles (small batches): allow enough splits for two units per SM; many query tiles: cap the number of
+    // partial lists per query
+    const int want = std::max(64, (int)ceil_div64(2 * (int64_t)num_sms, pl.n_mtiles));
+    const int max_splits = std::max(1, std::min(pl.n_tiles / 16, want));
     int best_s = 1;
     double best_cost = 1e30;
     for (int s = 1; s <= std::max(1, max_splits); ++s) {

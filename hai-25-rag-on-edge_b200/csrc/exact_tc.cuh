@@ -256,6 +256,8 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
             const int t1 = min(t0 + p.tiles_per_split, p.n_tiles);
             const int q = m_tile * TC_BM + row;
             const bool valid = q < p.nq;
+            // whole 32-lane quadrant beyond the last query (small batches): barriers only, no TMEM traffic
+            const bool quad_live = m_tile * TC_BM + quad * 32 < p.nq;
             float lbk = -INF;
             int32_t lbi = -1;
             if (HAS_LB && valid) {
@@ -280,10 +282,11 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
                 const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * TC_BN + grp * TC_GCOLS);
                 const float* bn_s = sN + acc * TC_BN + grp * TC_GCOLS;
                 uint32_t r[2][32];
-                if (!(p.dbg & 1)) tmem_ld32(taddr, r[0]);
+                const bool skip = (p.dbg & 1) || !quad_live;
+                if (!skip) tmem_ld32(taddr, r[0]);
 #pragma unroll
                 for (int c = 0; c < CH; ++c) {
-                    if (p.dbg & 1) break;
+                    if (skip) break;
                     tc_wait_ld();
                     if (c + 1 < CH) tmem_ld32(taddr + (c + 1) * 32, r[(c + 1) & 1]);
                     const int col0 = t * TC_BN + grp * TC_GCOLS + c * 32;

@@ -59,7 +59,19 @@ int launch_ivf_scan(const CUtensorMap& tmV, const float* q, const int32_t* probe
 int ivf_set_attributes();
 int ivf_scan_rows_per_chunk();
 
-// api.cu helpers shared with api_ivf.cu
+// int8_tc.cu -----------------------------------------------------------------------------------
+// K4: u8 = sat(trunc(x * inv_scale + 0.5)) (QnnRunner.cpp:13-55); K5: fused u8 x u8 -> s32 tcgen05 GEMM + requant +
+// largest-k, partial lists keyed by -score; helpers for the raw score matrix and the weight scale.
+int launch_quantize_u8(const float* src, int64_t count, float inv_scale, uint8_t* dst, cudaStream_t st);
+int launch_scores_to_u8(const float* src, int64_t count, uint8_t* dst, cudaStream_t st);
+int launch_int8_scores(const uint8_t* base, int64_t n, const uint8_t* q, int64_t nq, float m, uint8_t* out, cudaStream_t st);
+int launch_max_f32(const float* x, int64_t count, float* out_zeroed, cudaStream_t st);
+int int8_set_attributes();
+int int8_lists_per_split();
+int launch_int8_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, int32_t* gthr, float m, int nq, int64_t n, const TcPlan& plan,
+                   int ktop, float* part_key, int32_t* part_id, cudaStream_t st);
+
+// api.cu helpers shared with api_ivf.cu / api_int8.cu
 int make_tmap_2d(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_t cols, int elem_bytes, uint32_t box_rows);
 
 int round_up_ktop(int k);  // smallest supported register-list size >= k (1,5,10,16,32), 0 if k > 32

@@ -230,16 +230,17 @@ struct RegTopK {
 };
 
 // value d[j] for a run-time j without dynamic register indexing: 5-level multiplexer (31 selects)
-__device__ __forceinline__ float select32(const float (&d)[32], int j) {
-    float a[16], b[8], c[4];
+template <class T>
+__device__ __forceinline__ T select32(const T (&d)[32], int j) {
+    T a[16], b[8], c[4];
 #pragma unroll
     for (int i = 0; i < 16; ++i) a[i] = (j & 16) ? d[i + 16] : d[i];
 #pragma unroll
     for (int i = 0; i < 8; ++i) b[i] = (j & 8) ? a[i + 8] : a[i];
 #pragma unroll
     for (int i = 0; i < 4; ++i) c[i] = (j & 4) ? b[i + 4] : b[i];
-    const float e0 = (j & 2) ? c[2] : c[0];
-    const float e1 = (j & 2) ? c[3] : c[1];
+    const T e0 = (j & 2) ? c[2] : c[0];
+    const T e1 = (j & 2) ? c[3] : c[1];
     return (j & 1) ? e1 : e0;
 }
 

@@ -153,6 +153,44 @@ VSB_API int vs_ivf_build(const float* base, int64_t n, int dim, int nlist, int m
                          const char* out_dir, int reordered, int device, const float* init_centroids,
                          int* out_nlist, int* out_iters, double* out_inertia);
 
+/* ---------------------------------------------------------------------------------------------- */
+/* INT8 brute force (the QNN u8 MatMul path)                                                       */
+/* ---------------------------------------------------------------------------------------------- */
+typedef struct vs_int8 vs_int8_t;
+
+/* Replaces QnnRunner::QnnRunner (qidk_bruteforce/.../QnnRunner.h:20, QnnRunner.cpp:57-83): where the reference
+ * loads a QNN context binary whose MatMul weights are the u8-quantised documents (create_model.py:57-87 +
+ * convert_to_qnn.sh), this quantises base[n x dim] (fp32, raw SIFT values) once with
+ *   w = sat_u8(trunc(x * (1/w_scale) + 0.5))      (w_scale <= 0: max(base)/255, the converter's min/max rule)
+ * and keeps it resident.  in_scale / out_scale are the u8 encodings of the graph input and output
+ * (QnnRunner.cpp:70-71 defaults 0.6627451 and 1013.4312; offsets 0).  Scores are
+ *   sat_u8(floor(fl(fl(acc) * m) + 0.5)),  acc = sum q_u8*w_u8 (int32),  m = fl(fl(in_scale*w_scale)/out_scale)
+ * — the requantisation rule is defined by this project (the HTP's is proprietary), see DESIGN.md. */
+VSB_API int vs_int8_create(vs_int8_t** out, const float* base, int64_t n, int dim, float in_scale, float w_scale,
+                           float out_scale, int device, int64_t id_base);
+VSB_API int vs_int8_create_dev(vs_int8_t** out, const float* base_dev, int64_t n, int dim, float in_scale, float w_scale,
+                               float out_scale, int device, int64_t id_base);
+VSB_API int vs_int8_destroy(vs_int8_t* h);
+VSB_API int64_t vs_int8_num_docs(const vs_int8_t* h);      /* QnnRunner::getNumDocs     (QnnRunner.h:49) */
+VSB_API int vs_int8_dim(const vs_int8_t* h);               /* QnnRunner::getDim         (QnnRunner.h:48) */
+VSB_API float vs_int8_output_scale(const vs_int8_t* h);    /* QnnRunner::getOutputScale (QnnRunner.h:51) */
+VSB_API int vs_int8_scales(const vs_int8_t* h, float* in_scale, float* w_scale, float* out_scale, float* multiplier);
+/* executeBatchRaw + find_top_k_int8 fused (QnnRunner.cpp:597-638, main.cpp:36-71): fp32 queries are quantised with
+ * quantize_buffer_neon's rule (QnnRunner.cpp:13-55); out_ids[nq x k], out_scores[nq x k] raw u8, ordered
+ * (score descending, id ascending); the printed score of the reference is out_scores * out_scale (main.cpp:185).
+ * Any nq (the reference's fixed model batch + zero padding, main.cpp:206-211, is not needed). k <= 32. */
+VSB_API int vs_int8_search(vs_int8_t* h, const float* queries, int64_t nq, int k, int32_t* out_ids, uint8_t* out_scores);
+VSB_API int vs_int8_search_dev(vs_int8_t* h, const float* queries_dev, int64_t nq, int k, int32_t* out_ids_dev,
+                               uint8_t* out_scores_dev, void* stream);
+/* The whole raw u8 score matrix [nq x n] (QnnRunner::getRawOutputBuffer after executeBatchRaw, QnnRunner.h:41);
+ * for tests and small n only (nq*n <= 4e9). */
+VSB_API int vs_int8_scores_raw(vs_int8_t* h, const float* queries, int64_t nq, uint8_t* out_scores);
+/* quantize_buffer_neon on the device for host buffers (QnnRunner.cpp:13-55), scale as in the reference's callers
+ * (inv_scale = 1.0f / scale in fp32). */
+VSB_API int vs_int8_quantize(const float* src, int64_t count, float scale, uint8_t* dst, int device);
+VSB_API int vs_int8_set_profile(vs_int8_t* h, int enable);     /* CUDA-event timing of the fused INT8 kernel */
+VSB_API int vs_int8_last_kernel_ms(vs_int8_t* h, float* ms);
+
 /* Seeded synthetic SIFT-shaped rows generated on the device (bit-identical to the numpy generator in
  * hai-25-rag-on-edge_b200/synth.py). law: 0 "sift", 1 "cont", 2 "mix". */
 VSB_API int vs_synth_fill_dev(float* out_dev, int64_t row0, int64_t nrows, int dim, int law, uint64_t seed,

@@ -19,7 +19,7 @@ peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.ex
 HBM = peaks["hbm_gbs"]
 dev = torch.device("cuda:0")
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-what = sys.argv[1:] or ["batch1", "ivf"]
+what = sys.argv[1:] or ["batch1", "ivf", "int8"]
 N, NQ, K = 1_000_000, 10_000, 10
 
 if "batch1" in what:
@@ -98,4 +98,50 @@ if "ivf" in what:
                           "qps_e2e_host_buffers": NQ / e2e, "rows_scanned": total,
                           "roofline": {"bound": "hbm", "achieved": gb / (ms * 1e-3), "peak": HBM, "unit": "GB/s",
                                        "frac": gb / (ms * 1e-3) / HBM, "algorithmic_bytes": total * 512}}))
+    idx.close()
+
+if "int8" in what:
+    # BASELINE configs[3]: 10M x 128 u8 base (1.28 GB), batches of 32 and 1024 queries, top-10
+    NI = 10_000_000
+    base = torch.empty((NI, 128), dtype=torch.float32, device=dev)
+    vsb.synth_fill_dev(base.data_ptr(), 0, NI, 128, "mix", 2025)
+    torch.cuda.synchronize()
+    idx = vsb.Int8Index(base.data_ptr(), 218.0 / 255.0, 218.0 / 255.0, 9000.0, n=NI)
+    del base
+    torch.cuda.empty_cache()
+    idx.set_profile(True)
+    peak_bf16 = peaks.get("bf16_tflops", 1590.0)
+    st = torch.cuda.Stream()
+    for nq in (32, 1024):
+        qh = vsb.synth.make("mix", 2026, nq)
+        q = torch.from_numpy(qh).to(dev)
+        ids = torch.empty((nq, K), dtype=torch.int32, device=dev)
+        sc = torch.empty((nq, K), dtype=torch.uint8, device=dev)
+        ts, tot = [], []
+        for it in range(10):
+            flush.fill_(1)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(st)
+            idx.search_dev(q.data_ptr(), nq, K, ids.data_ptr(), sc.data_ptr(), st.cuda_stream)
+            e1.record(st)
+            st.synchronize()
+            ts.append(idx.last_kernel_ms())
+            tot.append(e0.elapsed_time(e1))
+        lat = []
+        for it in range(10):
+            t0 = time.perf_counter()
+            idx.search(qh, K)
+            lat.append(time.perf_counter() - t0)
+        ms = float(np.median(ts[2:]))
+        line = {"path": "int8 brute force 10Mx128 batch-%d top-10 (int8_tc_kernel)" % nq, "kernel_ms": ms,
+                "search_ms_all_kernels": float(np.median(tot[2:])), "qps_device": nq / (np.median(tot[2:]) * 1e-3),
+                "qps_e2e_host_buffers": nq / float(np.median(lat[2:]))}
+        gb = NI * 128 / 1e9
+        tops = 2.0 * nq * NI * 128 / 1e12
+        line["roofline_hbm"] = {"bound": "hbm", "achieved": gb / (ms * 1e-3), "peak": HBM, "unit": "GB/s", "frac": gb / (ms * 1e-3) / HBM}
+        line["roofline_tensor"] = {"bound": "tensor", "achieved": tops / (ms * 1e-3), "peak": 2 * peak_bf16, "unit": "TOP/s",
+                                   "frac": tops / (ms * 1e-3) / (2 * peak_bf16), "issued_frac_m128_tiles": (2.0 * ((nq + 127) // 128 * 128) * NI * 128 / 1e12) / (ms * 1e-3) / (2 * peak_bf16),
+                                   "peak_note": "int8 dense = 2 x MEASURED_PEAKS bf16 burst"}
+        print(json.dumps(line))
     idx.close()
