@@ -141,7 +141,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default="3xtf32", choices=["3xtf32", "auto", "1xtf32", "ffma"])
+    ap.add_argument("--precision", default="auto", choices=["auto", "f16cert", "3xtf32", "1xtf32", "ffma"])
     ap.add_argument("--nq", type=int, default=N_QUERY)
     ap.add_argument("--cpu-sample", type=int, default=128, help="queries timed on the CPU reference (bounded sample)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
@@ -192,7 +192,8 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    prec = {"3xtf32": vsb.PREC_3XTF32, "auto": vsb.PREC_AUTO, "1xtf32": vsb.PREC_TF32_1X, "ffma": vsb.PREC_FFMA}[args.precision]
+    prec = {"3xtf32": vsb.PREC_3XTF32, "auto": vsb.PREC_AUTO, "1xtf32": vsb.PREC_TF32_1X, "ffma": vsb.PREC_FFMA,
+            "f16cert": vsb.PREC_F16_CERT}[args.precision]
     nq, k = args.nq, TOPK
 
     # base shard of this rank, generated on the device (bit-identical to the numpy generator)
@@ -288,6 +289,7 @@ def main():
         t_dev += timed(dev_fn, 1)
         kernel_ms.append(index.last_kernel_ms())
     launches, prec_used = index.last_launches()
+    fallbacks = index.last_fallbacks()
     t_e2e = timed(e2e_step, args.steps, use_events=False)  # wall clock: the host-buffer call blocks the host
     barrier()
     clocks = sampler.stop() if rank == 0 else None
@@ -316,6 +318,13 @@ def main():
             alg_bytes = n_local * (DIM * 4 + 4)  # first launch: one pass over the shard
             roof = {"bound": "hbm", "achieved": alg_bytes / (ms_kernel * 1e-3) / 1e9, "peak": pk["hbm_gbs"],
                     "unit": "GB/s", "traffic": None, "kernel": "exact_stream_kernel (first of %d passes)" % passes}
+        elif prec_used == vsb.PREC_F16_CERT:
+            # one fp16 product per (query, row, dim): 2*Q*N*128 flop on the f16/bf16 tensor pipe (DESIGN.md "Roofline")
+            flops = 2.0 * nq * n_local * DIM
+            roof = {"bound": "tensor", "achieved": flops / (ms_kernel * 1e-3) / 1e12, "peak": pk["bf16"],
+                    "unit": "TFLOP/s", "traffic": None, "kernel": "exact_tc_kernel<32, F16>", "tf32_products": 0,
+                    "algorithmic_fp32_tflops": flops / (ms_kernel * 1e-3) / 1e12,
+                    "peak_note": f"fp16/bf16 dense = MEASURED_PEAKS bf16 burst ({pk['src']})"}
         else:
             # tensor work issued by the fused kernel for this rank's shard: 2*Q*N*128 flop per TF32 product, 3
             # products for the fp32-faithful split (DESIGN.md "Roofline")
@@ -332,7 +341,8 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{N_BASE}x{DIM} fp32 base, {nq} queries/step, exact L2 top-{k}, law={LAW}",
-                       "precision": vsb.PREC_NAMES[prec_used], "base_rows_per_gpu": n_local,
+                       "precision": vsb.PREC_NAMES[prec_used], "uncertified_queries_redone_in_fp32": fallbacks,
+                       "base_rows_per_gpu": n_local,
                        "parallelism": f"base rows sharded x{world}, queries replicated, all-gather + merge" if world > 1 else "single GPU",
                        "cache": "L2 flushed (256 MB write) between timed steps; operands (0.5-1 GB) exceed the 126 MB L2"},
             "e2e": {"value": nq / (ms_e2e * 1e-3), "unit": "queries/s", "ms_per_step": ms_e2e,

@@ -18,8 +18,8 @@ from . import synth  # noqa: F401  (re-exported: seeded synthetic SIFT-shaped da
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libvsb200.so")
 
-PREC_AUTO, PREC_3XTF32, PREC_FFMA, PREC_TF32_1X = 0, 1, 2, 3
-PREC_NAMES = {0: "auto", 1: "fp32_3xtf32", 2: "fp32_ffma", 3: "tf32_1x"}
+PREC_AUTO, PREC_3XTF32, PREC_FFMA, PREC_TF32_1X, PREC_F16_CERT = 0, 1, 2, 3, 4
+PREC_NAMES = {0: "auto", 1: "fp32_3xtf32", 2: "fp32_ffma", 3: "tf32_1x", 4: "f16_certified+fp32_refine"}
 
 
 class VsbError(RuntimeError):
@@ -127,6 +127,12 @@ class ExactIndex:
         a, b = C.c_int(0), C.c_int(0)
         _check(lib().vs_exact_last_launches(self._h, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+    def last_fallbacks(self) -> int:
+        """queries of the last certified search that had to be redone on the fp32 path"""
+        a = C.c_int(0)
+        _check(lib().vs_exact_last_fallbacks(self._h, C.byref(a)))
+        return a.value
 
 
 def merge_topk_dev(ids_ptr: int, keys_ptr: int, n_shards: int, nq: int, k: int, smallest: bool, out_ids_ptr: int,

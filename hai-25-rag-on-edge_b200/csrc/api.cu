@@ -43,7 +43,9 @@ static encode_tiled_fn get_encode_fn() {
 int make_tmap_2d(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_t cols, int elem_bytes, uint32_t box_rows) {
     encode_tiled_fn fn = get_encode_fn();
     if (!fn) return fail(VS_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
-    const CUtensorMapDataType dt = elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT8;
+    const CUtensorMapDataType dt = elem_bytes == 4   ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                   : elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+                                                     : CU_TENSOR_MAP_DATA_TYPE_UINT8;
     cuuint64_t gdim[2] = {cols, rows};
     cuuint64_t gstr[1] = {cols * (uint64_t)elem_bytes};
     cuuint32_t box[2] = {(cuuint32_t)(128 / elem_bytes), box_rows};
@@ -66,17 +68,23 @@ struct vs_exact {
     int64_t id_base = 0;
     bool owns_base = false;
     const float* d_base = nullptr;  // [n x dim] fp32
-    float* d_hi = nullptr;          // TF32 split (dim == 128 only); d_hi aliases d_base when the base is TF32-exact
-    float* d_lo = nullptr;
+    float* d_hi = nullptr;          // TF32 split, built on first use (dim == 128 only); d_hi aliases d_base when the
+    float* d_lo = nullptr;          // base is TF32-exact
+    bool split_ready = false;
+    void* d_f16 = nullptr;          // [n x 128] fp16 copy scaled by s_b (candidate pass)
+    float s_b = 1.f;                // power-of-two scale of the fp16 copy
+    float bn_max = 0.f;             // max ||x||^2
     float* d_norm = nullptr;        // [n_tiles*128] +inf padded
     bool base_exact = false;
-    CUtensorMap tmB_hi, tmB_lo;
+    CUtensorMap tmB_hi, tmB_lo, tmB_f16;
     cudaStream_t stream = nullptr;
     // workspace (grow-only)
-    DevBuf q, qhi, qlo, qnorm, part_key, part_id, lbk, lbi, out_ids, out_keys, flag, gthr;
-    int* h_flag = nullptr;  // pinned
+    DevBuf q, qhi, qlo, qf16, qnorm, part_key, part_id, lbk, lbi, out_ids, out_keys, flag, gthr, qparams, unc_list, fb_q,
+        fb_ids, fb_keys;
+    int* h_flag = nullptr;  // pinned: [0] exactness flag, [1] uncertified count
     int last_launches = 0;
     int last_precision = 0;
+    int last_fallback = 0;
     // optional CUDA-event timing of the dominant kernel (bench.py's roofline line)
     bool profile = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -90,9 +98,10 @@ static int exact_free(vs_exact* h) {
     if (h->owns_base && h->d_base) cudaFree((void*)h->d_base);
     if (h->d_hi && h->d_hi != h->d_base) cudaFree(h->d_hi);
     if (h->d_lo) cudaFree(h->d_lo);
+    if (h->d_f16) cudaFree(h->d_f16);
     if (h->d_norm) cudaFree(h->d_norm);
-    for (DevBuf* b : {&h->q, &h->qhi, &h->qlo, &h->qnorm, &h->part_key, &h->part_id, &h->lbk, &h->lbi, &h->out_ids,
-                      &h->out_keys, &h->flag, &h->gthr})
+    for (DevBuf* b : {&h->q, &h->qhi, &h->qlo, &h->qf16, &h->qnorm, &h->part_key, &h->part_id, &h->lbk, &h->lbi, &h->out_ids,
+                      &h->out_keys, &h->flag, &h->gthr, &h->qparams, &h->unc_list, &h->fb_q, &h->fb_ids, &h->fb_keys})
         b->release();
     if (h->h_flag) cudaFreeHost(h->h_flag);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -102,37 +111,63 @@ static int exact_free(vs_exact* h) {
     return VS_OK;
 }
 
+// flag buffer layout (device, 4 words): [0] "not TF32-exact" flag, [1] uncertified-query count, [2] abs-max bits
+// (queries), [3] scratch for max reductions at build time
 static int exact_build(vs_exact* h) {
     const int64_t n = h->n;
     const int dim = h->dim;
     const int64_t n_pad = ceil_div64(n, 128) * 128;
     VSB_CUDA(cudaMalloc((void**)&h->d_norm, sizeof(float) * (size_t)n_pad));
     VSB_TRY(launch_fill_f32(h->d_norm, n_pad, __builtin_inff(), h->stream));
-    VSB_TRY(h->flag.reserve(sizeof(int)));
-    VSB_CUDA(cudaMallocHost((void**)&h->h_flag, sizeof(int)));
-    VSB_CUDA(cudaMemsetAsync(h->flag.p, 0, sizeof(int), h->stream));
+    VSB_TRY(h->flag.reserve(4 * sizeof(int)));
+    if (!h->h_flag) VSB_CUDA(cudaMallocHost((void**)&h->h_flag, 4 * sizeof(int)));
+    VSB_CUDA(cudaMemsetAsync(h->flag.p, 0, 4 * sizeof(int), h->stream));
+    // norms in the reference's order + "is every component TF32-representable"
+    VSB_TRY(launch_prep_rows(h->d_base, n, dim, h->d_norm, nullptr, nullptr, h->flag.as<int>(), h->stream));
     if (dim == 128) {
-        VSB_CUDA(cudaMalloc((void**)&h->d_hi, sizeof(float) * (size_t)n * dim));
-        VSB_CUDA(cudaMalloc((void**)&h->d_lo, sizeof(float) * (size_t)n * dim));
-        VSB_TRY(launch_prep_rows(h->d_base, n, dim, h->d_norm, h->d_hi, h->d_lo, h->flag.as<int>(), h->stream));
-        VSB_CUDA(cudaMemcpyAsync(h->h_flag, h->flag.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        // scaled fp16 copy for the certified candidate pass: abs-max -> power-of-two scale; max norm for the bound
+        float* scratch = reinterpret_cast<float*>(h->flag.as<int>() + 3);
+        VSB_TRY(launch_absmax_f32(h->d_base, n * dim, scratch, h->stream));
+        VSB_CUDA(cudaMemcpyAsync(h->h_flag, h->flag.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
         VSB_CUDA(cudaStreamSynchronize(h->stream));
-        h->base_exact = (*h->h_flag == 0);
-        if (h->base_exact) {  // hi == x and lo == 0: keep one copy
-            cudaFree(h->d_hi);
-            cudaFree(h->d_lo);
-            h->d_hi = const_cast<float*>(h->d_base);
-            h->d_lo = nullptr;
-        }
-        VSB_TRY(make_tmap_2d(&h->tmB_hi, h->d_hi, (uint64_t)n, 128, 4, 128));
-        if (h->d_lo)
-            VSB_TRY(make_tmap_2d(&h->tmB_lo, h->d_lo, (uint64_t)n, 128, 4, 128));
-        else
-            h->tmB_lo = h->tmB_hi;
+        h->base_exact = (h->h_flag[0] == 0);
+        float absmax;
+        memcpy(&absmax, &h->h_flag[3], sizeof(float));
+        h->s_b = f16_scale_host(absmax);
+        VSB_CUDA(cudaMemsetAsync(scratch, 0, sizeof(float), h->stream));
+        VSB_TRY(launch_absmax_f32(h->d_norm, n, scratch, h->stream));
+        VSB_CUDA(cudaMemcpyAsync(&h->h_flag[3], scratch, sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+        VSB_CUDA(cudaMalloc(&h->d_f16, 2 * (size_t)n * dim));
+        VSB_TRY(launch_to_half_scaled(h->d_base, n * dim, h->s_b, nullptr, h->d_f16, h->stream));
+        VSB_CUDA(cudaStreamSynchronize(h->stream));
+        memcpy(&h->bn_max, &h->h_flag[3], sizeof(float));
+        VSB_TRY(make_tmap_2d(&h->tmB_f16, h->d_f16, (uint64_t)n, 128, 2, 128));
         VSB_TRY(tc_set_attributes());
     } else {
-        VSB_TRY(launch_prep_rows(h->d_base, n, dim, h->d_norm, nullptr, nullptr, nullptr, h->stream));
         VSB_CUDA(cudaStreamSynchronize(h->stream));
+    }
+    return VS_OK;
+}
+
+// TF32 hi/lo split of the base (2x the base bytes), built the first time a TF32 search needs it
+static int exact_ensure_split(vs_exact* h, bool need_lo, cudaStream_t st) {
+    if (!h->split_ready) {
+        if (h->base_exact) {  // hi == x and lo == 0: no copy
+            h->d_hi = const_cast<float*>(h->d_base);
+        } else {
+            VSB_CUDA(cudaMalloc((void**)&h->d_hi, sizeof(float) * (size_t)h->n * 128));
+            VSB_CUDA(cudaMalloc((void**)&h->d_lo, sizeof(float) * (size_t)h->n * 128));
+            VSB_TRY(launch_prep_rows(h->d_base, h->n, 128, nullptr, h->d_hi, h->d_lo, nullptr, st));
+            VSB_TRY(make_tmap_2d(&h->tmB_lo, h->d_lo, (uint64_t)h->n, 128, 4, 128));
+        }
+        VSB_TRY(make_tmap_2d(&h->tmB_hi, h->d_hi, (uint64_t)h->n, 128, 4, 128));
+        if (!h->d_lo) h->tmB_lo = h->tmB_hi;
+        h->split_ready = true;
+    }
+    if (need_lo && !h->d_lo) {  // 3x search over a TF32-exact base: a real zero lo operand keeps the arithmetic honest
+        VSB_CUDA(cudaMalloc((void**)&h->d_lo, sizeof(float) * (size_t)h->n * 128));
+        VSB_CUDA(cudaMemsetAsync(h->d_lo, 0, sizeof(float) * (size_t)h->n * 128, st));
+        VSB_TRY(make_tmap_2d(&h->tmB_lo, h->d_lo, (uint64_t)h->n, 128, 4, 128));
     }
     return VS_OK;
 }
@@ -194,20 +229,91 @@ static int exact_create_common(vs_exact_t** out, const float* base, bool on_devi
     return VS_OK;
 }
 
+static int exact_search_core(vs_exact* h, const float* q_dev, int64_t nq, int k, int precision, int32_t* out_ids,
+                             float* out_dists, cudaStream_t st);
+
+// Certified candidate pass: scaled fp16 tensor-core kernel keeps the 32 best keys per query (error bounded by
+// cert_a*sqrt(qn)+cert_b), the merge kernel recomputes those 32 distances in exact fp32, ranks them and certifies
+// the top k; the (rare) uncertified queries are redone on the 3xTF32 / FFMA path.  Synchronises `st` once (4-byte
+// count of uncertified queries).
+static int exact_search_certified(vs_exact* h, const float* q_dev, int64_t nq, int k, int32_t* out_ids, float* out_dists,
+                                  cudaStream_t st) {
+    const int ktop = kMaxRegK;
+    int* flag = h->flag.as<int>();
+    VSB_TRY(h->qf16.reserve(2 * (size_t)nq * 128));
+    VSB_TRY(h->qparams.reserve(sizeof(TcQueryParams)));
+    VSB_TRY(h->unc_list.reserve(sizeof(int32_t) * (size_t)nq));
+    VSB_CUDA(cudaMemsetAsync(flag + 1, 0, 2 * sizeof(int), st));
+    VSB_TRY(launch_prep_rows(q_dev, nq, 128, h->qnorm.as<float>(), nullptr, nullptr, nullptr, st));
+    VSB_TRY(launch_absmax_f32(q_dev, nq * 128, reinterpret_cast<float*>(flag + 2), st));
+    TcQueryParams* qp = h->qparams.as<TcQueryParams>();
+    VSB_TRY(launch_tc_query_params(reinterpret_cast<const float*>(flag + 2), h->s_b, h->bn_max, qp, st));
+    VSB_TRY(launch_to_half_scaled(q_dev, nq * 128, 1.f, qp, h->qf16.p, st));
+    const TcPlan plan = tc_make_plan(h->n, nq, h->num_sms);
+    const int n_lists = plan.n_splits * tc_lists_per_split();
+    VSB_TRY(h->part_key.reserve(sizeof(float) * (size_t)n_lists * nq * ktop));
+    VSB_TRY(h->part_id.reserve(sizeof(int32_t) * (size_t)n_lists * nq * ktop));
+    VSB_TRY(h->gthr.reserve(sizeof(int32_t) * (size_t)nq));
+    VSB_CUDA(cudaMemsetAsync(h->gthr.p, 0x7f, sizeof(int32_t) * (size_t)nq, st));
+    CUtensorMap tmA;
+    VSB_TRY(make_tmap_2d(&tmA, h->qf16.p, (uint64_t)nq, 128, 2, 128));
+    if (h->profile) VSB_CUDA(cudaEventRecord(h->ev0, st));
+    VSB_TRY(launch_exact_tc(tmA, tmA, h->tmB_f16, h->tmB_f16, h->d_norm, h->gthr.as<int32_t>(), (int)nq, plan, ktop, 2,
+                            &qp->key_scale, nullptr, nullptr, h->part_key.as<float>(), h->part_id.as<int32_t>(), st));
+    if (h->profile) {
+        VSB_CUDA(cudaEventRecord(h->ev1, st));
+        h->ev_valid = true;
+    }
+    VSB_TRY(launch_merge_lists(h->part_key.as<float>(), h->part_id.as<int32_t>(), n_lists, nq, ktop, ktop, k, h->id_base, 0, 0,
+                               out_dists, out_ids, k, 0, nullptr, nullptr, h->d_base, h->d_norm, q_dev, h->qnorm.as<float>(), st,
+                               qp, flag + 1, h->unc_list.as<int32_t>()));
+    h->last_launches = 6;
+    h->last_precision = VS_PREC_F16_CERTIFIED;
+    VSB_CUDA(cudaMemcpyAsync(h->h_flag + 1, flag + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+    VSB_CUDA(cudaStreamSynchronize(st));
+    const int n_unc = h->h_flag[1];
+    h->last_fallback = n_unc;
+    if (n_unc > 0) {
+        VSB_TRY(h->fb_q.reserve(sizeof(float) * (size_t)n_unc * 128));
+        VSB_TRY(h->fb_ids.reserve(sizeof(int32_t) * (size_t)n_unc * k));
+        VSB_TRY(h->fb_keys.reserve(sizeof(float) * (size_t)n_unc * k));
+        VSB_TRY(launch_gather_rows(q_dev, h->unc_list.as<int32_t>(), n_unc, h->fb_q.as<float>(), st));
+        const int launches = h->last_launches;
+        const bool prof = h->profile;
+        h->profile = false;  // keep the timing of the dominant (candidate) kernel
+        const int rc = exact_search_core(h, h->fb_q.as<float>(), n_unc, k, n_unc <= 8 ? VS_PREC_FP32_FFMA : VS_PREC_FP32_3XTF32,
+                                         h->fb_ids.as<int32_t>(), h->fb_keys.as<float>(), st);
+        h->profile = prof;
+        VSB_TRY(rc);
+        VSB_TRY(launch_scatter_results(h->fb_keys.as<float>(), h->fb_ids.as<int32_t>(), h->unc_list.as<int32_t>(), n_unc, k,
+                                       out_dists, out_ids, st));
+        h->last_launches += launches + 2;
+        h->last_precision = VS_PREC_F16_CERTIFIED;
+        h->last_fallback = n_unc;
+    }
+    return VS_OK;
+}
+
 // One group of <= 32 results per query: [pass]
 static int exact_search_core(vs_exact* h, const float* q_dev, int64_t nq, int k, int precision, int32_t* out_ids,
                              float* out_dists, cudaStream_t st) {
     h->last_launches = 0;
+    h->last_fallback = 0;
     if (nq == 0) return VS_OK;
     const int dim = h->dim;
     int prec = precision;
-    if (prec != VS_PREC_AUTO && prec != VS_PREC_FP32_3XTF32 && prec != VS_PREC_FP32_FFMA && prec != VS_PREC_TF32_1X)
+    if (prec != VS_PREC_AUTO && prec != VS_PREC_FP32_3XTF32 && prec != VS_PREC_FP32_FFMA && prec != VS_PREC_TF32_1X &&
+        prec != VS_PREC_F16_CERTIFIED)
         return fail(VS_ERR_INVALID, "unknown precision");
     if (nq > 0x7fffffff / 128) return fail(VS_ERR_INVALID, "nq too large");
-    const bool want_tc = (prec == VS_PREC_FP32_3XTF32 || prec == VS_PREC_TF32_1X || (prec == VS_PREC_AUTO && nq > 16));
+    if (prec == VS_PREC_F16_CERTIFIED && k > 16) return fail(VS_ERR_UNSUPPORTED, "certified fp16 candidate pass needs k <= 16");
+    if (prec == VS_PREC_AUTO && nq > 16 && k <= 16 && dim == 128) prec = VS_PREC_F16_CERTIFIED;
+    const bool want_tc = (prec == VS_PREC_FP32_3XTF32 || prec == VS_PREC_TF32_1X || prec == VS_PREC_F16_CERTIFIED ||
+                          (prec == VS_PREC_AUTO && nq > 16));
     if (want_tc && dim != 128) return fail(VS_ERR_UNSUPPORTED, "tensor-core path needs dim == 128");
 
     VSB_TRY(h->qnorm.reserve(sizeof(float) * (size_t)nq));
+    if (prec == VS_PREC_F16_CERTIFIED) return exact_search_certified(h, q_dev, nq, k, out_ids, out_dists, st);
     const int passes = (k + kMaxRegK - 1) / kMaxRegK;
     // single pass: keep a couple of spare candidates beyond k so that the exact refine can repair a k-th/k+1-th
     // swap caused by the tensor-core rounding bias
@@ -231,10 +337,10 @@ static int exact_search_core(vs_exact* h, const float* q_dev, int64_t nq, int k,
             if (h->base_exact) {  // 1xTF32 is bit-identical to 3xTF32 iff the query lo parts are all zero too
                 VSB_CUDA(cudaMemcpyAsync(h->h_flag, h->flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
                 VSB_CUDA(cudaStreamSynchronize(st));
-                split3 = (*h->h_flag != 0);
+                split3 = (h->h_flag[0] != 0);
             }
         }
-        if (split3 && !h->d_lo && !h->base_exact) return fail(VS_ERR_INVALID, "internal: lo split missing");
+        VSB_TRY(exact_ensure_split(h, split3, st));
         h->last_precision = split3 ? VS_PREC_FP32_3XTF32 : VS_PREC_TF32_1X;
         const TcPlan plan = tc_make_plan(h->n, nq, h->num_sms);
         const int n_lists = plan.n_splits * tc_lists_per_split();
@@ -244,14 +350,6 @@ static int exact_search_core(vs_exact* h, const float* q_dev, int64_t nq, int k,
         CUtensorMap tmA_hi, tmA_lo;
         VSB_TRY(make_tmap_2d(&tmA_hi, h->qhi.p, (uint64_t)nq, 128, 4, 128));
         VSB_TRY(make_tmap_2d(&tmA_lo, h->qlo.p, (uint64_t)nq, 128, 4, 128));
-        // base lo == 0 (TF32-exact base): the q_hi.x_lo product vanishes; the kernel still issues it against
-        // the hi map's zero... no: keep arithmetic honest — with an exact base the lo map aliases hi only when
-        // split3 is false (never read).  A 3x search over an exact base needs a real zero lo operand:
-        if (split3 && !h->d_lo) {
-            VSB_CUDA(cudaMalloc((void**)&h->d_lo, sizeof(float) * (size_t)h->n * 128));
-            VSB_CUDA(cudaMemsetAsync(h->d_lo, 0, sizeof(float) * (size_t)h->n * 128, st));
-            VSB_TRY(make_tmap_2d(&h->tmB_lo, h->d_lo, (uint64_t)h->n, 128, 4, 128));
-        }
         for (int pass = 0; pass < passes; ++pass) {
             const int kk = std::min(kMaxRegK, k - pass * kMaxRegK);
             const bool lb = pass > 0;
@@ -259,8 +357,8 @@ static int exact_search_core(vs_exact* h, const float* q_dev, int64_t nq, int k,
             VSB_CUDA(cudaMemsetAsync(h->gthr.p, 0x7f, sizeof(int32_t) * (size_t)nq, st));
             if (h->profile && pass == 0) VSB_CUDA(cudaEventRecord(h->ev0, st));
             VSB_TRY(launch_exact_tc(tmA_hi, tmA_lo, h->tmB_hi, h->tmB_lo, h->d_norm, h->gthr.as<int32_t>(), (int)nq, plan,
-                                    ktop, split3, lb ? h->lbk.as<float>() : nullptr, lb ? h->lbi.as<int32_t>() : nullptr,
-                                    h->part_key.as<float>(), h->part_id.as<int32_t>(), st));
+                                    ktop, split3 ? 1 : 0, nullptr, lb ? h->lbk.as<float>() : nullptr,
+                                    lb ? h->lbi.as<int32_t>() : nullptr, h->part_key.as<float>(), h->part_id.as<int32_t>(), st));
             if (h->profile && pass == 0) {
                 VSB_CUDA(cudaEventRecord(h->ev1, st));
                 h->ev_valid = true;
@@ -347,10 +445,11 @@ int vs_exact_refresh(vs_exact_t* h) {
     VSB_CUDA(cudaStreamSynchronize(h->stream));
     if (h->d_hi && h->d_hi != h->d_base) cudaFree(h->d_hi);
     if (h->d_lo) cudaFree(h->d_lo);
+    if (h->d_f16) cudaFree(h->d_f16);
     if (h->d_norm) cudaFree(h->d_norm);
-    if (h->h_flag) cudaFreeHost(h->h_flag);
     h->d_hi = h->d_lo = h->d_norm = nullptr;
-    h->h_flag = nullptr;
+    h->d_f16 = nullptr;
+    h->split_ready = false;
     return exact_build(h);
 }
 int64_t vs_exact_size(const vs_exact_t* h) { return h ? h->n : 0; }
@@ -392,6 +491,12 @@ int vs_exact_last_launches(const vs_exact_t* h, int* n_kernels, int* precision_u
     if (!h) return fail(VS_ERR_INVALID, "handle is NULL");
     if (n_kernels) *n_kernels = h->last_launches;
     if (precision_used) *precision_used = h->last_precision;
+    return VS_OK;
+}
+
+int vs_exact_last_fallbacks(const vs_exact_t* h, int* n_queries) {
+    if (!h || !n_queries) return fail(VS_ERR_INVALID, "NULL argument");
+    *n_queries = h->last_fallback;
     return VS_OK;
 }
 

@@ -39,34 +39,38 @@ TcPlan tc_make_plan(int64_t n, int64_t nq, int num_sms) {
     return pl;
 }
 
-template <int KTOP, bool SPLIT3, bool HAS_LB>
+template <int KTOP, int MODE, bool HAS_LB>
 static int set_attr_one() {
-    VSB_CUDA(cudaFuncSetAttribute(exact_tc_kernel<KTOP, SPLIT3, HAS_LB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  TcSmem<SPLIT3>::TOTAL));
+    VSB_CUDA(cudaFuncSetAttribute(exact_tc_kernel<KTOP, MODE, HAS_LB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  TcSmem<MODE>::TOTAL));
     return VS_OK;
 }
 
 int tc_lists_per_split() { return TC_EPI_GROUPS; }
 
 int tc_set_attributes() {
-    VSB_TRY((set_attr_one<1, false, false>()));
-    VSB_TRY((set_attr_one<1, true, false>()));
-    VSB_TRY((set_attr_one<5, false, false>()));
-    VSB_TRY((set_attr_one<5, true, false>()));
-    VSB_TRY((set_attr_one<10, false, false>()));
-    VSB_TRY((set_attr_one<10, true, false>()));
-    VSB_TRY((set_attr_one<16, false, false>()));
-    VSB_TRY((set_attr_one<16, true, false>()));
-    VSB_TRY((set_attr_one<32, false, false>()));
-    VSB_TRY((set_attr_one<32, true, false>()));
-    VSB_TRY((set_attr_one<32, false, true>()));
-    VSB_TRY((set_attr_one<32, true, true>()));
+    VSB_TRY((set_attr_one<1, TC_TF32X1, false>()));
+    VSB_TRY((set_attr_one<1, TC_TF32X3, false>()));
+    VSB_TRY((set_attr_one<5, TC_TF32X1, false>()));
+    VSB_TRY((set_attr_one<5, TC_TF32X3, false>()));
+    VSB_TRY((set_attr_one<10, TC_TF32X1, false>()));
+    VSB_TRY((set_attr_one<10, TC_TF32X3, false>()));
+    VSB_TRY((set_attr_one<16, TC_TF32X1, false>()));
+    VSB_TRY((set_attr_one<16, TC_TF32X3, false>()));
+    VSB_TRY((set_attr_one<32, TC_TF32X1, false>()));
+    VSB_TRY((set_attr_one<32, TC_TF32X3, false>()));
+    VSB_TRY((set_attr_one<32, TC_TF32X1, true>()));
+    VSB_TRY((set_attr_one<32, TC_TF32X3, true>()));
+    VSB_TRY((set_attr_one<16, TC_F16, false>()));
+    VSB_TRY((set_attr_one<32, TC_F16, false>()));
     return VS_OK;
 }
 
+// mode: TC_TF32X1 / TC_TF32X3 (tmA_lo / tmB_lo used by X3 only) / TC_F16 (tmA_hi / tmB_hi are the fp16 maps,
+// *key_scale_dev = -2 / (s_q * s_b); list sizes 16 and 32 only)
 int launch_exact_tc(const CUtensorMap& tmA_hi, const CUtensorMap& tmA_lo, const CUtensorMap& tmB_hi,
                     const CUtensorMap& tmB_lo, const float* bnorm, int32_t* gthr, int nq, const TcPlan& plan,
-                    int ktop, bool split3, const float* lb_key, const int32_t* lb_id, float* part_key,
+                    int ktop, int mode, const float* key_scale_dev, const float* lb_key, const int32_t* lb_id, float* part_key,
                     int32_t* part_id, cudaStream_t st) {
     TcParams p{};
     p.bnorm = bnorm;
@@ -80,40 +84,52 @@ int launch_exact_tc(const CUtensorMap& tmA_hi, const CUtensorMap& tmA_lo, const 
     p.n_mtiles = plan.n_mtiles;
     p.n_splits = plan.n_splits;
     p.tiles_per_split = plan.tiles_per_split;
+    p.key_scale_ptr = key_scale_dev;
+    if (mode == TC_F16 && !key_scale_dev) return fail(VS_ERR_INVALID, "tc: fp16 pass needs the device-side key scale");
     {
         const char* e = getenv("VSB_TC_DBG");
         p.dbg = e ? atoi(e) : 0;
     }
     if (lb_key && ktop != 32) return fail(VS_ERR_INVALID, "tc: lower bound needs the 32-entry list");
-#define VSB_TC_LAUNCH(KT, S3, LB)                                                                               \
-    exact_tc_kernel<KT, S3, LB><<<plan.grid, TC_THREADS, TcSmem<S3>::TOTAL, st>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, p)
-#define VSB_TC_CASE(KT)                         \
-    case KT:                                    \
-        if (split3)                             \
-            VSB_TC_LAUNCH(KT, true, false);     \
-        else                                    \
-            VSB_TC_LAUNCH(KT, false, false);    \
+    if (lb_key && mode == TC_F16) return fail(VS_ERR_INVALID, "tc: the fp16 candidate pass has no multi-pass mode");
+#define VSB_TC_LAUNCH(KT, MD, LB)                                                                                \
+    exact_tc_kernel<KT, MD, LB><<<plan.grid, TC_THREADS, TcSmem<MD>::TOTAL, st>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, p)
+#define VSB_TC_CASE(KT)                              \
+    case KT:                                         \
+        if (mode == TC_TF32X3)                       \
+            VSB_TC_LAUNCH(KT, TC_TF32X3, false);     \
+        else                                         \
+            VSB_TC_LAUNCH(KT, TC_TF32X1, false);     \
         break;
-    switch (ktop) {
-        VSB_TC_CASE(1)
-        VSB_TC_CASE(5)
-        VSB_TC_CASE(10)
-        VSB_TC_CASE(16)
-        case 32:
-            if (lb_key) {
-                if (split3)
-                    VSB_TC_LAUNCH(32, true, true);
-                else
-                    VSB_TC_LAUNCH(32, false, true);
-            } else {
-                if (split3)
-                    VSB_TC_LAUNCH(32, true, false);
-                else
-                    VSB_TC_LAUNCH(32, false, false);
-            }
-            break;
-        default:
-            return fail(VS_ERR_INVALID, "tc: unsupported list size");
+    if (mode == TC_F16) {
+        if (ktop == 16)
+            VSB_TC_LAUNCH(16, TC_F16, false);
+        else if (ktop == 32)
+            VSB_TC_LAUNCH(32, TC_F16, false);
+        else
+            return fail(VS_ERR_INVALID, "tc: fp16 pass supports list sizes 16 and 32");
+    } else {
+        switch (ktop) {
+            VSB_TC_CASE(1)
+            VSB_TC_CASE(5)
+            VSB_TC_CASE(10)
+            VSB_TC_CASE(16)
+            case 32:
+                if (lb_key) {
+                    if (mode == TC_TF32X3)
+                        VSB_TC_LAUNCH(32, TC_TF32X3, true);
+                    else
+                        VSB_TC_LAUNCH(32, TC_TF32X1, true);
+                } else {
+                    if (mode == TC_TF32X3)
+                        VSB_TC_LAUNCH(32, TC_TF32X3, false);
+                    else
+                        VSB_TC_LAUNCH(32, TC_TF32X1, false);
+                }
+                break;
+            default:
+                return fail(VS_ERR_INVALID, "tc: unsupported list size");
+        }
     }
 #undef VSB_TC_CASE
 #undef VSB_TC_LAUNCH

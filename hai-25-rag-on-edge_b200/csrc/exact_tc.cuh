@@ -29,7 +29,6 @@ namespace vsb {
 
 constexpr int TC_BM = 128;        // queries per CTA tile
 constexpr int TC_BN = 128;        // base rows per accumulator tile
-constexpr int TC_NKB = 4;         // k-blocks (dim 128 = 4 x 32 fp32)
 constexpr int TC_KB_BYTES = 128 * 128;  // one k-block of a 128-row operand tile: 128 rows x 128 B
 constexpr int TC_NACC = 4;        // accumulator buffers in TMEM (4 x 128 columns = all 512)
 constexpr int TC_EPI_GROUPS = 2;  // epilogue warpgroups (column halves)
@@ -37,10 +36,20 @@ constexpr int TC_GCOLS = TC_BN / TC_EPI_GROUPS;
 constexpr int TC_THREADS = 64 + 128 * TC_EPI_GROUPS;
 constexpr int TC_THR_REFRESH = 8; // tiles between reads of the shared threshold (power of two)
 
-template <bool SPLIT3>
+// Operand arithmetic of the tensor-core pass
+//   TC_TF32X1  kind::tf32, one product                    (exact when operands are TF32-representable)
+//   TC_TF32X3  kind::tf32, hi/lo split, three products    (fp32-faithful)
+//   TC_F16     kind::f16 on power-of-two-scaled fp16 copies: a CANDIDATE generator whose key error is bounded
+//              (api.cu derives the bound); the merge kernel refines the candidates in exact fp32 and certifies,
+//              per query, that no true neighbour can have been missed.
+enum TcMode : int { TC_TF32X1 = 0, TC_TF32X3 = 1, TC_F16 = 2 };
+
+template <int MODE>
 struct TcSmem {
-    static constexpr int A_BYTES = (SPLIT3 ? 2 : 1) * TC_NKB * TC_KB_BYTES;
-    static constexpr int NSTAGE = SPLIT3 ? 5 : 8;
+    static constexpr bool SPLIT3 = MODE == TC_TF32X3;
+    static constexpr int NKB = MODE == TC_F16 ? 2 : 4;  // 128-byte k-blocks per row (128 fp16 = 256 B, 128 fp32 = 512 B)
+    static constexpr int A_BYTES = (SPLIT3 ? 2 : 1) * NKB * TC_KB_BYTES;
+    static constexpr int NSTAGE = MODE == TC_F16 ? 10 : (SPLIT3 ? 5 : 8);
     static constexpr int B_BYTES = NSTAGE * TC_KB_BYTES;
     static constexpr int NORM_BYTES = TC_NACC * TC_BN * 4;
     static constexpr int BAR_BYTES = 1024;
@@ -59,7 +68,9 @@ struct TcParams {
     int n_mtiles;        // ceil(nq / 128)
     int n_splits;
     int tiles_per_split;
-    int dbg;             // timing experiments only (VSB_TC_DBG): 1 no epilogue work, 2 no inserts, 4 no MMA, 8 no B loads
+    const float* key_scale_ptr;  // TC_F16: key = bn + (*key_scale_ptr) * acc, -2 / (s_q * s_b), derived on the device
+    int dbg;             // timing experiments only (VSB_TC_DBG): 1 no epilogue work, 2 no inserts, 4 no MMA, 8 no B loads,
+                         // 16 epilogue = TMEM loads only, 32 epilogue = math only (no TMEM loads)
 };
 
 // smallest float strictly greater than x (x finite or +inf; +inf maps to itself)
@@ -70,13 +81,31 @@ __device__ __forceinline__ float next_up(float x) {
     return __int_as_float(i > 0 ? i + 1 : i - 1);
 }
 
-template <int KTOP, bool SPLIT3, bool HAS_LB>
+// 16-byte shared-memory load with an explicit shared-space address (a generic-pointer LD costs a longer scoreboard wait)
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+template <int KTOP, int MODE, bool HAS_LB>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                 const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                 const TcParams p) {
-    using S = TcSmem<SPLIT3>;
+    using S = TcSmem<MODE>;
     constexpr int NSTAGE = S::NSTAGE;
+    constexpr bool SPLIT3 = S::SPLIT3;
+    constexpr int TC_NKB = S::NKB;
+    constexpr int KB_ELEMS = MODE == TC_F16 ? 64 : 32;  // elements per 128-byte k-block
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* sA = smem;
@@ -139,7 +168,7 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
                 mbar_expect_tx(a_full, (uint32_t)S::A_BYTES);
 #pragma unroll
                 for (int kb = 0; kb < TC_NKB; ++kb) {
-                    tma_load_2d(sA + kb * TC_KB_BYTES, &tmA_hi, a_full, kb * 32, m_tile * TC_BM);
+                    tma_load_2d(sA + kb * TC_KB_BYTES, &tmA_hi, a_full, kb * KB_ELEMS, m_tile * TC_BM);
                     if (SPLIT3) tma_load_2d(sA + (TC_NKB + kb) * TC_KB_BYTES, &tmA_lo, a_full, kb * 32, m_tile * TC_BM);
                 }
                 const int t0 = split * p.tiles_per_split;
@@ -157,7 +186,7 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
                             mbar_arrive(&full[stage]);
                         } else {
                             mbar_expect_tx(&full[stage], (uint32_t)TC_KB_BYTES);
-                            tma_load_2d(sB + stage * TC_KB_BYTES, &tmB_hi, &full[stage], kb * 32, t * TC_BN);
+                            tma_load_2d(sB + stage * TC_KB_BYTES, &tmB_hi, &full[stage], kb * KB_ELEMS, t * TC_BN);
                         }
                         if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
                         if (SPLIT3) {
@@ -177,7 +206,7 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
     } else if (warp == 1) {
         // ===================================== MMA issuer =======================================
         if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc(kIdescCF32, kIdescTF32, TC_BM, TC_BN);
+            constexpr uint32_t idesc = umma_idesc(kIdescCF32, MODE == TC_F16 ? kIdescF16 : kIdescTF32, TC_BM, TC_BN);
             const uint32_t sA_u = smem_u32(sA);
             const uint32_t sB_u = smem_u32(sB);
             int stage = 0, acc = 0;
@@ -212,8 +241,11 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
                             }
                             if (!(p.dbg & 4)) {
 #pragma unroll
-                                for (int ks = 0; ks < 4; ++ks) {  // q_hi . x_hi
-                                    tc_mma_tf32(d_tmem, a_hi + 2 * ks, b + 2 * ks, idesc, accum);
+                                for (int ks = 0; ks < 4; ++ks) {  // q_hi . x_hi   (32 bytes of K per instruction)
+                                    if (MODE == TC_F16)
+                                        tc_mma_f16(d_tmem, a_hi + 2 * ks, b + 2 * ks, idesc, accum);
+                                    else
+                                        tc_mma_tf32(d_tmem, a_hi + 2 * ks, b + 2 * ks, idesc, accum);
                                     accum = 1;
                                 }
                             }
@@ -246,6 +278,7 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         const int grp = (warp - 2) >> 2;  // column half handled by this warpgroup
         const int row = quad * 32 + lane;
         const float INF = __int_as_float(0x7f800000);
+        const float key_scale = MODE == TC_F16 ? __ldg(p.key_scale_ptr) : -2.0f;
         constexpr int CH = TC_GCOLS / 32;  // 32-column chunks per thread per tile
         int acc = 0;
         uint32_t acc_phase = 0;
@@ -280,24 +313,34 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
                 mbar_wait(&acc_full[acc], acc_phase);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * TC_BN + grp * TC_GCOLS);
-                const float* bn_s = sN + acc * TC_BN + grp * TC_GCOLS;
+                const uint32_t bn_s = smem_u32(sN + acc * TC_BN + grp * TC_GCOLS);
                 uint32_t r[2][32];
                 const bool skip = (p.dbg & 1) || !quad_live;
-                if (!skip) tmem_ld32(taddr, r[0]);
+                if (!skip && !(p.dbg & 32)) tmem_ld32(taddr, r[0]);
 #pragma unroll
                 for (int c = 0; c < CH; ++c) {
                     if (skip) break;
-                    tc_wait_ld();
-                    if (c + 1 < CH) tmem_ld32(taddr + (c + 1) * 32, r[(c + 1) & 1]);
+                    if (!(p.dbg & 32)) {
+                        tc_wait_ld();
+                        if (c + 1 < CH) tmem_ld32(taddr + (c + 1) * 32, r[(c + 1) & 1]);
+                    }
+                    if (p.dbg & 16) continue;
                     const int col0 = t * TC_BN + grp * TC_GCOLS + c * 32;
                     float d[32];
 #pragma unroll
                     for (int j4 = 0; j4 < 8; ++j4) {
-                        const float4 bn = *reinterpret_cast<const float4*>(bn_s + c * 32 + 4 * j4);  // smem broadcast
-                        d[4 * j4 + 0] = fmaf(-2.0f, __uint_as_float(r[c & 1][4 * j4 + 0]), bn.x);
-                        d[4 * j4 + 1] = fmaf(-2.0f, __uint_as_float(r[c & 1][4 * j4 + 1]), bn.y);
-                        d[4 * j4 + 2] = fmaf(-2.0f, __uint_as_float(r[c & 1][4 * j4 + 2]), bn.z);
-                        d[4 * j4 + 3] = fmaf(-2.0f, __uint_as_float(r[c & 1][4 * j4 + 3]), bn.w);
+                        const float4 bn = lds128(bn_s + (uint32_t)(c * 32 + 4 * j4) * 4u);  // smem broadcast
+                        if (MODE == TC_F16) {
+                            d[4 * j4 + 0] = fmaf(key_scale, __uint_as_float(r[c & 1][4 * j4 + 0]), bn.x);
+                            d[4 * j4 + 1] = fmaf(key_scale, __uint_as_float(r[c & 1][4 * j4 + 1]), bn.y);
+                            d[4 * j4 + 2] = fmaf(key_scale, __uint_as_float(r[c & 1][4 * j4 + 2]), bn.z);
+                            d[4 * j4 + 3] = fmaf(key_scale, __uint_as_float(r[c & 1][4 * j4 + 3]), bn.w);
+                        } else {
+                            d[4 * j4 + 0] = fmaf(-2.0f, __uint_as_float(r[c & 1][4 * j4 + 0]), bn.x);
+                            d[4 * j4 + 1] = fmaf(-2.0f, __uint_as_float(r[c & 1][4 * j4 + 1]), bn.y);
+                            d[4 * j4 + 2] = fmaf(-2.0f, __uint_as_float(r[c & 1][4 * j4 + 2]), bn.z);
+                            d[4 * j4 + 3] = fmaf(-2.0f, __uint_as_float(r[c & 1][4 * j4 + 3]), bn.w);
+                        }
                     }
                     if (HAS_LB) {
 #pragma unroll

@@ -1,4 +1,6 @@
 // Index-build / query-prep kernels, list merge (K3) and the device-side synthetic data generator.
+#include <cuda_fp16.h>
+
 #include "kernels.cuh"
 #include "vsb_common.cuh"
 
@@ -45,6 +47,8 @@ __global__ void __launch_bounds__(256) prep_rows_kernel(const float* __restrict_
                 hi[row * (int64_t)dim + i] = h;
                 lo[row * (int64_t)dim + i] = r;
                 inexact |= (r != 0.f);
+            } else if (not_exact) {
+                inexact |= (round_tf32(a) != a);
             }
         }
     }
@@ -65,6 +69,8 @@ __global__ void __launch_bounds__(256) prep_rows_kernel(const float* __restrict_
                 hi[row * (int64_t)dim + i] = h;
                 lo[row * (int64_t)dim + i] = r;
                 inexact |= (r != 0.f);
+            } else if (not_exact) {
+                inexact |= (round_tf32(a) != a);
             }
         }
         if (norms) norms[row] = s;
@@ -94,6 +100,118 @@ int launch_fill_f32(float* p, int64_t n, float v, cudaStream_t st) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// scaled fp16 operand copies for the candidate pass (TC_F16) and the per-call certification constants
+// ------------------------------------------------------------------------------------------------
+__global__ void absmax_f32_kernel(const float* __restrict__ x, int64_t count, float* __restrict__ out) {
+    float mx = 0.f;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x)
+        mx = fmaxf(mx, fabsf(__ldg(x + i)));  // fmaxf drops NaN: garbage in, garbage out
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(out), __float_as_int(mx));  // non-negative floats order as ints
+}
+int launch_absmax_f32(const float* x, int64_t count, float* out_zeroed, cudaStream_t st) {
+    if (count <= 0) return VS_OK;
+    const int64_t blocks = ceil_div64(count, 256);
+    absmax_f32_kernel<<<(unsigned)(blocks > 148 * 8 ? 148 * 8 : blocks), 256, 0, st>>>(x, count, out_zeroed);
+    VSB_CUDA(cudaGetLastError());
+    return VS_OK;
+}
+
+// power-of-two scale that brings absmax into [2^14, 2^15): fp16 keeps 11 significant bits for everything above
+// 2^-14 in scaled units (i.e. 2^-29 of the largest magnitude)
+__host__ __device__ inline float f16_scale_for(float absmax) {
+    if (!(absmax > 0.f) || !(absmax < 3.0e38f)) return 1.0f;
+    int e;
+    frexpf(absmax, &e);  // absmax = m * 2^e, m in [0.5, 1)
+    int se = 15 - e;
+    se = se < -100 ? -100 : (se > 100 ? 100 : se);
+    return ldexpf(1.0f, se);
+}
+float f16_scale_host(float absmax) { return f16_scale_for(absmax); }
+
+// TcQueryParams (kernels.cuh): scale of the query copy, key factor and the two certification constants.
+//   |key_f16 - key_exact| <= cert_a * sqrt(qn) + cert_b   with, per element, |x^ - x| <= eps|x| + u (eps = 2^-11,
+//   u = 2^-25 / scale: half the fp16 subnormal spacing), Cauchy-Schwarz for sum|q||x| <= sqrt(qn * bn_max) and
+//   sum|v| <= sqrt(128 * ||v||^2), plus 2^-15 * sum|q||x| for the tensor core's fp32 accumulation, times 1.02,
+//   plus the fp32 rounding of the refined distances themselves (4e-6 * (qn + bn_max), folded into cert_b per query
+//   by the merge kernel).
+__global__ void tc_query_params_kernel(const float* __restrict__ q_absmax, float s_b, float bn_max, TcQueryParams* out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const float s_q = f16_scale_for(*q_absmax);
+    const float eps = 1.0f / 2048.0f;
+    const float A = 2.0f * eps + eps * eps + 1.0f / 32768.0f;
+    const float u_q = ldexpf(1.0f, -25) / s_q, u_b = ldexpf(1.0f, -25) / s_b;
+    TcQueryParams r;
+    r.s_q = s_q;
+    r.key_scale = -2.0f / (s_q * s_b);
+    r.cert_a = 2.04f * (A * sqrtf(bn_max) + u_b * sqrtf(128.0f));
+    r.cert_b = 2.04f * (u_q * sqrtf(128.0f * bn_max) + 128.0f * u_q * u_b);
+    r.bn_max = bn_max;
+    *out = r;
+}
+int launch_tc_query_params(const float* q_absmax, float s_b, float bn_max, TcQueryParams* out, cudaStream_t st) {
+    tc_query_params_kernel<<<1, 32, 0, st>>>(q_absmax, s_b, bn_max, out);
+    VSB_CUDA(cudaGetLastError());
+    return VS_OK;
+}
+
+// out[i] = fp16_rn(x[i] * scale); scale either given or read from *scale_dev (the query scale is derived on the device)
+__global__ void to_half_scaled_kernel(const float* __restrict__ x, int64_t count, float scale, const TcQueryParams* scale_dev,
+                                      __half* __restrict__ out) {
+    const float s = scale_dev ? scale_dev->s_q : scale;
+    for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < count; i += (int64_t)gridDim.x * blockDim.x * 4) {
+        if (i + 3 < count) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(x + i));
+            __half2 a = __floats2half2_rn(v.x * s, v.y * s);
+            __half2 b = __floats2half2_rn(v.z * s, v.w * s);
+            uint2 pk;
+            pk.x = *reinterpret_cast<uint32_t*>(&a);
+            pk.y = *reinterpret_cast<uint32_t*>(&b);
+            *reinterpret_cast<uint2*>(out + i) = pk;
+        } else {
+            for (int e = 0; e < 4 && i + e < count; ++e) out[i + e] = __float2half_rn(__ldg(x + i + e) * s);
+        }
+    }
+}
+int launch_to_half_scaled(const float* x, int64_t count, float scale, const TcQueryParams* scale_dev, void* out, cudaStream_t st) {
+    if (count <= 0) return VS_OK;
+    const int64_t blocks = ceil_div64(count, 4 * 256);
+    to_half_scaled_kernel<<<(unsigned)(blocks > 148 * 16 ? 148 * 16 : blocks), 256, 0, st>>>(x, count, scale, scale_dev,
+                                                                                         (__half*)out);
+    VSB_CUDA(cudaGetLastError());
+    return VS_OK;
+}
+
+// rows gather / result scatter for the fallback of uncertified queries
+__global__ void gather_rows_kernel(const float* __restrict__ src, const int32_t* __restrict__ idx, int n_idx, float* __restrict__ dst) {
+    const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= n_idx) return;
+    const int lane = threadIdx.x & 31;
+    reinterpret_cast<float4*>(dst + (size_t)r * 128)[lane] = __ldg(reinterpret_cast<const float4*>(src + (size_t)idx[r] * 128) + lane);
+}
+__global__ void scatter_results_kernel(const float* __restrict__ key, const int32_t* __restrict__ id, const int32_t* __restrict__ idx,
+                                       int n_idx, int k, float* __restrict__ out_key, int32_t* __restrict__ out_id) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_idx * k) return;
+    const int r = i / k, c = i % k;
+    out_key[(size_t)idx[r] * k + c] = key[i];
+    out_id[(size_t)idx[r] * k + c] = id[i];
+}
+int launch_gather_rows(const float* src, const int32_t* idx, int n_idx, float* dst, cudaStream_t st) {
+    if (n_idx <= 0) return VS_OK;
+    gather_rows_kernel<<<(unsigned)((n_idx + 3) / 4), 128, 0, st>>>(src, idx, n_idx, dst);
+    VSB_CUDA(cudaGetLastError());
+    return VS_OK;
+}
+int launch_scatter_results(const float* key, const int32_t* id, const int32_t* idx, int n_idx, int k, float* out_key,
+                           int32_t* out_id, cudaStream_t st) {
+    if (n_idx <= 0) return VS_OK;
+    scatter_results_kernel<<<(unsigned)((n_idx * k + 255) / 256), 256, 0, st>>>(key, id, idx, n_idx, k, out_key, out_id);
+    VSB_CUDA(cudaGetLastError());
+    return VS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // K3: merge sorted partial lists (+ optional exact fp32 refine).  One warp per query; lane j folds lists
 // j, j+32, ... into a register list, then the warp pops the global minimum `nsel` times.
 //
@@ -109,6 +227,12 @@ struct RefineArgs {
     const float* bnorm;
     const float* q;      // [nq x 128]
     const float* qnorm;
+    // certification of a bounded-error candidate pass (TC_F16), or qp == nullptr: a query is certified when no row
+    // outside its nsel candidates can beat the k-th refined distance:  qn + a_last - E_q > D_k  (a_last = largest
+    // candidate key, D_k = k-th smallest refined distance), or when fewer than nsel candidates exist at all.
+    const TcQueryParams* qp;
+    int32_t* uncert_count;  // number of uncertified queries
+    int32_t* uncert_list;   // their indices
 };
 
 __device__ __forceinline__ float dot16_128(const float* __restrict__ a, const float* __restrict__ b) {
@@ -233,6 +357,17 @@ __global__ void __launch_bounds__(128) merge_lists_kernel(const float* __restric
         rank += (oi >= 0 && pair_less(ok, oi, myk, myid)) ? 1 : 0;
     }
     const int n_valid = __popc(__ballot_sync(0xffffffffu, myid >= 0));
+    if (rf.qp) {
+        // lastk = key of the last popped candidate = largest candidate key (lists pop in ascending key order)
+        const unsigned holder = __ballot_sync(0xffffffffu, myid >= 0 && rank == k - 1);
+        const float dk = __shfl_sync(0xffffffffu, myk, holder ? __ffs(holder) - 1 : 0);
+        if (lane == 0 && n_valid == nsel) {
+            const float qn = __ldg(rf.qnorm + q);
+            const float e = rf.qp->cert_a * sqrtf(qn) + rf.qp->cert_b + 4e-6f * (qn + rf.qp->bn_max);
+            const bool ok = holder != 0 && (qn + lastk) - e > dk;
+            if (!ok) rf.uncert_list[atomicAdd(rf.uncert_count, 1)] = (int32_t)q;
+        }
+    }
     float* ok_row = out_key + q * out_stride + out_off;
     int32_t* oi_row = out_id + q * out_stride + out_off;
     if (myid >= 0 && rank < k) {
@@ -248,11 +383,13 @@ __global__ void __launch_bounds__(128) merge_lists_kernel(const float* __restric
 int launch_merge_lists(const float* part_key, const int32_t* part_id, int n_lists, int64_t nq, int list_len, int nsel,
                        int k, int64_t id_base, int neg_in, int neg_out, float* out_key, int32_t* out_id, int out_stride,
                        int out_off, float* lb_key_out, int32_t* lb_id_out, const float* rf_base, const float* rf_bnorm,
-                       const float* rf_q, const float* rf_qnorm, cudaStream_t st) {
+                       const float* rf_q, const float* rf_qnorm, cudaStream_t st, const TcQueryParams* cert_qp,
+                       int32_t* uncert_count, int32_t* uncert_list) {
     if (nq <= 0) return VS_OK;
     if (nsel > list_len || k > nsel || nsel > 32) return fail(VS_ERR_INVALID, "merge: need k <= nsel <= list length <= 32");
+    if (cert_qp && (!rf_base || !uncert_count || !uncert_list)) return fail(VS_ERR_INVALID, "merge: certification needs the refine");
     const unsigned blocks = (unsigned)ceil_div64(nq, 4);
-    RefineArgs rf{rf_base, rf_bnorm, rf_q, rf_qnorm};
+    RefineArgs rf{rf_base, rf_bnorm, rf_q, rf_qnorm, cert_qp, uncert_count, uncert_list};
 #define VSB_MERGE_CASE(KT)                                                                                            \
     case KT:                                                                                                          \
         merge_lists_kernel<KT><<<blocks, 128, 0, st>>>(part_key, part_id, n_lists, nq, list_len, nsel, k, id_base,    \

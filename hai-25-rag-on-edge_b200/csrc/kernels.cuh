@@ -6,6 +6,23 @@
 
 namespace vsb {
 
+// per-call constants of the scaled-fp16 candidate pass, derived on the device from the queries (no host round trip)
+struct TcQueryParams {
+    float s_q;        // power-of-two scale of the fp16 query copy
+    float key_scale;  // key = bn + (*key_scale_dev) * acc,  -2 / (s_q * s_b)
+    float cert_a;     // |key_f16 - key_exact| <= cert_a * sqrt(qn) + cert_b
+    float cert_b;
+    float bn_max;
+};
+int launch_absmax_f32(const float* x, int64_t count, float* out_zeroed, cudaStream_t st);
+float f16_scale_host(float absmax);
+int launch_tc_query_params(const float* q_absmax, float s_b, float bn_max, TcQueryParams* out, cudaStream_t st);
+int launch_to_half_scaled(const float* x, int64_t count, float scale, const TcQueryParams* scale_dev, void* out_half,
+                          cudaStream_t st);
+int launch_gather_rows(const float* src, const int32_t* idx, int n_idx, float* dst, cudaStream_t st);
+int launch_scatter_results(const float* key, const int32_t* id, const int32_t* idx, int n_idx, int k, float* out_key,
+                           int32_t* out_id, cudaStream_t st);
+
 // prep.cu ---------------------------------------------------------------------------------------
 // ||x||^2 per row in the reference's summation order (cpu_baseline.cpp:95-114) and, when hi/lo are non-null,
 // the TF32 split x = hi + lo (hi = rna_tf32(x), lo = rna_tf32(x - hi)).  *not_tf32_exact is OR-ed with 1 when
@@ -27,9 +44,10 @@ struct TcPlan {
     int n_tiles, n_mtiles, n_splits, tiles_per_split, grid;
 };
 TcPlan tc_make_plan(int64_t n, int64_t nq, int num_sms);
+// mode: 0 = 1xTF32, 1 = 3xTF32, 2 = scaled fp16 candidate pass (exact_tc.cuh TcMode); key = bn + (*key_scale_dev) * acc
 int launch_exact_tc(const CUtensorMap& tmA_hi, const CUtensorMap& tmA_lo, const CUtensorMap& tmB_hi,
                     const CUtensorMap& tmB_lo, const float* bnorm, int32_t* gthr, int nq, const TcPlan& plan,
-                    int ktop, bool split3, const float* lb_key, const int32_t* lb_id, float* part_key,
+                    int ktop, int mode, const float* key_scale_dev, const float* lb_key, const int32_t* lb_id, float* part_key,
                     int32_t* part_id, cudaStream_t st);
 int tc_lists_per_split();  // partial lists written per (split, query)
 int tc_set_attributes();  // opt-in to > 48 KB dynamic shared memory for every instantiation
@@ -40,10 +58,13 @@ int tc_set_attributes();  // opt-in to > 48 KB dynamic shared memory for every i
 // ids), orders them by (key asc, id asc) and writes the first k to out[q*out_stride + out_off ...]; adds id_base
 // to valid ids; neg_in / neg_out flip the key sign on load / store (descending scores are handled as ascending
 // negated keys).  lb_*_out receive the last selected candidate (exclusive lower bound of the next pass, k > 32).
+// cert_qp != nullptr (needs the refine): queries whose answer cannot be certified complete from the bounded-error
+// candidate pass are appended to uncert_list / counted in *uncert_count (zeroed by the caller).
 int launch_merge_lists(const float* part_key, const int32_t* part_id, int n_lists, int64_t nq, int list_len, int nsel,
                        int k, int64_t id_base, int neg_in, int neg_out, float* out_key, int32_t* out_id, int out_stride,
                        int out_off, float* lb_key_out, int32_t* lb_id_out, const float* rf_base, const float* rf_bnorm,
-                       const float* rf_q, const float* rf_qnorm, cudaStream_t st);
+                       const float* rf_q, const float* rf_qnorm, cudaStream_t st, const TcQueryParams* cert_qp = nullptr,
+                       int32_t* uncert_count = nullptr, int32_t* uncert_list = nullptr);
 int launch_sort_rows(float* key, int32_t* id, int64_t nq, int k, cudaStream_t st);
 
 // synth.cu --------------------------------------------------------------------------------------

@@ -175,7 +175,7 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 __host__ __device__ constexpr uint32_t umma_idesc(uint32_t c_fmt, uint32_t ab_fmt, uint32_t M, uint32_t N) {
     return (c_fmt << 4) | (ab_fmt << 7) | (ab_fmt << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
-constexpr uint32_t kIdescCF32 = 1, kIdescCS32 = 2, kIdescTF32 = 2, kIdescU8 = 0;
+constexpr uint32_t kIdescCF32 = 1, kIdescCS32 = 2, kIdescTF32 = 2, kIdescF16 = 0, kIdescU8 = 0;
 
 // ------------------------------------------------------------------------------------------------
 // Per-thread sorted top-k list in registers: smallest keys first, ties keep the earlier insertion first

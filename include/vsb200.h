@@ -53,11 +53,17 @@ typedef enum vs_status {
 /* Arithmetic of the exact path's dot products (distances are always combined in fp32 as
  * (qn + bn) - 2*dot, cpu_baseline.cpp:241). */
 typedef enum vs_precision {
-    VS_PREC_AUTO = 0,        /* small batches -> FFMA stream; otherwise 1xTF32 when every operand is exactly
-                                representable in TF32 (integer SIFT data: bit-identical to fp32), else 3xTF32 */
+    VS_PREC_AUTO = 0,        /* <= 16 queries -> FFMA stream; k <= 16 -> certified fp16 candidate pass (below);
+                                otherwise 1xTF32 when every operand is exactly representable in TF32 (integer SIFT
+                                data: bit-identical to fp32), else 3xTF32 */
     VS_PREC_FP32_3XTF32 = 1, /* tcgen05 kind::tf32, hi/lo split, 3 products, fp32 accumulate in TMEM */
     VS_PREC_FP32_FFMA = 2,   /* CUDA-core FFMA streaming kernel (HBM-bound; any batch, slow for large ones) */
-    VS_PREC_TF32_1X = 3      /* single TF32 product; exact only for TF32-representable data */
+    VS_PREC_TF32_1X = 3,     /* single TF32 product; exact only for TF32-representable data */
+    VS_PREC_F16_CERTIFIED = 4 /* fp32-faithful results from a cheaper tensor-core pass: tcgen05 kind::f16 on power-of-two
+                                scaled fp16 copies keeps the 32 best keys per query (key error rigorously bounded), those
+                                32 distances are recomputed in exact fp32 and the top k is certified complete per query
+                                (every excluded row is provably farther than the k-th result); queries that cannot be
+                                certified are redone with 3xTF32 / FFMA.  k <= 16.  Synchronises the stream once. */
 } vs_precision;
 
 VSB_API const char* vs_last_error(void);
@@ -97,6 +103,8 @@ VSB_API int vs_exact_search_dev(vs_exact_t* h, const float* queries_dev, int64_t
  * search is measured by the caller with CUDA events on the stream; this returns how many kernels the last
  * search launched and which precision path AUTO resolved to. */
 VSB_API int vs_exact_last_launches(const vs_exact_t* h, int* n_kernels, int* precision_used);
+/* number of queries of the last search that the certified path could not certify and redid on the fp32 path */
+VSB_API int vs_exact_last_fallbacks(const vs_exact_t* h, int* n_queries);
 /* When enabled, every search brackets its dominant kernel (the fused distance+top-k kernel: tcgen05 or FFMA
  * stream) with CUDA events on the launching stream; vs_exact_last_kernel_ms waits for and returns that duration. */
 VSB_API int vs_exact_set_profile(vs_exact_t* h, int enable);

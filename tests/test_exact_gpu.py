@@ -9,7 +9,7 @@ pytestmark = pytest.mark.gpu
 
 
 def _precisions(vsb, law):
-    p = [vsb.PREC_3XTF32, vsb.PREC_FFMA, vsb.PREC_AUTO]
+    p = [vsb.PREC_3XTF32, vsb.PREC_FFMA, vsb.PREC_AUTO, vsb.PREC_F16_CERT]
     if law == "sift":
         p.append(vsb.PREC_TF32_1X)  # exact on TF32-representable (integer) data
     return p
@@ -24,6 +24,8 @@ def test_golden_reference_vectors(path, gpu_vsb, oracle):
     try:
         assert idx.base_is_tf32_exact == exact
         for prec in _precisions(vsb, law):
+            if prec == vsb.PREC_F16_CERT and k > 16:
+                continue
             ids, d = idx.search(qry, k, prec)
             rec = oracle.exact_distances_at(base, qry, ids)
             assert_topk_matches(ids, d, g["ids"], g["dists"], rec, exact=exact,
@@ -48,6 +50,8 @@ def test_ragged_shapes_vs_oracle(nb, nq, k, law, gpu_vsb, oracle):
     idx = vsb.ExactIndex(base)
     try:
         for prec in _precisions(vsb, law):
+            if prec == vsb.PREC_F16_CERT and k > 16:
+                continue
             ids, d = idx.search(qry, k, prec)
             rec = oracle.exact_distances_at(base, qry, ids)
             assert_topk_matches(ids, d, oi, od, rec, exact=(law == "sift"),
@@ -157,5 +161,43 @@ def test_argument_errors(gpu_vsb):
             idx.search(base[:2], 0)
         ids, d = idx.search(base[:0], 5)  # empty batch
         assert ids.shape == (0, 5)
+    finally:
+        idx.close()
+
+
+def test_certified_path_falls_back_when_it_cannot_certify(gpu_vsb, oracle):
+    """Adversarial base for the fp16 candidate pass: 200 near-duplicates of one row (perturbations far below the fp16
+    key error bound) so that more than 32 rows sit within the bound of the 10th neighbour.  Queries near that row
+    cannot be certified and must be redone on the fp32 path; the answer still has to match the oracle."""
+    vsb = gpu_vsb
+    rng = np.random.default_rng(11)
+    base = vsb.synth.make("cont", 77, 50_000)
+    centre = base[123].copy()
+    dup = centre[None, :] + rng.uniform(-0.02, 0.02, (200, 128)).astype(np.float32)
+    base[1000:1200] = dup
+    qry = vsb.synth.make("cont", 78, 300)
+    qry[:40] = centre[None, :] + rng.uniform(-0.05, 0.05, (40, 128)).astype(np.float32)
+    oi, od = oracle.exact_search(base, qry, 10, mode=1)
+    idx = vsb.ExactIndex(base)
+    try:
+        ids, d = idx.search(qry, 10, vsb.PREC_F16_CERT)
+        nfb = idx.last_fallbacks()
+        assert 40 <= nfb < 100, nfb  # the 40 adversarial queries (plus at most a few unlucky ones)
+        rec = oracle.exact_distances_at(base, qry, ids)
+        # distances of near-duplicates are ~1e-1 after cancellation of ~1e5-sized terms: compare those absolutely
+        assert np.allclose(d[40:], od[40:], rtol=RTOL, atol=0)
+        assert np.allclose(d[:40], od[:40], rtol=0, atol=0.5)
+        assert np.allclose(rec, d, rtol=RTOL, atol=0.5)
+        assert (ids[40:] == oi[40:]).mean() > 0.999
+        for r in range(40):  # the ten best of a cluster of near-ties: same set up to ties within the tolerance
+            assert set(ids[r]) <= set(range(1000, 1200)) | {123}
+        # three adversarial queries only: the fallback goes through the FFMA stream kernel
+        ids3, d3 = idx.search(qry[37:140], 10, vsb.PREC_F16_CERT)
+        assert 3 <= idx.last_fallbacks() <= 8
+        assert np.array_equal(ids3[3:], ids[40:140]) and np.allclose(d3[:3], od[37:40], rtol=0, atol=0.5)
+        # a normal batch certifies everything
+        ids2, d2 = idx.search(qry[40:], 10, vsb.PREC_F16_CERT)
+        assert idx.last_fallbacks() == 0
+        assert np.array_equal(ids2, ids[40:]) and np.array_equal(d2, d[40:])
     finally:
         idx.close()
