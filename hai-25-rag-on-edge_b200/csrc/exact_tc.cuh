@@ -31,10 +31,10 @@ constexpr int TC_BM = 128;        // queries per CTA tile
 constexpr int TC_BN = 128;        // base rows per accumulator tile
 constexpr int TC_KB_BYTES = 128 * 128;  // one k-block of a 128-row operand tile: 128 rows x 128 B
 constexpr int TC_NACC = 4;        // accumulator buffers in TMEM (4 x 128 columns = all 512)
-constexpr int TC_EPI_GROUPS = 2;  // epilogue warpgroups (column halves)
-constexpr int TC_GCOLS = TC_BN / TC_EPI_GROUPS;
-constexpr int TC_THREADS = 64 + 128 * TC_EPI_GROUPS;
-constexpr int TC_THR_REFRESH = 8; // tiles between reads of the shared threshold (power of two)
+constexpr int TC_EPI_GROUPS = 3;  // epilogue warpgroups; tiles rotate over them
+constexpr int TC_THREADS = 128 + 128 * TC_EPI_GROUPS;  // warpgroup 0: TMA producer, MMA issuer, two idle warps
+constexpr int TC_REGS_CTRL = 80, TC_REGS_EPI = 144;   // setmaxnreg budgets: 128*80 + 384*144 == 64K registers
+constexpr int TC_THR_REFRESH = 4; // tiles of one group between reads of the shared threshold (power of two)
 
 // Operand arithmetic of the tensor-core pass
 //   TC_TF32X1  kind::tf32, one product                    (exact when operands are TF32-representable)
@@ -52,8 +52,9 @@ struct TcSmem {
     static constexpr int NSTAGE = MODE == TC_F16 ? 10 : (SPLIT3 ? 5 : 8);
     static constexpr int B_BYTES = NSTAGE * TC_KB_BYTES;
     static constexpr int NORM_BYTES = TC_NACC * TC_BN * 4;
+    static constexpr int PUB_BYTES = TC_EPI_GROUPS * TC_BM * 8;  // per (group, query row): {key, unit tag}
     static constexpr int BAR_BYTES = 1024;
-    static constexpr int TOTAL = A_BYTES + B_BYTES + NORM_BYTES + BAR_BYTES + 1024;  // + slack for 1024-B alignment
+    static constexpr int TOTAL = A_BYTES + B_BYTES + NORM_BYTES + PUB_BYTES + BAR_BYTES + 1024;  // + slack for 1024-B alignment
 };
 
 struct TcParams {
@@ -87,6 +88,14 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
     return v;
 }
+__device__ __forceinline__ uint2 lds64_volatile(uint32_t addr) {
+    uint2 v;
+    asm volatile("ld.volatile.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts64_volatile(uint32_t addr, uint2 v) {
+    asm volatile("st.volatile.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(v.x), "r"(v.y) : "memory");
+}
 __device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -111,7 +120,8 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
     uint8_t* sA = smem;
     uint8_t* sB = smem + S::A_BYTES;
     float* sN = (float*)(sB + S::B_BYTES);      // [TC_NACC][128] base norms of the tile in accumulator slot i
-    uint64_t* bars = (uint64_t*)((uint8_t*)sN + S::NORM_BYTES);
+    uint2* sPub = (uint2*)((uint8_t*)sN + S::NORM_BYTES);  // [TC_EPI_GROUPS][TC_BM]
+    uint64_t* bars = (uint64_t*)((uint8_t*)sPub + S::PUB_BYTES);
     uint64_t* full = bars;                    // [NSTAGE]  TMA -> MMA
     uint64_t* empty = full + NSTAGE;          // [NSTAGE]  MMA -> TMA
     uint64_t* acc_full = empty + NSTAGE;      // [TC_NACC] MMA -> epilogue
@@ -131,7 +141,7 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         }
         for (int i = 0; i < TC_NACC; ++i) {
             mbar_init(&acc_full[i], 1);
-            mbar_init(&acc_empty[i], 4 * TC_EPI_GROUPS);
+            mbar_init(&acc_empty[i], 4);  // the four warps of the group that consumed the tile
             mbar_init(&n_full[i], 1);
         }
         mbar_init(a_full, 1);
@@ -149,14 +159,21 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
 
     const int n_units = p.n_mtiles * p.n_splits;
 
-    if (warp == 0) {
+    if (warp < 4) {
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TC_REGS_CTRL));
+      if (warp == 0) {
         // ===================================== TMA producer =====================================
-        if (lane == 0) {
-            tma_prefetch_desc(&tmA_hi);
-            tma_prefetch_desc(&tmB_hi);
-            if (SPLIT3) {
-                tma_prefetch_desc(&tmA_lo);
-                tma_prefetch_desc(&tmB_lo);
+        // the whole warp walks the loop (warp-uniform addresses stay in uniform registers); one elected lane
+        // issues the asynchronous copies and barrier operations
+        const bool leader = elect_one();
+        {
+            if (leader) {
+                tma_prefetch_desc(&tmA_hi);
+                tma_prefetch_desc(&tmB_hi);
+                if (SPLIT3) {
+                    tma_prefetch_desc(&tmA_lo);
+                    tma_prefetch_desc(&tmB_lo);
+                }
             }
             int stage = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0;
@@ -165,37 +182,45 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
                 const int m_tile = unit % p.n_mtiles;
                 const int split = unit / p.n_mtiles;
                 mbar_wait(a_empty, (uint32_t)((it & 1) ^ 1));
-                mbar_expect_tx(a_full, (uint32_t)S::A_BYTES);
+                if (leader) {
+                    mbar_expect_tx(a_full, (uint32_t)S::A_BYTES);
 #pragma unroll
-                for (int kb = 0; kb < TC_NKB; ++kb) {
-                    tma_load_2d(sA + kb * TC_KB_BYTES, &tmA_hi, a_full, kb * KB_ELEMS, m_tile * TC_BM);
-                    if (SPLIT3) tma_load_2d(sA + (TC_NKB + kb) * TC_KB_BYTES, &tmA_lo, a_full, kb * 32, m_tile * TC_BM);
+                    for (int kb = 0; kb < TC_NKB; ++kb) {
+                        tma_load_2d(sA + kb * TC_KB_BYTES, &tmA_hi, a_full, kb * KB_ELEMS, m_tile * TC_BM);
+                        if (SPLIT3) tma_load_2d(sA + (TC_NKB + kb) * TC_KB_BYTES, &tmA_lo, a_full, kb * 32, m_tile * TC_BM);
+                    }
                 }
                 const int t0 = split * p.tiles_per_split;
                 const int t1 = min(t0 + p.tiles_per_split, p.n_tiles);
                 for (int t = t0; t < t1; ++t) {
                     // norms of this tile go to the slot of the accumulator the tile will use
                     mbar_wait(&acc_empty[acc], acc_phase ^ 1);
-                    mbar_expect_tx(&n_full[acc], (uint32_t)(TC_BN * 4));
-                    bulk_load_1d(sN + acc * TC_BN, p.bnorm + (size_t)t * TC_BN, TC_BN * 4, &n_full[acc]);
+                    if (leader) {
+                        mbar_expect_tx(&n_full[acc], (uint32_t)(TC_BN * 4));
+                        bulk_load_1d(sN + acc * TC_BN, p.bnorm + (size_t)t * TC_BN, TC_BN * 4, &n_full[acc]);
+                    }
                     if (++acc == TC_NACC) { acc = 0; acc_phase ^= 1; }
 #pragma unroll
                     for (int kb = 0; kb < TC_NKB; ++kb) {
                         mbar_wait(&empty[stage], phase ^ 1);
-                        if (p.dbg & 8) {
-                            mbar_arrive(&full[stage]);
-                        } else {
-                            mbar_expect_tx(&full[stage], (uint32_t)TC_KB_BYTES);
-                            tma_load_2d(sB + stage * TC_KB_BYTES, &tmB_hi, &full[stage], kb * KB_ELEMS, t * TC_BN);
-                        }
-                        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
-                        if (SPLIT3) {
-                            mbar_wait(&empty[stage], phase ^ 1);
+                        if (leader) {
                             if (p.dbg & 8) {
                                 mbar_arrive(&full[stage]);
                             } else {
                                 mbar_expect_tx(&full[stage], (uint32_t)TC_KB_BYTES);
-                                tma_load_2d(sB + stage * TC_KB_BYTES, &tmB_lo, &full[stage], kb * 32, t * TC_BN);
+                                tma_load_2d(sB + stage * TC_KB_BYTES, &tmB_hi, &full[stage], kb * KB_ELEMS, t * TC_BN);
+                            }
+                        }
+                        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                        if (SPLIT3) {
+                            mbar_wait(&empty[stage], phase ^ 1);
+                            if (leader) {
+                                if (p.dbg & 8) {
+                                    mbar_arrive(&full[stage]);
+                                } else {
+                                    mbar_expect_tx(&full[stage], (uint32_t)TC_KB_BYTES);
+                                    tma_load_2d(sB + stage * TC_KB_BYTES, &tmB_lo, &full[stage], kb * 32, t * TC_BN);
+                                }
                             }
                             if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
                         }
@@ -205,7 +230,8 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         }
     } else if (warp == 1) {
         // ===================================== MMA issuer =======================================
-        if (lane == 0) {
+        const bool leader = elect_one();  // the same lane issues every MMA and every commit
+        {
             constexpr uint32_t idesc = umma_idesc(kIdescCF32, MODE == TC_F16 ? kIdescF16 : kIdescTF32, TC_BM, TC_BN);
             const uint32_t sA_u = smem_u32(sA);
             const uint32_t sB_u = smem_u32(sB);
@@ -222,7 +248,6 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
                     mbar_wait(&acc_empty[acc], acc_phase ^ 1);
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TC_BN);
-                    uint32_t accum = 0;
 #pragma unroll
                     for (int kb = 0; kb < TC_NKB; ++kb) {
                         const uint64_t a_hi = umma_desc_sw128(sA_u + kb * TC_KB_BYTES);
@@ -232,56 +257,58 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
                         tc_fence_after();
                         {
                             const uint64_t b = umma_desc_sw128(sB_u + stage * TC_KB_BYTES);
-                            if (SPLIT3 && !(p.dbg & 4)) {
+                            if (SPLIT3 && !(p.dbg & 4) && leader) {
 #pragma unroll
-                                for (int ks = 0; ks < 4; ++ks) {  // q_lo . x_hi   (small term first)
-                                    tc_mma_tf32(d_tmem, a_lo + 2 * ks, b + 2 * ks, idesc, accum);
-                                    accum = 1;
-                                }
+                                for (int ks = 0; ks < 4; ++ks)    // q_lo . x_hi   (small term first)
+                                    tc_mma_tf32(d_tmem, a_lo + 2 * ks, b + 2 * ks, idesc, (kb | ks) ? 1u : 0u);
                             }
-                            if (!(p.dbg & 4)) {
+                            if (!(p.dbg & 4) && leader) {
 #pragma unroll
                                 for (int ks = 0; ks < 4; ++ks) {  // q_hi . x_hi   (32 bytes of K per instruction)
                                     if (MODE == TC_F16)
-                                        tc_mma_f16(d_tmem, a_hi + 2 * ks, b + 2 * ks, idesc, accum);
+                                        tc_mma_f16(d_tmem, a_hi + 2 * ks, b + 2 * ks, idesc, (kb | ks) ? 1u : 0u);
                                     else
-                                        tc_mma_tf32(d_tmem, a_hi + 2 * ks, b + 2 * ks, idesc, accum);
-                                    accum = 1;
+                                        tc_mma_tf32(d_tmem, a_hi + 2 * ks, b + 2 * ks, idesc, (SPLIT3 || (kb | ks)) ? 1u : 0u);
                                 }
                             }
                         }
-                        tc_commit(&empty[stage]);
+                        if (leader) tc_commit(&empty[stage]);
                         if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
                         if (SPLIT3) {
                             // ---- stage holding x_lo[kb]
                             mbar_wait(&full[stage], phase);
                             tc_fence_after();
                             const uint64_t b = umma_desc_sw128(sB_u + stage * TC_KB_BYTES);
-                            if (!(p.dbg & 4)) {
+                            if (!(p.dbg & 4) && leader) {
 #pragma unroll
                                 for (int ks = 0; ks < 4; ++ks)    // q_hi . x_lo
                                     tc_mma_tf32(d_tmem, a_hi + 2 * ks, b + 2 * ks, idesc, 1u);
                             }
-                            tc_commit(&empty[stage]);
+                            if (leader) tc_commit(&empty[stage]);
                             if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
                         }
                     }
-                    tc_commit(&acc_full[acc]);
+                    if (leader) tc_commit(&acc_full[acc]);
                     if (++acc == TC_NACC) { acc = 0; acc_phase ^= 1; }
                 }
-                tc_commit(a_empty);
+                if (leader) tc_commit(a_empty);
             }
         }
+      }
     } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(TC_REGS_EPI));
         // ===================================== epilogue ==========================================
+        // Tiles rotate over the TC_EPI_GROUPS warpgroups (the CTA's running tile count modulo the group count), so
+        // several tiles are in flight in the epilogue and each warp's TMEM-load / barrier latencies are covered by
+        // the other groups' arithmetic.  A thread owns one query row of its group's tiles (all 128 columns).
         const int quad = warp & 3;
-        const int grp = (warp - 2) >> 2;  // column half handled by this warpgroup
+        const int grp = (warp - 4) >> 2;
         const int row = quad * 32 + lane;
         const float INF = __int_as_float(0x7f800000);
         const float key_scale = MODE == TC_F16 ? __ldg(p.key_scale_ptr) : -2.0f;
-        constexpr int CH = TC_GCOLS / 32;  // 32-column chunks per thread per tile
-        int acc = 0;
-        uint32_t acc_phase = 0;
+        constexpr int CH = TC_BN / 32;        // 32-column chunks per thread per tile
+        constexpr bool DB = KTOP <= 16;       // double-buffered TMEM loads while the register budget allows
+        int tcount = 0;                       // tiles this CTA has gone through before the current unit
         for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
             const int m_tile = unit % p.n_mtiles;
             const int split = unit / p.n_mtiles;
@@ -299,91 +326,118 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
             }
             RegTopK<KTOP> top;
             top.init();
-            // cap = smallest "worst kept key" published by any full list of this query so far.  Keys equal to it
-            // may still belong to the canonical answer (smaller id), hence the strict test against next_up(cap).
+            // Threshold sharing.  The groups of a CTA hold disjoint lists of the same query: once each of them keeps
+            // at least SUB = ceil(KTOP / groups) entries, the largest of their SUB-th best keys bounds the query's
+            // KTOP-th best key (groups x SUB >= KTOP rows lie at or below it).  Each thread posts its SUB-th best key,
+            // tagged with the unit it belongs to (groups run a few tiles apart and may be in different units), in
+            // shared memory; the combined bound also goes to the global per-query array read by the other CTAs.
+            // cap = best such bound seen so far.  Keys equal to it may still belong to the canonical answer (smaller
+            // id), hence the strict test against next_up(cap).
+            constexpr int SUB = (KTOP + TC_EPI_GROUPS - 1) / TC_EPI_GROUPS;
+            const uint32_t my_pub = smem_u32(sPub + grp * TC_BM + row);
+            sts64_volatile(my_pub, make_uint2(__float_as_uint(INF), (uint32_t)unit));
             float cap = INF;
             float thr = INF;  // invariant: thr == min(top.threshold(), next_up(cap))
-            for (int t = t0; t < t1; ++t) {
-                const int rel = (t - t0) & (TC_THR_REFRESH - 1);
-                if (rel == 0 && valid) {
-                    cap = fminf(cap, ordered_to_float(__ldcg(p.gthr + q)));
+            // shared threshold: the value consumed at a refresh point was requested one refresh earlier
+            int32_t pending = valid ? __ldcg(p.gthr + q) : 0x7f7f7f7f;
+            int first = (grp - tcount % TC_EPI_GROUPS + TC_EPI_GROUPS) % TC_EPI_GROUPS;
+            int j = 0;  // tiles of this unit seen by this group
+            for (int i = first; i < t1 - t0; i += TC_EPI_GROUPS, ++j) {
+                const int t = t0 + i;
+                const int tc = tcount + i;
+                const int acc = tc & (TC_NACC - 1);
+                const uint32_t acc_phase = (uint32_t)(tc / TC_NACC) & 1u;
+                const int rel = j & (TC_THR_REFRESH - 1);
+                if (valid) {
+                    // bound from the sibling groups' posts (every tile: three 8-byte shared loads)
+                    float comb = top.key[SUB - 1];
+#pragma unroll
+                    for (int g = 1; g < TC_EPI_GROUPS; ++g) {
+                        const uint2 o = lds64_volatile(smem_u32(sPub + ((grp + g) % TC_EPI_GROUPS) * TC_BM + row));
+                        comb = fmaxf(comb, o.y == (uint32_t)unit ? __uint_as_float(o.x) : INF);
+                    }
+                    if (comb < cap) {
+                        cap = comb;
+                        if (rel == TC_THR_REFRESH - 1) atomicMin(p.gthr + q, float_to_ordered(comb));
+                    }
+                    if (rel == 0) {
+                        cap = fminf(cap, ordered_to_float(pending));
+                        pending = __ldcg(p.gthr + q);
+                    }
                     thr = fminf(top.threshold(), next_up(cap));
                 }
                 mbar_wait(&n_full[acc], acc_phase);
                 mbar_wait(&acc_full[acc], acc_phase);
                 tc_fence_after();
-                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * TC_BN + grp * TC_GCOLS);
-                const uint32_t bn_s = smem_u32(sN + acc * TC_BN + grp * TC_GCOLS);
-                uint32_t r[2][32];
+                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * TC_BN);
+                const uint32_t bn_s = smem_u32(sN + acc * TC_BN);
+                uint32_t r[DB ? 2 : 1][32];
                 const bool skip = (p.dbg & 1) || !quad_live;
-                if (!skip && !(p.dbg & 32)) tmem_ld32(taddr, r[0]);
+                if (!skip) tmem_ld32(taddr, r[0]);
 #pragma unroll
                 for (int c = 0; c < CH; ++c) {
                     if (skip) break;
-                    if (!(p.dbg & 32)) {
-                        tc_wait_ld();
-                        if (c + 1 < CH) tmem_ld32(taddr + (c + 1) * 32, r[(c + 1) & 1]);
-                    }
-                    if (p.dbg & 16) continue;
-                    const int col0 = t * TC_BN + grp * TC_GCOLS + c * 32;
+                    tc_wait_ld();
+                    if (DB && c + 1 < CH) tmem_ld32(taddr + (c + 1) * 32, r[(c + 1) & 1]);
+                    const int col0 = t * TC_BN + c * 32;
                     float d[32];
 #pragma unroll
                     for (int j4 = 0; j4 < 8; ++j4) {
                         const float4 bn = lds128(bn_s + (uint32_t)(c * 32 + 4 * j4) * 4u);  // smem broadcast
+                        const uint32_t* rr = r[DB ? (c & 1) : 0] + 4 * j4;
                         if (MODE == TC_F16) {
-                            d[4 * j4 + 0] = fmaf(key_scale, __uint_as_float(r[c & 1][4 * j4 + 0]), bn.x);
-                            d[4 * j4 + 1] = fmaf(key_scale, __uint_as_float(r[c & 1][4 * j4 + 1]), bn.y);
-                            d[4 * j4 + 2] = fmaf(key_scale, __uint_as_float(r[c & 1][4 * j4 + 2]), bn.z);
-                            d[4 * j4 + 3] = fmaf(key_scale, __uint_as_float(r[c & 1][4 * j4 + 3]), bn.w);
+                            d[4 * j4 + 0] = fmaf(key_scale, __uint_as_float(rr[0]), bn.x);
+                            d[4 * j4 + 1] = fmaf(key_scale, __uint_as_float(rr[1]), bn.y);
+                            d[4 * j4 + 2] = fmaf(key_scale, __uint_as_float(rr[2]), bn.z);
+                            d[4 * j4 + 3] = fmaf(key_scale, __uint_as_float(rr[3]), bn.w);
                         } else {
-                            d[4 * j4 + 0] = fmaf(-2.0f, __uint_as_float(r[c & 1][4 * j4 + 0]), bn.x);
-                            d[4 * j4 + 1] = fmaf(-2.0f, __uint_as_float(r[c & 1][4 * j4 + 1]), bn.y);
-                            d[4 * j4 + 2] = fmaf(-2.0f, __uint_as_float(r[c & 1][4 * j4 + 2]), bn.z);
-                            d[4 * j4 + 3] = fmaf(-2.0f, __uint_as_float(r[c & 1][4 * j4 + 3]), bn.w);
+                            d[4 * j4 + 0] = fmaf(-2.0f, __uint_as_float(rr[0]), bn.x);
+                            d[4 * j4 + 1] = fmaf(-2.0f, __uint_as_float(rr[1]), bn.y);
+                            d[4 * j4 + 2] = fmaf(-2.0f, __uint_as_float(rr[2]), bn.z);
+                            d[4 * j4 + 3] = fmaf(-2.0f, __uint_as_float(rr[3]), bn.w);
                         }
                     }
+                    if (!DB && c + 1 < CH) tmem_ld32(taddr + (c + 1) * 32, r[0]);  // r[0] is dead from here on
+                    if (p.dbg & 16) continue;
                     if (HAS_LB) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const bool after = d[j] > lbk || (d[j] == lbk && (col0 + j) > lbi);
-                            d[j] = after ? d[j] : INF;
+                        for (int jj = 0; jj < 32; ++jj) {
+                            const bool after = d[jj] > lbk || (d[jj] == lbk && (col0 + jj) > lbi);
+                            d[jj] = after ? d[jj] : INF;
                         }
                     }
                     float m[16];  // pairwise min tree (depth 5)
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) m[j] = fminf(d[j], d[j + 16]);
+                    for (int jj = 0; jj < 16; ++jj) m[jj] = fminf(d[jj], d[jj + 16]);
 #pragma unroll
                     for (int w = 8; w >= 1; w >>= 1)
 #pragma unroll
-                        for (int j = 0; j < w; ++j) m[j] = fminf(m[j], m[j + w]);
+                        for (int jj = 0; jj < w; ++jj) m[jj] = fminf(m[jj], m[jj + w]);
                     if (m[0] < thr && !(p.dbg & 2)) {
                         // rare path: bit mask of the qualifying columns, then one insertion per set bit
                         uint32_t mask = 0;
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) mask |= (d[j] < thr) ? (1u << j) : 0u;
+                        for (int jj = 0; jj < 32; ++jj) mask |= (d[jj] < thr) ? (1u << jj) : 0u;
                         while (mask) {
-                            const int j = __ffs(mask) - 1;
+                            const int jj = __ffs(mask) - 1;
                             mask &= mask - 1;
-                            const float v = select32(d, j);
+                            const float v = select32(d, jj);
                             if (v < thr) {
-                                top.insert(v, col0 + j);
+                                top.insert(v, col0 + jj);
                                 thr = fminf(thr, top.threshold());
                             }
                         }
+                        // +inf until SUB entries are kept
+                        sts64_volatile(my_pub, make_uint2(__float_as_uint(top.key[SUB - 1]), (uint32_t)unit));
                     }
                 }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&acc_empty[acc]);
-                if (++acc == TC_NACC) { acc = 0; acc_phase ^= 1; }
-                // publish this list's worst kept key: a valid upper bound of the query's KTOP-th best key
-                if (valid && rel == TC_THR_REFRESH - 1 && top.threshold() < cap) {
-                    atomicMin(p.gthr + q, float_to_ordered(top.threshold()));
-                    cap = top.threshold();
-                }
             }
+            tcount += t1 - t0;
             if (valid) {
-                if (top.threshold() < cap) atomicMin(p.gthr + q, float_to_ordered(top.threshold()));
+                if (cap < INF) atomicMin(p.gthr + q, float_to_ordered(cap));
                 const size_t list = (size_t)split * TC_EPI_GROUPS + grp;
                 float* pk = p.part_key + (list * p.nq + q) * KTOP;
                 int32_t* pi = p.part_id + (list * p.nq + q) * KTOP;
