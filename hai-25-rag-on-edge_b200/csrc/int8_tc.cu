@@ -104,9 +104,13 @@ int8_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int n_units = p.n_mtiles * p.n_splits;
 
     if (warp == 0) {
-        if (lane == 0) {
-            tma_prefetch_desc(&tmA);
-            tma_prefetch_desc(&tmB);
+        // whole warp walks the loop (uniform addresses), one elected lane issues the copies
+        const bool leader = elect_one();
+        {
+            if (leader) {
+                tma_prefetch_desc(&tmA);
+                tma_prefetch_desc(&tmB);
+            }
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
@@ -114,20 +118,25 @@ int8_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int m_tile = unit % p.n_mtiles;
                 const int split = unit / p.n_mtiles;
                 mbar_wait(a_empty, (uint32_t)((it & 1) ^ 1));
-                mbar_expect_tx(a_full, (uint32_t)I8_TILE_BYTES);
-                tma_load_2d(sA, &tmA, a_full, 0, m_tile * I8_BM);
+                if (leader) {
+                    mbar_expect_tx(a_full, (uint32_t)I8_TILE_BYTES);
+                    tma_load_2d(sA, &tmA, a_full, 0, m_tile * I8_BM);
+                }
                 const int t0 = split * p.tiles_per_split;
                 const int t1 = min(t0 + p.tiles_per_split, p.n_tiles);
                 for (int t = t0; t < t1; ++t) {
                     mbar_wait(&empty[stage], phase ^ 1);
-                    mbar_expect_tx(&full[stage], (uint32_t)I8_TILE_BYTES);
-                    tma_load_2d(sB + stage * I8_TILE_BYTES, &tmB, &full[stage], 0, t * I8_BN);
+                    if (leader) {
+                        mbar_expect_tx(&full[stage], (uint32_t)I8_TILE_BYTES);
+                        tma_load_2d(sB + stage * I8_TILE_BYTES, &tmB, &full[stage], 0, t * I8_BN);
+                    }
                     if (++stage == I8_NSTAGE) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        const bool leader = elect_one();  // the same lane issues every MMA and commit
+        {
             constexpr uint32_t idesc = umma_idesc(kIdescCS32, kIdescU8, I8_BM, I8_BN);
             const uint64_t a_desc = umma_desc_sw128(smem_u32(sA));
             const uint32_t sB_u = smem_u32(sB);
@@ -146,15 +155,17 @@ int8_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + (uint32_t)(acc * I8_BN);
                     const uint64_t b_desc = umma_desc_sw128(sB_u + stage * I8_TILE_BYTES);
+                    if (leader) {
 #pragma unroll
-                    for (int ks = 0; ks < 4; ++ks)  // K = 32 u8 = 32 B per step
-                        tc_mma_i8(d_tmem, a_desc + 2 * ks, b_desc + 2 * ks, idesc, ks > 0 ? 1u : 0u);
-                    tc_commit(&empty[stage]);
-                    tc_commit(&acc_full[acc]);
+                        for (int ks = 0; ks < 4; ++ks)  // K = 32 u8 = 32 B per step
+                            tc_mma_i8(d_tmem, a_desc + 2 * ks, b_desc + 2 * ks, idesc, ks > 0 ? 1u : 0u);
+                        tc_commit(&empty[stage]);
+                        tc_commit(&acc_full[acc]);
+                    }
                     if (++stage == I8_NSTAGE) { stage = 0; phase ^= 1; }
                     if (++acc == I8_NACC) { acc = 0; acc_phase ^= 1; }
                 }
-                tc_commit(a_empty);
+                if (leader) tc_commit(a_empty);
             }
         }
     } else {
