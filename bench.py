@@ -197,8 +197,9 @@ def main():
     nq, k = args.nq, TOPK
 
     # base shard of this rank, generated on the device (bit-identical to the numpy generator)
-    r0 = (N_BASE * rank) // world
-    r1 = (N_BASE * (rank + 1)) // world
+    from vsb200 import sharded as vsb_sharded
+
+    r0, r1 = vsb_sharded.shard_range(N_BASE, rank, world)
     base_d = torch.empty((r1 - r0, DIM), dtype=torch.float32, device=dev)
     vsb.synth_fill_dev(base_d.data_ptr(), r0, r1 - r0, DIM, LAW, BASE_SEED)
     torch.cuda.synchronize()
@@ -207,12 +208,6 @@ def main():
 
     q_host = torch.from_numpy(vsb.synth.make(LAW, QUERY_SEED, nq)).pin_memory()
     q_dev = q_host.to(dev)
-    ids_loc = torch.empty((nq, k), dtype=torch.int32, device=dev)
-    d_loc = torch.empty((nq, k), dtype=torch.float32, device=dev)
-    ids_all = torch.empty((world, nq, k), dtype=torch.int32, device=dev)
-    d_all = torch.empty((world, nq, k), dtype=torch.float32, device=dev)
-    ids_out = torch.empty((nq, k), dtype=torch.int32, device=dev)
-    d_out = torch.empty((nq, k), dtype=torch.float32, device=dev)
     ids_h = torch.empty((nq, k), dtype=torch.int32).pin_memory()
     d_h = torch.empty((nq, k), dtype=torch.float32).pin_memory()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
@@ -221,16 +216,11 @@ def main():
     torch.cuda.set_stream(stream)
     sptr = stream.cuda_stream
     assert sptr != 0
+    searcher = vsb_sharded.ShardedExact(vsb, index, nq, k, dev)
 
     def device_step(q_ptr):
-        index.search_dev(q_ptr, nq, k, prec, ids_loc.data_ptr(), d_loc.data_ptr(), sptr)
-        if world > 1:
-            dist.all_gather_into_tensor(ids_all, ids_loc)
-            dist.all_gather_into_tensor(d_all, d_loc)
-            vsb.merge_topk_dev(ids_all.data_ptr(), d_all.data_ptr(), world, nq, k, True, ids_out.data_ptr(),
-                               d_out.data_ptr(), sptr)
-            return ids_out, d_out
-        return ids_loc, d_loc
+        # local fused search; for N > 1: NCCL all-gather of the [nq x k] candidates + merge kernel
+        return searcher.search(q_ptr, nq, prec, sptr)
 
     q_stage = torch.empty_like(q_dev)
 
