@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -250,7 +251,7 @@ static int exact_search_certified(vs_exact* h, const float* q_dev, int64_t nq, i
     VSB_TRY(launch_tc_query_params(reinterpret_cast<const float*>(flag + 2), h->s_b, h->bn_max, qp, st));
     VSB_TRY(launch_to_half_scaled(q_dev, nq * 128, 1.f, qp, h->qf16.p, st));
     const TcPlan plan = tc_make_plan(h->n, nq, h->num_sms);
-    const int n_lists = plan.n_splits * tc_lists_per_split();
+    const int n_lists = plan.n_splits * tc_lists_per_split(2);
     VSB_TRY(h->part_key.reserve(sizeof(float) * (size_t)n_lists * nq * ktop));
     VSB_TRY(h->part_id.reserve(sizeof(int32_t) * (size_t)n_lists * nq * ktop));
     VSB_TRY(h->gthr.reserve(sizeof(int32_t) * (size_t)nq));
@@ -343,7 +344,7 @@ static int exact_search_core(vs_exact* h, const float* q_dev, int64_t nq, int k,
         VSB_TRY(exact_ensure_split(h, split3, st));
         h->last_precision = split3 ? VS_PREC_FP32_3XTF32 : VS_PREC_TF32_1X;
         const TcPlan plan = tc_make_plan(h->n, nq, h->num_sms);
-        const int n_lists = plan.n_splits * tc_lists_per_split();
+        const int n_lists = plan.n_splits * tc_lists_per_split(split3 ? 1 : 0);
         VSB_TRY(h->part_key.reserve(sizeof(float) * (size_t)n_lists * nq * ktop));
         VSB_TRY(h->part_id.reserve(sizeof(int32_t) * (size_t)n_lists * nq * ktop));
         VSB_TRY(h->gthr.reserve(sizeof(int32_t) * (size_t)nq));
@@ -524,7 +525,9 @@ int vs_merge_topk_dev(const int32_t* ids_dev, const float* keys_dev, int n_shard
                       int32_t* out_ids_dev, float* out_keys_dev, void* stream) {
     if (!ids_dev || !keys_dev || !out_ids_dev || !out_keys_dev) return fail(VS_ERR_INVALID, "NULL buffer");
     if (n_shards <= 0 || nq < 0 || k <= 0) return fail(VS_ERR_INVALID, "bad sizes");
-    if (k > kMaxRegK) return fail(VS_ERR_UNSUPPORTED, "merge of k > 32 lists is not implemented");
+    if (k > kMaxRegK)
+        return launch_merge_shards(keys_dev, ids_dev, n_shards, nq, k, smallest ? 0 : 1, out_keys_dev, out_ids_dev,
+                                   (cudaStream_t)stream);
     return launch_merge_lists(keys_dev, ids_dev, n_shards, nq, k, k, k, 0, smallest ? 0 : 1, smallest ? 0 : 1,
                               out_keys_dev, out_ids_dev, k, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
                               (cudaStream_t)stream);

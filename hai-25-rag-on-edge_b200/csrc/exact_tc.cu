@@ -2,6 +2,7 @@
 #include "exact_tc.cuh"
 
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 
 #include "kernels.cuh"
@@ -46,7 +47,7 @@ static int set_attr_one() {
     return VS_OK;
 }
 
-int tc_lists_per_split() { return TC_EPI_GROUPS; }
+int tc_lists_per_split(int mode) { return mode == TC_F16 ? 1 : TC_EPI_GROUPS; }
 
 int tc_set_attributes() {
     VSB_TRY((set_attr_one<1, TC_TF32X1, false>()));
@@ -61,7 +62,6 @@ int tc_set_attributes() {
     VSB_TRY((set_attr_one<32, TC_TF32X3, false>()));
     VSB_TRY((set_attr_one<32, TC_TF32X1, true>()));
     VSB_TRY((set_attr_one<32, TC_TF32X3, true>()));
-    VSB_TRY((set_attr_one<16, TC_F16, false>()));
     VSB_TRY((set_attr_one<32, TC_F16, false>()));
     return VS_OK;
 }
@@ -90,10 +90,17 @@ int launch_exact_tc(const CUtensorMap& tmA_hi, const CUtensorMap& tmA_lo, const 
         const char* e = getenv("VSB_TC_DBG");
         p.dbg = e ? atoi(e) : 0;
     }
+    static unsigned long long* d_stats = nullptr;
+    const bool want_stats = getenv("VSB_TC_STATS") != nullptr;
+    if (want_stats) {
+        if (!d_stats) VSB_CUDA(cudaMalloc((void**)&d_stats, 16 * sizeof(unsigned long long)));
+        VSB_CUDA(cudaMemsetAsync(d_stats, 0, 16 * sizeof(unsigned long long), st));
+        p.stats = d_stats;
+    }
     if (lb_key && ktop != 32) return fail(VS_ERR_INVALID, "tc: lower bound needs the 32-entry list");
     if (lb_key && mode == TC_F16) return fail(VS_ERR_INVALID, "tc: the fp16 candidate pass has no multi-pass mode");
 #define VSB_TC_LAUNCH(KT, MD, LB)                                                                                \
-    exact_tc_kernel<KT, MD, LB><<<plan.grid, TC_THREADS, TcSmem<MD>::TOTAL, st>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, p)
+    exact_tc_kernel<KT, MD, LB><<<plan.grid, TcSmem<MD>::THREADS, TcSmem<MD>::TOTAL, st>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, p)
 #define VSB_TC_CASE(KT)                              \
     case KT:                                         \
         if (mode == TC_TF32X3)                       \
@@ -102,12 +109,10 @@ int launch_exact_tc(const CUtensorMap& tmA_hi, const CUtensorMap& tmA_lo, const 
             VSB_TC_LAUNCH(KT, TC_TF32X1, false);     \
         break;
     if (mode == TC_F16) {
-        if (ktop == 16)
-            VSB_TC_LAUNCH(16, TC_F16, false);
-        else if (ktop == 32)
+        if (ktop == 32)
             VSB_TC_LAUNCH(32, TC_F16, false);
         else
-            return fail(VS_ERR_INVALID, "tc: fp16 pass supports list sizes 16 and 32");
+            return fail(VS_ERR_INVALID, "tc: the fp16 candidate pass keeps 32 candidates per query");
     } else {
         switch (ktop) {
             VSB_TC_CASE(1)
@@ -134,6 +139,24 @@ int launch_exact_tc(const CUtensorMap& tmA_hi, const CUtensorMap& tmA_lo, const 
 #undef VSB_TC_CASE
 #undef VSB_TC_LAUNCH
     VSB_CUDA(cudaGetLastError());
+    if (want_stats) {
+        unsigned long long hs[16];
+        VSB_CUDA(cudaMemcpyAsync(hs, d_stats, sizeof(hs), cudaMemcpyDeviceToHost, st));
+        VSB_CUDA(cudaStreamSynchronize(st));
+        const double chunks = (double)plan.n_mtiles * 4.0 * plan.n_tiles * 4.0;  // warp-chunks of the whole sweep
+        fprintf(stderr, "[tc stats] mode=%d ktop=%d splits=%d: warp slow-path entries %llu (%.2f%% of warp-chunks), lane entries %llu, "
+                "qualifying %llu, inserts %llu (%.1f per query)\n", mode, ktop, plan.n_splits, hs[0], 100.0 * hs[0] / chunks, hs[1],
+                hs[2], hs[3], (double)hs[3] / nq);
+        if (hs[5])
+            fprintf(stderr, "[tc stats] keeper: %llu batches, %.1f entries/batch, %.0f busy cycles/batch (%.2f Mcycles per keeper warp); "
+                    "producer hand-off: %.0f cycles per warp entry (%.2f Mcycles per epilogue warp)\n", hs[5], (double)hs[4] / hs[5],
+                    (double)hs[6] / hs[5], (double)hs[6] / (4.0 * plan.grid) / 1e6, hs[0] ? (double)hs[7] / hs[0] : 0.0,
+                    (double)hs[7] / (12.0 * plan.grid) / 1e6);
+        if (hs[5])
+            fprintf(stderr, "[tc stats] keeper: header+scan %.0f cycles/batch, match %.0f cycles/batch, %.2f rounds/batch, %.0f cycles/round\n",
+                    (double)hs[8] / hs[5], (double)hs[10] / hs[5], (double)hs[9] / hs[5],
+                    hs[9] ? (double)(hs[6] - hs[8] - hs[10]) / hs[9] : 0.0);
+    }
     return VS_OK;
 }
 

@@ -34,6 +34,14 @@ constexpr int TC_NACC = 4;        // accumulator buffers in TMEM (4 x 128 column
 constexpr int TC_EPI_GROUPS = 3;  // epilogue warpgroups; tiles rotate over them
 constexpr int TC_THREADS = 128 + 128 * TC_EPI_GROUPS;  // warpgroup 0: TMA producer, MMA issuer, two idle warps
 constexpr int TC_REGS_CTRL = 80, TC_REGS_EPI = 144;   // setmaxnreg budgets: 128*80 + 384*144 == 64K registers
+// TC_F16 adds a fifth warpgroup of four list-keeper warps (one per TMEM lane quadrant): 640 threads start with 96
+// registers (61440); control and keeper warpgroups drop to 48, the three epilogue warpgroups rise to 128 (2*128*48 + 384*128 == 61440:
+// setmaxnreg.inc can only take what the CTA itself released)
+constexpr int TC_THREADS_Q = TC_THREADS + 128;
+constexpr int TC_REGS_SMALL_Q = 48, TC_REGS_EPI_Q = 128;
+constexpr int TC_QN = 64;             // candidate-queue entries per quadrant
+constexpr int TC_QENTRY = 144;        // bytes per entry: 32 keys + {row in quadrant, first column, threshold, -}
+constexpr int TC_LROW = 36 * 4;       // bytes per shared-memory list row: 32 keys (or ids) + 16 bytes of padding (banks)
 constexpr int TC_THR_REFRESH = 4; // tiles of one group between reads of the shared threshold (power of two)
 
 // Operand arithmetic of the tensor-core pass
@@ -49,12 +57,21 @@ struct TcSmem {
     static constexpr bool SPLIT3 = MODE == TC_TF32X3;
     static constexpr int NKB = MODE == TC_F16 ? 2 : 4;  // 128-byte k-blocks per row (128 fp16 = 256 B, 128 fp32 = 512 B)
     static constexpr int A_BYTES = (SPLIT3 ? 2 : 1) * NKB * TC_KB_BYTES;
-    static constexpr int NSTAGE = MODE == TC_F16 ? 10 : (SPLIT3 ? 5 : 8);
+    // TC_F16 keeps ONE candidate list per query row in shared memory, maintained by dedicated list-keeper warps that
+    // are fed through per-quadrant queues; the other modes keep per-thread register lists (their query tile leaves
+    // no room: 64 / 128 KB)
+    static constexpr bool SMEM_LIST = MODE == TC_F16;
+    static constexpr int THREADS = SMEM_LIST ? TC_THREADS_Q : TC_THREADS;
+    static constexpr int NSTAGE = MODE == TC_F16 ? 7 : (SPLIT3 ? 5 : 8);
     static constexpr int B_BYTES = NSTAGE * TC_KB_BYTES;
     static constexpr int NORM_BYTES = TC_NACC * TC_BN * 4;
-    static constexpr int PUB_BYTES = TC_EPI_GROUPS * TC_BM * 8;  // per (group, query row): {key, unit tag}
+    static constexpr int PUB_BYTES = SMEM_LIST ? 0 : TC_EPI_GROUPS * TC_BM * 8;  // per (group, query row): {key, unit tag}
+    static constexpr int LIST_BYTES = SMEM_LIST ? 2 * TC_BM * TC_LROW : 0;          // keys [128] rows, then ids [128] rows
+    static constexpr int STAGE_BYTES = SMEM_LIST ? 4 * TC_QN * TC_QENTRY : 0;       // candidate queues, one per quadrant
+    static constexpr int AUX_BYTES = SMEM_LIST ? TC_BM * 8 + 4 * TC_QN * 4 + 64 : 0;  // worst kept key + its slot per row, ready words, tail/head
     static constexpr int BAR_BYTES = 1024;
-    static constexpr int TOTAL = A_BYTES + B_BYTES + NORM_BYTES + PUB_BYTES + BAR_BYTES + 1024;  // + slack for 1024-B alignment
+    static constexpr int TOTAL = A_BYTES + B_BYTES + NORM_BYTES + PUB_BYTES + LIST_BYTES + STAGE_BYTES + AUX_BYTES +
+                                 BAR_BYTES + 1024;  // + slack for 1024-B alignment
 };
 
 struct TcParams {
@@ -70,6 +87,8 @@ struct TcParams {
     int n_splits;
     int tiles_per_split;
     const float* key_scale_ptr;  // TC_F16: key = bn + (*key_scale_ptr) * acc, -2 / (s_q * s_b), derived on the device
+    unsigned long long* stats;  // debug counters (VSB_TC_STATS) or nullptr: [0] warp slow-path entries, [1] lane entries,
+                         // [2] qualifying elements, [3] insertions
     int dbg;             // timing experiments only (VSB_TC_DBG): 1 no epilogue work, 2 no inserts, 4 no MMA, 8 no B loads,
                          // 16 epilogue = TMEM loads only, 32 epilogue = math only (no TMEM loads)
 };
@@ -87,6 +106,36 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
     float4 v;
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
     return v;
+}
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+    return v;
+}
+// volatile accesses with an explicit shared-space address: a generic `volatile` access compiles to LD/ST.E.STRONG.SYS,
+// which costs hundreds of cycles
+__device__ __forceinline__ uint32_t ldsv_u32(const void* p) {
+    uint32_t v;
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ float ldsv_f32(const void* p) { return __uint_as_float(ldsv_u32(p)); }
+__device__ __forceinline__ void stsv_u32(void* p, uint32_t x) {
+    asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(x) : "memory");
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t x) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(x) : "memory"); }
+__device__ __forceinline__ uint2 lds64(uint32_t addr) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts64(uint32_t addr, uint32_t x, uint32_t y) {
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(x), "r"(y) : "memory");
 }
 __device__ __forceinline__ uint2 lds64_volatile(uint32_t addr) {
     uint2 v;
@@ -106,7 +155,7 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint
 }
 
 template <int KTOP, int MODE, bool HAS_LB>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TcSmem<MODE>::THREADS, 1)
 exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                 const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                 const TcParams p) {
@@ -121,7 +170,14 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
     uint8_t* sB = smem + S::A_BYTES;
     float* sN = (float*)(sB + S::B_BYTES);      // [TC_NACC][128] base norms of the tile in accumulator slot i
     uint2* sPub = (uint2*)((uint8_t*)sN + S::NORM_BYTES);  // [TC_EPI_GROUPS][TC_BM]
-    uint64_t* bars = (uint64_t*)((uint8_t*)sPub + S::PUB_BYTES);
+    uint8_t* sList = (uint8_t*)sPub + S::PUB_BYTES;               // [TC_BM] rows of TC_LROW bytes   (SMEM_LIST)
+    uint8_t* sQueue = sList + S::LIST_BYTES;                      // [4][TC_QN] entries of TC_QENTRY bytes
+    float* sWorst = (float*)(sQueue + S::STAGE_BYTES);            // [TC_BM] 32nd best key of the row's list (+inf until full)
+    int* sWpos = (int*)(sWorst + (S::SMEM_LIST ? TC_BM : 0));     // [TC_BM] slot holding that key
+    int* sReady = sWpos + (S::SMEM_LIST ? TC_BM : 0);             // [4][TC_QN] sequence number + 1 of the entry in the slot
+    int* sTail = sReady + (S::SMEM_LIST ? 4 * TC_QN : 0);         // [4] entries reserved so far (monotonic)
+    int* sHead = sTail + 4;                                       // [4] entries consumed so far
+    uint64_t* bars = (uint64_t*)(sList + S::LIST_BYTES + S::STAGE_BYTES + S::AUX_BYTES);
     uint64_t* full = bars;                    // [NSTAGE]  TMA -> MMA
     uint64_t* empty = full + NSTAGE;          // [NSTAGE]  MMA -> TMA
     uint64_t* acc_full = empty + NSTAGE;      // [TC_NACC] MMA -> epilogue
@@ -129,7 +185,9 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
     uint64_t* n_full = acc_empty + TC_NACC;   // [TC_NACC] norms landed
     uint64_t* a_full = n_full + TC_NACC;      // query tile landed
     uint64_t* a_empty = a_full + 1;           // query tile no longer read by the tensor core
-    uint32_t* tmem_slot = (uint32_t*)(a_empty + 1);
+    uint64_t* u_done = a_empty + 1;           // (SMEM_LIST) the epilogue warps have queued every candidate of the unit
+    uint64_t* u_flushed = u_done + 1;         // (SMEM_LIST) the keepers have written out and reset the lists
+    uint32_t* tmem_slot = (uint32_t*)(u_flushed + 1);
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     const int lane = threadIdx.x & 31;
@@ -146,6 +204,13 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         }
         mbar_init(a_full, 1);
         mbar_init(a_empty, 1);
+        mbar_init(u_done, 4 * TC_EPI_GROUPS);
+        mbar_init(u_flushed, 4);
+        if (S::SMEM_LIST) {
+            for (int i = 0; i < TC_BM; ++i) sWorst[i] = __int_as_float(0x7f800000);
+            for (int i = 0; i < 4 * TC_QN; ++i) sReady[i] = 0;
+            for (int i = 0; i < 8; ++i) sTail[i] = 0;  // tails and heads
+        }
         fence_barrier_init();
     }
     if (warp == 1) {
@@ -160,7 +225,10 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
     const int n_units = p.n_mtiles * p.n_splits;
 
     if (warp < 4) {
-      asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TC_REGS_CTRL));
+      if constexpr (S::SMEM_LIST)
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TC_REGS_SMALL_Q));
+      else
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TC_REGS_CTRL));
       if (warp == 0) {
         // ===================================== TMA producer =====================================
         // the whole warp walks the loop (warp-uniform addresses stay in uniform registers); one elected lane
@@ -296,6 +364,278 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         }
       }
     } else {
+      if constexpr (S::SMEM_LIST) {
+       if (warp >= 4 + 4 * TC_EPI_GROUPS) {
+        // ===================================== list keepers (TC_F16) ==============================
+        // Keeper warp `quad` owns the 32 candidate lists of TMEM lane quadrant `quad` (no locks).  It drains the
+        // quadrant's queue in BATCHES: an entry = one query row + the 32 keys of one 32-column chunk, and every lane
+        // takes one entry.  The epilogue's qualifying rows are sparse (1-4 lanes of a warp per chunk); the queue
+        // compacts them, so the list maintenance runs with (nearly) all lanes busy instead of one.
+        // A list is an UNSORTED set of 32 (key, id) slots plus its current maximum and the slot holding it: an
+        // insertion overwrites that slot and rescans the 32 keys for the new maximum (eight independent 16-byte
+        // loads: no dependent search / shift chain).  Lists are sorted once, when the unit is written out.
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TC_REGS_SMALL_Q));
+        const int quad = warp & 3;
+        const float INF = __int_as_float(0x7f800000);
+        const uint32_t keys_u = smem_u32(sList) + (uint32_t)(quad * 32) * TC_LROW;                 // this quadrant's 32 rows
+        const uint32_t ids_u = keys_u + (uint32_t)TC_BM * TC_LROW;
+        const int* ready = sReady + quad * TC_QN;
+        const uint32_t queue_u = smem_u32(sQueue + quad * TC_QN * TC_QENTRY);
+        int next = 0;  // entries consumed so far (monotonic over the whole kernel)
+        int it = 0;
+        for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++it) {
+            const int m_tile = unit % p.n_mtiles;
+            const int split = unit / p.n_mtiles;
+            for (int rr = 0; rr < 32; ++rr) {
+                sts32(keys_u + (uint32_t)rr * TC_LROW + (uint32_t)lane * 4u, __float_as_uint(INF));
+                sts32(ids_u + (uint32_t)rr * TC_LROW + (uint32_t)lane * 4u, 0xffffffffu);
+            }
+            sWorst[quad * 32 + lane] = INF;
+            sWpos[quad * 32 + lane] = 0;
+            __syncwarp();
+            if (it > 0 && lane == 0) mbar_arrive(u_flushed);  // lists of the previous unit written out and reset
+            int final_tail = -1;
+            while (true) {
+                const int my = next + lane;
+                const unsigned rm = __ballot_sync(0xffffffffu, (int)ldsv_u32(ready + (my & (TC_QN - 1))) == my + 1);
+                const int n = rm == 0xffffffffu ? 32 : __ffs(~rm) - 1;  // consecutive ready entries
+                if (n == 0) {
+                    if (final_tail < 0) {
+                        if (mbar_try_wait(u_done, (uint32_t)(it & 1))) final_tail = (int)ldsv_u32(sTail + quad);
+                        else __nanosleep(64);
+                    } else if (next == final_tail) {
+                        break;
+                    }
+                    continue;
+                }
+                asm volatile("fence.acq_rel.cta;" ::: "memory");
+                const long long kc0 = p.stats ? clock64() : 0;
+                const bool act = lane < n;
+                const uint32_t e = queue_u + (uint32_t)(my & (TC_QN - 1)) * TC_QENTRY;
+                int rr = 64 + lane, col0 = 0, pad_;
+                float thr_e = -INF;
+                if (act) asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(rr), "=r"(col0), "=f"(thr_e), "=r"(pad_) : "r"(e + 128u) : "memory");
+                const int srow = quad * 32 + (rr & 31);
+                const uint32_t krow = keys_u + (uint32_t)(rr & 31) * TC_LROW;
+                const uint32_t irow = ids_u + (uint32_t)(rr & 31) * TC_LROW;
+                // ---- phase 1: which of the entry's 32 keys still qualify (lane-rotated order: conflict-free banks)
+                unsigned qm = 0;
+                if (!(p.dbg & 64)) {
+                    const float bound = act ? fminf(thr_e, ldsv_f32(sWorst + srow)) : -INF;
+#pragma unroll 8
+                    for (int j = 0; j < 32; ++j) {
+                        const int jr = (j + lane) & 31;
+                        qm |= (lds_f32(e + (uint32_t)jr * 4u) < bound) ? (1u << jr) : 0u;
+                    }
+                }
+                // ---- phase 2: rounds; per round every lane inserts one key, one lane per distinct row
+                const long long kc1 = p.stats ? clock64() : 0;
+                int nrounds = 0;
+                const unsigned peers = __match_any_sync(0xffffffffu, rr);
+                const long long kc2 = p.stats ? clock64() : 0;
+                unsigned alive;
+                while ((alive = __ballot_sync(0xffffffffu, qm != 0)) != 0) {
+                    ++nrounds;
+                    if (qm != 0 && lane == __ffs(peers & alive) - 1) {
+                        const int jr = __ffs(qm) - 1;
+                        qm &= qm - 1;
+                        const float x = lds_f32(e + (uint32_t)jr * 4u);
+                        if (x < fminf(thr_e, ldsv_f32(sWorst + srow))) {
+                            const int pw = (int)ldsv_u32(sWpos + srow);
+                            sts32(krow + (uint32_t)pw * 4u, __float_as_uint(x));
+                            sts32(irow + (uint32_t)pw * 4u, (uint32_t)(col0 + jr));
+                            // new maximum and its slot, 16 keys at a time
+                            float mx = -INF;
+                            int pm = 0;
+#pragma unroll
+                            for (int h = 0; h < 2; ++h) {
+                                float v[16];
+#pragma unroll
+                                for (int g = 0; g < 4; ++g) {
+                                    const float4 f = lds128(krow + (uint32_t)(h * 64 + g * 16));
+                                    v[4 * g + 0] = f.x; v[4 * g + 1] = f.y; v[4 * g + 2] = f.z; v[4 * g + 3] = f.w;
+                                }
+                                float t[8];
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) t[i] = fmaxf(v[i], v[i + 8]);
+#pragma unroll
+                                for (int w = 4; w >= 1; w >>= 1)
+#pragma unroll
+                                    for (int i = 0; i < w; ++i) t[i] = fmaxf(t[i], t[i + w]);
+                                if (t[0] > mx || h == 0) {
+                                    mx = t[0];
+#pragma unroll
+                                    for (int i = 15; i >= 0; --i) pm = (v[i] == mx) ? h * 16 + i : pm;
+                                }
+                            }
+                            stsv_u32(sWorst + srow, __float_as_uint(mx));
+                            stsv_u32(sWpos + srow, (uint32_t)pm);
+                            if (p.stats) atomicAdd(p.stats + 3, 1ull);
+                        }
+                    }
+                    __syncwarp();
+                }
+                next += n;
+                if (lane == 0) stsv_u32(sHead + quad, (uint32_t)next);  // the slots may be reused
+                if (p.stats && lane == 0) {
+                    atomicAdd(p.stats + 4, (unsigned long long)n);
+                    atomicAdd(p.stats + 5, 1ull);
+                    atomicAdd(p.stats + 6, (unsigned long long)(clock64() - kc0));
+                    atomicAdd(p.stats + 8, (unsigned long long)(kc1 - kc0));
+                    atomicAdd(p.stats + 9, (unsigned long long)nrounds);
+                    atomicAdd(p.stats + 10, (unsigned long long)(kc2 - kc1));
+                }
+            }
+            // ---- unit done: publish the bound, sort each list (rank by counting) and write it out (128-byte rows)
+            __syncwarp();
+            {
+                const int q0 = m_tile * TC_BM + quad * 32;
+                const int qv = q0 + lane;
+                if (qv < p.nq) {
+                    const float w = sWorst[quad * 32 + lane];
+                    if (w < INF) atomicMin(p.gthr + qv, float_to_ordered(w));
+                }
+                float* pk = p.part_key + ((size_t)split * p.nq + q0) * 32;
+                int32_t* pi = p.part_id + ((size_t)split * p.nq + q0) * 32;
+                const int rows_valid = max(0, min(32, p.nq - q0));
+                for (int rr = 0; rr < rows_valid; ++rr) {
+                    const float kk = lds_f32(keys_u + (uint32_t)rr * TC_LROW + (uint32_t)lane * 4u);
+                    const int32_t ii = (int32_t)lds_u32(ids_u + (uint32_t)rr * TC_LROW + (uint32_t)lane * 4u);
+                    int rank = 0;
+#pragma unroll 8
+                    for (int i = 0; i < 32; ++i) {
+                        const float ok = __shfl_sync(0xffffffffu, kk, i);
+                        const int32_t oi = __shfl_sync(0xffffffffu, ii, i);
+                        rank += (pair_less(ok, oi, kk, ii) || (ok == kk && oi == ii && i < lane)) ? 1 : 0;
+                    }
+                    pk[rr * 32 + rank] = kk;
+                    pi[rr * 32 + rank] = ii;
+                }
+            }
+            __syncwarp();
+        }
+       } else {
+        // ===================================== epilogue, queued candidates (TC_F16) ===============
+        // Fast path per 32-column chunk: keys, min tree, one test of the row minimum against the row's threshold.
+        // A row that qualifies is handed to the quadrant's list keeper as a whole: the thread copies its 32 keys into
+        // a queue entry (eight 16-byte stores; all qualifying lanes of the warp execute them together), so the
+        // epilogue warps never run an insertion themselves.
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(TC_REGS_EPI_Q));
+        static_assert(KTOP == 32, "shared-memory lists hold exactly one entry per lane");
+        const int quad = warp & 3;
+        const int grp = (warp - 4) >> 2;
+        const int row = quad * 32 + lane;
+        const float INF = __int_as_float(0x7f800000);
+        const float key_scale = __ldg(p.key_scale_ptr);
+        constexpr int CH = TC_BN / 32;
+        const uint32_t queue_u = smem_u32(sQueue + quad * TC_QN * TC_QENTRY);
+        int tcount = 0;
+        int it = 0;
+        for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++it) {
+            const int m_tile = unit % p.n_mtiles;
+            const int split = unit / p.n_mtiles;
+            const int t0 = split * p.tiles_per_split;
+            const int t1 = min(t0 + p.tiles_per_split, p.n_tiles);
+            const int q = m_tile * TC_BM + row;
+            const bool valid = q < p.nq;
+            const bool quad_live = m_tile * TC_BM + quad * 32 < p.nq;
+            if (it > 0) mbar_wait(u_flushed, (uint32_t)((it - 1) & 1));  // lists and bounds belong to this unit now
+            float cap = INF;                     // bound of the query's 32nd best key learnt from other CTAs
+            float posted = INF;                  // last value this thread pushed to the global array
+            int32_t pending = valid ? __ldcg(p.gthr + q) : 0x7f7f7f7f;
+            int first = (grp - tcount % TC_EPI_GROUPS + TC_EPI_GROUPS) % TC_EPI_GROUPS;
+            int j = 0;
+            for (int i = first; i < t1 - t0; i += TC_EPI_GROUPS, ++j) {
+                const int t = t0 + i;
+                const int tc = tcount + i;
+                const int acc = tc & (TC_NACC - 1);
+                const uint32_t acc_phase = (uint32_t)(tc / TC_NACC) & 1u;
+                const int rel = j & (TC_THR_REFRESH - 1);
+                if (valid) {
+                    if (rel == TC_THR_REFRESH - 1) {
+                        const float w = ldsv_f32(sWorst + row);
+                        if (w < posted) {
+                            atomicMin(p.gthr + q, float_to_ordered(w));
+                            posted = w;
+                        }
+                    }
+                    if (rel == 0) {
+                        cap = fminf(cap, ordered_to_float(pending));
+                        pending = __ldcg(p.gthr + q);
+                    }
+                }
+                const float capn = valid ? next_up(cap) : -INF;  // rows beyond the last query never qualify
+                mbar_wait(&n_full[acc], acc_phase);
+                mbar_wait(&acc_full[acc], acc_phase);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * TC_BN);
+                const uint32_t bn_s = smem_u32(sN + acc * TC_BN);
+                uint32_t r[2][32];
+                const bool skip = (p.dbg & 1) || !quad_live;
+                if (!skip) tmem_ld32(taddr, r[0]);
+#pragma unroll
+                for (int c = 0; c < CH; ++c) {
+                    if (skip) break;
+                    const float thr = fminf(ldsv_f32(sWorst + row), capn);  // kept fresh by the keeper
+                    tc_wait_ld();
+                    if (c + 1 < CH) tmem_ld32(taddr + (c + 1) * 32, r[(c + 1) & 1]);
+                    float d[32];
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; ++j4) {
+                        const float4 bn = lds128(bn_s + (uint32_t)(c * 32 + 4 * j4) * 4u);  // smem broadcast
+                        const uint32_t* rr = r[c & 1] + 4 * j4;
+                        d[4 * j4 + 0] = fmaf(key_scale, __uint_as_float(rr[0]), bn.x);
+                        d[4 * j4 + 1] = fmaf(key_scale, __uint_as_float(rr[1]), bn.y);
+                        d[4 * j4 + 2] = fmaf(key_scale, __uint_as_float(rr[2]), bn.z);
+                        d[4 * j4 + 3] = fmaf(key_scale, __uint_as_float(rr[3]), bn.w);
+                    }
+                    float m[16];  // min tree (the compiler folds it into 3-input FMNMX3)
+#pragma unroll
+                    for (int jj = 0; jj < 16; ++jj) m[jj] = fminf(d[jj], d[jj + 16]);
+#pragma unroll
+                    for (int w = 8; w >= 1; w >>= 1)
+#pragma unroll
+                        for (int jj = 0; jj < w; ++jj) m[jj] = fminf(m[jj], m[jj + w]);
+                    const bool hit = m[0] < thr;
+                    const unsigned todo = __ballot_sync(0xffffffffu, hit);
+                    if (todo != 0 && !(p.dbg & 2)) {
+                        const long long pc0 = p.stats ? clock64() : 0;
+                        int base = 0;
+                        if (lane == 0) {
+                            base = atomicAdd(sTail + quad, __popc(todo));
+                            if (p.stats) {
+                                atomicAdd(p.stats + 0, 1ull);
+                                atomicAdd(p.stats + 1, (unsigned long long)__popc(todo));
+                            }
+                        }
+                        base = __shfl_sync(0xffffffffu, base, 0);
+                        if (hit) {
+                            const int idx = base + __popc(todo & ((1u << lane) - 1u));
+                            while (idx - (int)ldsv_u32(sHead + quad) >= TC_QN) __nanosleep(200);  // queue full: leave the issue slots to the keeper
+                            const uint32_t e = queue_u + (uint32_t)(idx & (TC_QN - 1)) * TC_QENTRY;
+#pragma unroll
+                            for (int j4 = 0; j4 < 8; ++j4)
+                                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(e + (uint32_t)(j4 << 4)),
+                                             "f"(d[4 * j4 + 0]), "f"(d[4 * j4 + 1]), "f"(d[4 * j4 + 2]), "f"(d[4 * j4 + 3]) : "memory");
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(e + 128u), "r"(lane), "r"(t * TC_BN + c * 32),
+                                         "f"(thr), "r"(0) : "memory");
+                            asm volatile("fence.acq_rel.cta;" ::: "memory");
+                            stsv_u32(sReady + quad * TC_QN + (idx & (TC_QN - 1)), (uint32_t)(idx + 1));
+                        }
+                        __syncwarp();
+                        if (p.stats && lane == 0) atomicAdd(p.stats + 7, (unsigned long long)(clock64() - pc0));
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[acc]);
+            }
+            tcount += t1 - t0;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(u_done);  // every candidate of this warp is in the queue (release)
+        }
+       }
+      } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(TC_REGS_EPI));
         // ===================================== epilogue ==========================================
         // Tiles rotate over the TC_EPI_GROUPS warpgroups (the CTA's running tile count modulo the group count), so
@@ -418,11 +758,17 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
                         uint32_t mask = 0;
 #pragma unroll
                         for (int jj = 0; jj < 32; ++jj) mask |= (d[jj] < thr) ? (1u << jj) : 0u;
+                        if (p.stats) {
+                            if ((__activemask() & ((1u << lane) - 1)) == 0) atomicAdd(p.stats + 0, 1ull);
+                            atomicAdd(p.stats + 1, 1ull);
+                            atomicAdd(p.stats + 2, (unsigned long long)__popc(mask));
+                        }
                         while (mask) {
                             const int jj = __ffs(mask) - 1;
                             mask &= mask - 1;
                             const float v = select32(d, jj);
                             if (v < thr) {
+                                if (p.stats) atomicAdd(p.stats + 3, 1ull);
                                 top.insert(v, col0 + jj);
                                 thr = fminf(thr, top.threshold());
                             }
@@ -448,6 +794,7 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
                 }
             }
         }
+      }
     }
     tc_fence_before();
     __syncthreads();

@@ -410,6 +410,61 @@ int launch_merge_lists(const float* part_key, const int32_t* part_id, int n_list
     return VS_OK;
 }
 
+// Merge of G <= 32 per-shard result lists of any length k (the exchange step of the row-sharded search when k > 32):
+// in[g][q][0..k) sorted in canonical order ((key asc | desc), id asc), -1 ids = padding at the tail.  One warp per
+// query, lane g walks list g; every round the warp picks the best head with a shuffle arg-min and that lane advances.
+__global__ void __launch_bounds__(128) merge_shards_kernel(const float* __restrict__ in_key, const int32_t* __restrict__ in_id,
+                                                           int n_shards, int64_t nq, int k, int neg,
+                                                           float* __restrict__ out_key, int32_t* __restrict__ out_id) {
+    const int lane = threadIdx.x & 31;
+    const int64_t q = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (q >= nq) return;
+    const float INF = __int_as_float(0x7f800000);
+    const float* pk = in_key + ((size_t)min(lane, n_shards - 1) * nq + q) * k;
+    const int32_t* pi = in_id + ((size_t)min(lane, n_shards - 1) * nq + q) * k;
+    int pos = lane < n_shards ? 0 : k;
+    float hk = INF;
+    int32_t hid = -1;
+    if (pos < k) {
+        hid = pi[0];
+        hk = hid >= 0 ? (neg ? -pk[0] : pk[0]) : INF;
+    }
+    for (int r = 0; r < k; ++r) {
+        float bk = hk;
+        int32_t bi = hid;
+        int src = lane;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ok = __shfl_xor_sync(0xffffffffu, bk, o);
+            const int32_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            const int os = __shfl_xor_sync(0xffffffffu, src, o);
+            if (pair_less(ok, oi, bk, bi)) {
+                bk = ok;
+                bi = oi;
+                src = os;
+            }
+        }
+        if (lane == 0) {
+            out_key[q * k + r] = bi >= 0 ? (neg ? -bk : bk) : (neg ? -INF : INF);
+            out_id[q * k + r] = bi;
+        }
+        if (src == lane && bi >= 0) {
+            ++pos;
+            hid = pos < k ? pi[pos] : -1;
+            hk = hid >= 0 ? (neg ? -pk[pos] : pk[pos]) : INF;
+        }
+    }
+}
+
+int launch_merge_shards(const float* in_key, const int32_t* in_id, int n_shards, int64_t nq, int k, int neg, float* out_key,
+                        int32_t* out_id, cudaStream_t st) {
+    if (nq <= 0) return VS_OK;
+    if (n_shards > 32) return fail(VS_ERR_UNSUPPORTED, "merge: more than 32 shards");
+    merge_shards_kernel<<<(unsigned)ceil_div64(nq, 4), 128, 0, st>>>(in_key, in_id, n_shards, nq, k, neg, out_key, out_id);
+    VSB_CUDA(cudaGetLastError());
+    return VS_OK;
+}
+
 // Final (key, id) sort of each row of out[nq][k] for multi-pass results (k > 32): passes are ordered by the
 // candidate ranking, refined keys may reorder neighbours across a pass boundary.  One warp per row.
 __global__ void __launch_bounds__(128) sort_rows_kernel(float* __restrict__ key, int32_t* __restrict__ id, int64_t nq, int k) {

@@ -49,7 +49,7 @@ int launch_exact_tc(const CUtensorMap& tmA_hi, const CUtensorMap& tmA_lo, const 
                     const CUtensorMap& tmB_lo, const float* bnorm, int32_t* gthr, int nq, const TcPlan& plan,
                     int ktop, int mode, const float* key_scale_dev, const float* lb_key, const int32_t* lb_id, float* part_key,
                     int32_t* part_id, cudaStream_t st);
-int tc_lists_per_split();  // partial lists written per (split, query)
+int tc_lists_per_split(int mode);  // partial lists written per (split, query): 1 (TC_F16, mode 2) or 3
 int tc_set_attributes();  // opt-in to > 48 KB dynamic shared memory for every instantiation
 
 // kernels.cu (K3) ----------------------------------------------------------------------------
@@ -66,6 +66,9 @@ int launch_merge_lists(const float* part_key, const int32_t* part_id, int n_list
                        const float* rf_q, const float* rf_qnorm, cudaStream_t st, const TcQueryParams* cert_qp = nullptr,
                        int32_t* uncert_count = nullptr, int32_t* uncert_list = nullptr);
 int launch_sort_rows(float* key, int32_t* id, int64_t nq, int k, cudaStream_t st);
+// G <= 32 sorted per-shard lists [G][nq][k] of any k -> the k best per query, canonical order (neg: largest key first)
+int launch_merge_shards(const float* in_key, const int32_t* in_id, int n_shards, int64_t nq, int k, int neg, float* out_key,
+                        int32_t* out_id, cudaStream_t st);
 
 // synth.cu --------------------------------------------------------------------------------------
 int launch_synth(float* out, int64_t row0, int64_t nrows, int dim, int law, uint64_t seed, uint64_t centre_seed,

@@ -201,3 +201,38 @@ def test_certified_path_falls_back_when_it_cannot_certify(gpu_vsb, oracle):
         assert np.array_equal(ids2, ids[40:]) and np.array_equal(d2, d[40:])
     finally:
         idx.close()
+
+
+@pytest.mark.parametrize("g,k,smallest", [(2, 33, True), (5, 100, True), (8, 100, True), (8, 257, False), (3, 64, False)])
+def test_merge_topk_dev_any_k(gpu_vsb, g, k, smallest):
+    """vs_merge_topk_dev for k > 32 (the exchange step of config 5: top-100 over 8 shards): per-shard lists in
+    canonical order, tie groups across shards, -1 padding at the tail of short lists."""
+    import torch
+
+    vsb = gpu_vsb
+    rng = np.random.default_rng(g * 1000 + k)
+    nq = 77
+    keys = rng.integers(0, 40, size=(g, nq, k)).astype(np.float32)  # few distinct values: many ties
+    ids = np.stack([rng.permutation(g * k)[:g * k].reshape(g, k) for _ in range(nq)], axis=1).astype(np.int32)
+    sgn = 1.0 if smallest else -1.0
+    for s in range(g):       # each shard's list in canonical order
+        for q in range(nq):
+            o = np.lexsort((ids[s, q], sgn * keys[s, q]))
+            keys[s, q], ids[s, q] = keys[s, q][o], ids[s, q][o]
+    ids[0, :5, k // 2:] = -1   # short lists: padding
+    ids[1, 3, :] = -1
+    flat_k = np.where(ids >= 0, sgn * keys, np.inf).transpose(1, 0, 2).reshape(nq, g * k)
+    flat_i = ids.transpose(1, 0, 2).reshape(nq, g * k)
+    order = np.lexsort((flat_i.astype(np.uint32), flat_k), axis=1)[:, :k]
+    want_i = np.take_along_axis(flat_i, order, 1)
+    want_k = sgn * np.take_along_axis(flat_k, order, 1)
+    dev = torch.device("cuda:0")
+    gi, gk = torch.from_numpy(ids).to(dev), torch.from_numpy(keys).to(dev)
+    oi = torch.empty((nq, k), dtype=torch.int32, device=dev)
+    ok = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    vsb.merge_topk_dev(gi.data_ptr(), gk.data_ptr(), g, nq, k, smallest, oi.data_ptr(), ok.data_ptr(),
+                       torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(oi.cpu().numpy(), want_i)
+    valid = want_i >= 0
+    assert np.array_equal(ok.cpu().numpy()[valid], want_k[valid])
