@@ -35,13 +35,14 @@ constexpr int TC_EPI_GROUPS = 3;  // epilogue warpgroups; tiles rotate over them
 constexpr int TC_THREADS = 128 + 128 * TC_EPI_GROUPS;  // warpgroup 0: TMA producer, MMA issuer, two idle warps
 constexpr int TC_REGS_CTRL = 80, TC_REGS_EPI = 144;   // setmaxnreg budgets: 128*80 + 384*144 == 64K registers
 // TC_F16 adds a fifth warpgroup of four list-keeper warps (one per TMEM lane quadrant): 640 threads start with 96
-// registers (61440); control and keeper warpgroups drop to 48, the three epilogue warpgroups rise to 128 (2*128*48 + 384*128 == 61440:
-// setmaxnreg.inc can only take what the CTA itself released)
+// registers (61440); control drops to 24, the keepers rise to 104 (a 32-entry register list per lane), the three
+// epilogue warpgroups to 112 (128*24 + 128*104 + 384*112 = 59392 <= 61440: setmaxnreg.inc can only take what the CTA
+// itself released)
 constexpr int TC_THREADS_Q = TC_THREADS + 128;
-constexpr int TC_REGS_SMALL_Q = 48, TC_REGS_EPI_Q = 128;
-constexpr int TC_QN = 64;             // candidate-queue entries per quadrant
+constexpr int TC_REGS_CTRL_Q = 24, TC_REGS_KEEP_Q = 104, TC_REGS_EPI_Q = 112;
+constexpr int TC_QN = 128;            // candidate-queue entries per quadrant
+constexpr int TC_QBATCH = 24;         // queued rows that make a batch worth folding
 constexpr int TC_QENTRY = 144;        // bytes per entry: 32 keys + {row in quadrant, first column, threshold, -}
-constexpr int TC_LROW = 36 * 4;       // bytes per shared-memory list row: 32 keys (or ids) + 16 bytes of padding (banks)
 constexpr int TC_THR_REFRESH = 4; // tiles of one group between reads of the shared threshold (power of two)
 
 // Operand arithmetic of the tensor-core pass
@@ -57,21 +58,20 @@ struct TcSmem {
     static constexpr bool SPLIT3 = MODE == TC_TF32X3;
     static constexpr int NKB = MODE == TC_F16 ? 2 : 4;  // 128-byte k-blocks per row (128 fp16 = 256 B, 128 fp32 = 512 B)
     static constexpr int A_BYTES = (SPLIT3 ? 2 : 1) * NKB * TC_KB_BYTES;
-    // TC_F16 keeps ONE candidate list per query row in shared memory, maintained by dedicated list-keeper warps that
-    // are fed through per-quadrant queues; the other modes keep per-thread register lists (their query tile leaves
-    // no room: 64 / 128 KB)
+    // TC_F16 keeps ONE candidate list per query row in the registers of dedicated list-keeper warps that are fed
+    // through per-quadrant shared-memory queues; the other modes keep three per-thread register lists per row in the
+    // epilogue warps themselves (their query tile leaves no room for the queues: 64 / 128 KB)
     static constexpr bool SMEM_LIST = MODE == TC_F16;
     static constexpr int THREADS = SMEM_LIST ? TC_THREADS_Q : TC_THREADS;
     static constexpr int NSTAGE = MODE == TC_F16 ? 7 : (SPLIT3 ? 5 : 8);
     static constexpr int B_BYTES = NSTAGE * TC_KB_BYTES;
     static constexpr int NORM_BYTES = TC_NACC * TC_BN * 4;
     static constexpr int PUB_BYTES = SMEM_LIST ? 0 : TC_EPI_GROUPS * TC_BM * 8;  // per (group, query row): {key, unit tag}
-    static constexpr int LIST_BYTES = SMEM_LIST ? 2 * TC_BM * TC_LROW : 0;          // keys [128] rows, then ids [128] rows
     static constexpr int STAGE_BYTES = SMEM_LIST ? 4 * TC_QN * TC_QENTRY : 0;       // candidate queues, one per quadrant
-    static constexpr int AUX_BYTES = SMEM_LIST ? TC_BM * 8 + 4 * TC_QN * 4 + 64 : 0;  // worst kept key + its slot per row, ready words, tail/head
+    static constexpr int AUX_BYTES = SMEM_LIST ? TC_BM * 8 + 4 * TC_QN * 4 + 64 : 0;  // worst kept key per row, entry mask per row, ready words, tail/head
     static constexpr int BAR_BYTES = 1024;
-    static constexpr int TOTAL = A_BYTES + B_BYTES + NORM_BYTES + PUB_BYTES + LIST_BYTES + STAGE_BYTES + AUX_BYTES +
-                                 BAR_BYTES + 1024;  // + slack for 1024-B alignment
+    static constexpr int TOTAL = A_BYTES + B_BYTES + NORM_BYTES + PUB_BYTES + STAGE_BYTES + AUX_BYTES + BAR_BYTES +
+                                 1024;  // + slack for 1024-B alignment
 };
 
 struct TcParams {
@@ -89,6 +89,7 @@ struct TcParams {
     const float* key_scale_ptr;  // TC_F16: key = bn + (*key_scale_ptr) * acc, -2 / (s_q * s_b), derived on the device
     unsigned long long* stats;  // debug counters (VSB_TC_STATS) or nullptr: [0] warp slow-path entries, [1] lane entries,
                          // [2] qualifying elements, [3] insertions
+    int qbatch;          // TC_F16: queued rows that make a batch worth folding (0 = default)
     int dbg;             // timing experiments only (VSB_TC_DBG): 1 no epilogue work, 2 no inserts, 4 no MMA, 8 no B loads,
                          // 16 epilogue = TMEM loads only, 32 epilogue = math only (no TMEM loads)
 };
@@ -170,14 +171,13 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
     uint8_t* sB = smem + S::A_BYTES;
     float* sN = (float*)(sB + S::B_BYTES);      // [TC_NACC][128] base norms of the tile in accumulator slot i
     uint2* sPub = (uint2*)((uint8_t*)sN + S::NORM_BYTES);  // [TC_EPI_GROUPS][TC_BM]
-    uint8_t* sList = (uint8_t*)sPub + S::PUB_BYTES;               // [TC_BM] rows of TC_LROW bytes   (SMEM_LIST)
-    uint8_t* sQueue = sList + S::LIST_BYTES;                      // [4][TC_QN] entries of TC_QENTRY bytes
+    uint8_t* sQueue = (uint8_t*)sPub + S::PUB_BYTES;              // [4][TC_QN] entries of TC_QENTRY bytes   (SMEM_LIST)
     float* sWorst = (float*)(sQueue + S::STAGE_BYTES);            // [TC_BM] 32nd best key of the row's list (+inf until full)
-    int* sWpos = (int*)(sWorst + (S::SMEM_LIST ? TC_BM : 0));     // [TC_BM] slot holding that key
+    int* sWpos = (int*)(sWorst + (S::SMEM_LIST ? TC_BM : 0));     // [TC_BM] scratch of a batch: the entries that belong to the row
     int* sReady = sWpos + (S::SMEM_LIST ? TC_BM : 0);             // [4][TC_QN] sequence number + 1 of the entry in the slot
     int* sTail = sReady + (S::SMEM_LIST ? 4 * TC_QN : 0);         // [4] entries reserved so far (monotonic)
     int* sHead = sTail + 4;                                       // [4] entries consumed so far
-    uint64_t* bars = (uint64_t*)(sList + S::LIST_BYTES + S::STAGE_BYTES + S::AUX_BYTES);
+    uint64_t* bars = (uint64_t*)(sQueue + S::STAGE_BYTES + S::AUX_BYTES);
     uint64_t* full = bars;                    // [NSTAGE]  TMA -> MMA
     uint64_t* empty = full + NSTAGE;          // [NSTAGE]  MMA -> TMA
     uint64_t* acc_full = empty + NSTAGE;      // [TC_NACC] MMA -> epilogue
@@ -207,7 +207,10 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         mbar_init(u_done, 4 * TC_EPI_GROUPS);
         mbar_init(u_flushed, 4);
         if (S::SMEM_LIST) {
-            for (int i = 0; i < TC_BM; ++i) sWorst[i] = __int_as_float(0x7f800000);
+            for (int i = 0; i < TC_BM; ++i) {
+                sWorst[i] = __int_as_float(0x7f800000);
+                sWpos[i] = 0;
+            }
             for (int i = 0; i < 4 * TC_QN; ++i) sReady[i] = 0;
             for (int i = 0; i < 8; ++i) sTail[i] = 0;  // tails and heads
         }
@@ -226,7 +229,7 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
 
     if (warp < 4) {
       if constexpr (S::SMEM_LIST)
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TC_REGS_SMALL_Q));
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TC_REGS_CTRL_Q));
       else
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TC_REGS_CTRL));
       if (warp == 0) {
@@ -367,31 +370,33 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
       if constexpr (S::SMEM_LIST) {
        if (warp >= 4 + 4 * TC_EPI_GROUPS) {
         // ===================================== list keepers (TC_F16) ==============================
-        // Keeper warp `quad` owns the 32 candidate lists of TMEM lane quadrant `quad` (no locks).  It drains the
-        // quadrant's queue in BATCHES: an entry = one query row + the 32 keys of one 32-column chunk, and every lane
-        // takes one entry.  The epilogue's qualifying rows are sparse (1-4 lanes of a warp per chunk); the queue
-        // compacts them, so the list maintenance runs with (nearly) all lanes busy instead of one.
-        // A list is an UNSORTED set of 32 (key, id) slots plus its current maximum and the slot holding it: an
-        // insertion overwrites that slot and rescans the 32 keys for the new maximum (eight independent 16-byte
-        // loads: no dependent search / shift chain).  Lists are sorted once, when the unit is written out.
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TC_REGS_SMALL_Q));
+        // Keeper warp `quad` owns the 32 candidate lists of TMEM lane quadrant `quad`: LANE l KEEPS THE LIST OF ROW l
+        // IN ITS REGISTERS (sorted, 32 entries).  The epilogue's qualifying rows are sparse (1-4 lanes of a warp per
+        // chunk); they arrive through the quadrant's queue (entry = one row + the 32 keys of one 32-column chunk).
+        // Per batch of queued entries:
+        //   1. lane i scans entry i for the keys that still qualify (lane-rotated order, conflict-free banks);
+        //   2. the entries are handed to the lanes that own their rows (an atomicOr of the entry bit into a per-row
+        //      word of shared memory);
+        //   3. every lane folds the keys of its entries into its register list — the same instruction stream for all
+        //      lanes, so an insertion (~160 ALU instructions, no shared-memory dependency chain) serves up to 32 rows
+        //      at once instead of one.
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(TC_REGS_KEEP_Q));
+        static_assert(KTOP == 32, "the keeper lists hold 32 candidates per query");
         const int quad = warp & 3;
         const float INF = __int_as_float(0x7f800000);
-        const uint32_t keys_u = smem_u32(sList) + (uint32_t)(quad * 32) * TC_LROW;                 // this quadrant's 32 rows
-        const uint32_t ids_u = keys_u + (uint32_t)TC_BM * TC_LROW;
         const int* ready = sReady + quad * TC_QN;
         const uint32_t queue_u = smem_u32(sQueue + quad * TC_QN * TC_QENTRY);
+        float* my_worst = sWorst + quad * 32 + lane;
+        int* my_mask = sWpos + quad * 32 + lane;
+        const int qbatch = p.qbatch > 0 ? p.qbatch : TC_QBATCH;
         int next = 0;  // entries consumed so far (monotonic over the whole kernel)
         int it = 0;
         for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++it) {
             const int m_tile = unit % p.n_mtiles;
             const int split = unit / p.n_mtiles;
-            for (int rr = 0; rr < 32; ++rr) {
-                sts32(keys_u + (uint32_t)rr * TC_LROW + (uint32_t)lane * 4u, __float_as_uint(INF));
-                sts32(ids_u + (uint32_t)rr * TC_LROW + (uint32_t)lane * 4u, 0xffffffffu);
-            }
-            sWorst[quad * 32 + lane] = INF;
-            sWpos[quad * 32 + lane] = 0;
+            RegTopK<32> top;
+            top.init();
+            stsv_u32(my_worst, __float_as_uint(INF));
             __syncwarp();
             if (it > 0 && lane == 0) mbar_arrive(u_flushed);  // lists of the previous unit written out and reset
             int final_tail = -1;
@@ -408,108 +413,96 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
                     }
                     continue;
                 }
+                // a batch has a (mostly) fixed cost: wait for a worthwhile one unless the queue fills up or the unit ends
+                if (n < qbatch && final_tail < 0 && (int)ldsv_u32(sTail + quad) - next < TC_QN / 2) {
+                    if (mbar_try_wait(u_done, (uint32_t)(it & 1))) final_tail = (int)ldsv_u32(sTail + quad);
+                    else __nanosleep(100);
+                    continue;
+                }
                 asm volatile("fence.acq_rel.cta;" ::: "memory");
                 const long long kc0 = p.stats ? clock64() : 0;
                 const bool act = lane < n;
                 const uint32_t e = queue_u + (uint32_t)(my & (TC_QN - 1)) * TC_QENTRY;
-                int rr = 64 + lane, col0 = 0, pad_;
+                int rr = 0, col0 = 0, pad_;
                 float thr_e = -INF;
                 if (act) asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(rr), "=r"(col0), "=f"(thr_e), "=r"(pad_) : "r"(e + 128u) : "memory");
-                const int srow = quad * 32 + (rr & 31);
-                const uint32_t krow = keys_u + (uint32_t)(rr & 31) * TC_LROW;
-                const uint32_t irow = ids_u + (uint32_t)(rr & 31) * TC_LROW;
-                // ---- phase 1: which of the entry's 32 keys still qualify (lane-rotated order: conflict-free banks)
+                // ---- 1. which of the entry's 32 keys still qualify (the epilogue warps are the critical resource: the
+                // keeper does this scan, with the row's freshest bound)
                 unsigned qm = 0;
                 if (!(p.dbg & 64)) {
-                    const float bound = act ? fminf(thr_e, ldsv_f32(sWorst + srow)) : -INF;
-#pragma unroll 8
-                    for (int j = 0; j < 32; ++j) {
-                        const int jr = (j + lane) & 31;
-                        qm |= (lds_f32(e + (uint32_t)jr * 4u) < bound) ? (1u << jr) : 0u;
+                    const float bound = act ? fminf(thr_e, ldsv_f32(sWorst + quad * 32 + rr)) : -INF;
+#pragma unroll
+                    for (int j0 = 0; j0 < 32; j0 += 8) {  // eight loads in flight, then their tests
+                        float v[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) v[u] = lds_f32(e + (uint32_t)((j0 + u + lane) & 31) * 4u);
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) qm |= (v[u] < bound) ? (1u << ((j0 + u + lane) & 31)) : 0u;
                     }
                 }
-                // ---- phase 2: rounds; per round every lane inserts one key, one lane per distinct row
+                // ---- 2. entry i -> the lane that owns its row
+                if (qm != 0) atomicOr(sWpos + quad * 32 + rr, 1 << lane);
+                __syncwarp();
+                unsigned mine = (unsigned)ldsv_u32(my_mask);
+                if (mine != 0) stsv_u32(my_mask, 0u);
                 const long long kc1 = p.stats ? clock64() : 0;
-                int nrounds = 0;
-                const unsigned peers = __match_any_sync(0xffffffffu, rr);
-                const long long kc2 = p.stats ? clock64() : 0;
-                unsigned alive;
-                while ((alive = __ballot_sync(0xffffffffu, qm != 0)) != 0) {
-                    ++nrounds;
-                    if (qm != 0 && lane == __ffs(peers & alive) - 1) {
-                        const int jr = __ffs(qm) - 1;
-                        qm &= qm - 1;
-                        const float x = lds_f32(e + (uint32_t)jr * 4u);
-                        if (x < fminf(thr_e, ldsv_f32(sWorst + srow))) {
-                            const int pw = (int)ldsv_u32(sWpos + srow);
-                            sts32(krow + (uint32_t)pw * 4u, __float_as_uint(x));
-                            sts32(irow + (uint32_t)pw * 4u, (uint32_t)(col0 + jr));
-                            // new maximum and its slot, 16 keys at a time
-                            float mx = -INF;
-                            int pm = 0;
-#pragma unroll
-                            for (int h = 0; h < 2; ++h) {
-                                float v[16];
-#pragma unroll
-                                for (int g = 0; g < 4; ++g) {
-                                    const float4 f = lds128(krow + (uint32_t)(h * 64 + g * 16));
-                                    v[4 * g + 0] = f.x; v[4 * g + 1] = f.y; v[4 * g + 2] = f.z; v[4 * g + 3] = f.w;
-                                }
-                                float t[8];
-#pragma unroll
-                                for (int i = 0; i < 8; ++i) t[i] = fmaxf(v[i], v[i + 8]);
-#pragma unroll
-                                for (int w = 4; w >= 1; w >>= 1)
-#pragma unroll
-                                    for (int i = 0; i < w; ++i) t[i] = fmaxf(t[i], t[i + w]);
-                                if (t[0] > mx || h == 0) {
-                                    mx = t[0];
-#pragma unroll
-                                    for (int i = 15; i >= 0; --i) pm = (v[i] == mx) ? h * 16 + i : pm;
-                                }
-                            }
-                            stsv_u32(sWorst + srow, __float_as_uint(mx));
-                            stsv_u32(sWpos + srow, (uint32_t)pm);
-                            if (p.stats) atomicAdd(p.stats + 3, 1ull);
+                // ---- 3. fold: one entry per lane and outer iteration, one key per lane and inner iteration
+                int nins = 0, nrounds = 0;
+                while (__any_sync(0xffffffffu, mine != 0)) {
+                    const bool has = mine != 0;
+                    const int i = has ? __ffs(mine) - 1 : 0;
+                    mine &= mine - 1;
+                    unsigned qmi = __shfl_sync(0xffffffffu, qm, i);
+                    const int c0 = __shfl_sync(0xffffffffu, col0, i);
+                    const float the = __shfl_sync(0xffffffffu, thr_e, i);
+                    if (!has) qmi = 0;
+                    const uint32_t ei = queue_u + (uint32_t)((next + i) & (TC_QN - 1)) * TC_QENTRY;
+                    // the next key is loaded while the current one is inserted
+                    int jr = qmi ? __ffs(qmi) - 1 : 0;
+                    float x = qmi ? lds_f32(ei + (uint32_t)jr * 4u) : INF;
+                    while (__any_sync(0xffffffffu, qmi != 0)) {
+                        ++nrounds;
+                        const float cx = x;
+                        const int cj = jr;
+                        const bool cur = qmi != 0;
+                        qmi &= qmi - 1;
+                        if (qmi != 0) {
+                            jr = __ffs(qmi) - 1;
+                            x = lds_f32(ei + (uint32_t)jr * 4u);
+                        }
+                        if (cur && cx < fminf(the, top.threshold())) {
+                            top.insert(cx, c0 + cj);
+                            ++nins;
                         }
                     }
-                    __syncwarp();
                 }
+                if (nins) stsv_u32(my_worst, __float_as_uint(top.threshold()));
+                __syncwarp();
                 next += n;
                 if (lane == 0) stsv_u32(sHead + quad, (uint32_t)next);  // the slots may be reused
-                if (p.stats && lane == 0) {
-                    atomicAdd(p.stats + 4, (unsigned long long)n);
-                    atomicAdd(p.stats + 5, 1ull);
-                    atomicAdd(p.stats + 6, (unsigned long long)(clock64() - kc0));
-                    atomicAdd(p.stats + 8, (unsigned long long)(kc1 - kc0));
-                    atomicAdd(p.stats + 9, (unsigned long long)nrounds);
-                    atomicAdd(p.stats + 10, (unsigned long long)(kc2 - kc1));
+                if (p.stats) {
+                    atomicAdd(p.stats + 3, (unsigned long long)nins);
+                    if (lane == 0) {
+                        atomicAdd(p.stats + 4, (unsigned long long)n);
+                        atomicAdd(p.stats + 5, 1ull);
+                        atomicAdd(p.stats + 6, (unsigned long long)(clock64() - kc0));
+                        atomicAdd(p.stats + 8, (unsigned long long)(kc1 - kc0));
+                        atomicAdd(p.stats + 9, (unsigned long long)nrounds);
+                    }
                 }
             }
-            // ---- unit done: publish the bound, sort each list (rank by counting) and write it out (128-byte rows)
-            __syncwarp();
+            // ---- unit done: publish the bound and write this lane's (sorted) list
             {
-                const int q0 = m_tile * TC_BM + quad * 32;
-                const int qv = q0 + lane;
+                const int qv = m_tile * TC_BM + quad * 32 + lane;
                 if (qv < p.nq) {
-                    const float w = sWorst[quad * 32 + lane];
-                    if (w < INF) atomicMin(p.gthr + qv, float_to_ordered(w));
-                }
-                float* pk = p.part_key + ((size_t)split * p.nq + q0) * 32;
-                int32_t* pi = p.part_id + ((size_t)split * p.nq + q0) * 32;
-                const int rows_valid = max(0, min(32, p.nq - q0));
-                for (int rr = 0; rr < rows_valid; ++rr) {
-                    const float kk = lds_f32(keys_u + (uint32_t)rr * TC_LROW + (uint32_t)lane * 4u);
-                    const int32_t ii = (int32_t)lds_u32(ids_u + (uint32_t)rr * TC_LROW + (uint32_t)lane * 4u);
-                    int rank = 0;
-#pragma unroll 8
-                    for (int i = 0; i < 32; ++i) {
-                        const float ok = __shfl_sync(0xffffffffu, kk, i);
-                        const int32_t oi = __shfl_sync(0xffffffffu, ii, i);
-                        rank += (pair_less(ok, oi, kk, ii) || (ok == kk && oi == ii && i < lane)) ? 1 : 0;
+                    if (top.threshold() < INF) atomicMin(p.gthr + qv, float_to_ordered(top.threshold()));
+                    float4* pk = reinterpret_cast<float4*>(p.part_key + ((size_t)split * p.nq + qv) * 32);
+                    int4* pi = reinterpret_cast<int4*>(p.part_id + ((size_t)split * p.nq + qv) * 32);
+#pragma unroll
+                    for (int g = 0; g < 8; ++g) {
+                        pk[g] = make_float4(top.key[4 * g], top.key[4 * g + 1], top.key[4 * g + 2], top.key[4 * g + 3]);
+                        pi[g] = make_int4(top.id[4 * g], top.id[4 * g + 1], top.id[4 * g + 2], top.id[4 * g + 3]);
                     }
-                    pk[rr * 32 + rank] = kk;
-                    pi[rr * 32 + rank] = ii;
                 }
             }
             __syncwarp();
@@ -611,7 +604,7 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
                         base = __shfl_sync(0xffffffffu, base, 0);
                         if (hit) {
                             const int idx = base + __popc(todo & ((1u << lane) - 1u));
-                            while (idx - (int)ldsv_u32(sHead + quad) >= TC_QN) __nanosleep(200);  // queue full: leave the issue slots to the keeper
+                            while (idx - (int)ldsv_u32(sHead + quad) >= TC_QN) __nanosleep(100);  // queue full: leave the issue slots to the keeper
                             const uint32_t e = queue_u + (uint32_t)(idx & (TC_QN - 1)) * TC_QENTRY;
 #pragma unroll
                             for (int j4 = 0; j4 < 8; ++j4)
