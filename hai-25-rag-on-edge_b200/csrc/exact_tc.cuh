@@ -42,6 +42,7 @@ constexpr int TC_THREADS_Q = TC_THREADS + 128;
 constexpr int TC_REGS_CTRL_Q = 24, TC_REGS_KEEP_Q = 104, TC_REGS_EPI_Q = 112;
 constexpr int TC_QN = 128;            // candidate-queue entries per quadrant
 constexpr int TC_QBATCH = 24;         // queued rows that make a batch worth folding
+constexpr int TC_QUANT_REFRESH = 16;  // tiles of one group between reads of the finished units' quantile posts (power of two)
 constexpr int TC_QENTRY = 144;        // bytes per entry: 32 keys + {row in quadrant, first column, threshold, -}
 constexpr int TC_THR_REFRESH = 4; // tiles of one group between reads of the shared threshold (power of two)
 
@@ -78,7 +79,8 @@ struct TcParams {
     const float* bnorm;  // [n_tiles*128], +inf beyond n
     const float* lb_key; // optional per-query exclusive lower bound (multi-pass k > 32), or nullptr
     const int32_t* lb_id;
-    int32_t* gthr;       // [nq] shared thresholds (order-preserving int encoding), preset to a huge value
+    int32_t* gthr;       // [nq] shared thresholds (order-preserving int encoding), preset to a huge value; TC_F16: followed
+                         // by [2][n_splits][nq] floats, the 8th / 16th best key of every finished (split, query) list
     float* part_key;     // [n_splits*TC_EPI_GROUPS][nq][KTOP]
     int32_t* part_id;
     int nq;
@@ -153,6 +155,31 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
+}
+
+// Bound of a query's 32nd best key from the lists of FINISHED units (TC_F16): every finished (split, query) list posts
+// its 8th and its 16th best key.  Units cover disjoint rows, so the 4th smallest posted 8th-key has 4 x 8 = 32 rows at
+// or below it, and so has the 2nd smallest posted 16th-key.  Much tighter than the best single list's 32nd key once a
+// few units are done: that one only knows its own 1/n_splits of the rows.
+__device__ __forceinline__ float tc_quantile_cap(const int32_t* gthr, int nq, int n_splits, int q) {
+    const float* g8 = reinterpret_cast<const float*>(gthr + nq) + q;
+    const float* g16 = g8 + (size_t)n_splits * nq;
+    const float BIG = __int_as_float(0x7f7f7f7f);
+    float a0 = BIG, a1 = BIG;                       // two smallest 16th-keys
+    float b0 = BIG, b1 = BIG, b2 = BIG, b3 = BIG;   // four smallest 8th-keys
+    for (int s = 0; s < n_splits; ++s) {
+        const float v16 = __ldcg(g16 + (size_t)s * nq);
+        float x = __ldcg(g8 + (size_t)s * nq);
+        a1 = fminf(a1, fmaxf(a0, v16));
+        a0 = fminf(a0, v16);
+        float lo;
+        lo = fminf(b0, x); x = fmaxf(b0, x); b0 = lo;
+        lo = fminf(b1, x); x = fmaxf(b1, x); b1 = lo;
+        lo = fminf(b2, x); x = fmaxf(b2, x); b2 = lo;
+        b3 = fminf(b3, x);
+    }
+    const float c = fminf(a1, b3);
+    return c < BIG ? c : __int_as_float(0x7f800000);
 }
 
 template <int KTOP, int MODE, bool HAS_LB>
@@ -496,6 +523,11 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
                 const int qv = m_tile * TC_BM + quad * 32 + lane;
                 if (qv < p.nq) {
                     if (top.threshold() < INF) atomicMin(p.gthr + qv, float_to_ordered(top.threshold()));
+                    // 8 (16) rows of this unit lie at or below its 8th (16th) best key: four (two) such posts from
+                    // different units bound the query's 32nd best key (tc_quantile_cap)
+                    float* gq = reinterpret_cast<float*>(p.gthr + p.nq);
+                    if (top.key[7] < INF) __stcg(gq + (size_t)split * p.nq + qv, top.key[7]);
+                    if (top.key[15] < INF) __stcg(gq + ((size_t)p.n_splits + split) * p.nq + qv, top.key[15]);
                     float4* pk = reinterpret_cast<float4*>(p.part_key + ((size_t)split * p.nq + qv) * 32);
                     int4* pi = reinterpret_cast<int4*>(p.part_id + ((size_t)split * p.nq + qv) * 32);
 #pragma unroll
@@ -556,6 +588,7 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
                         cap = fminf(cap, ordered_to_float(pending));
                         pending = __ldcg(p.gthr + q);
                     }
+                    if ((j & (TC_QUANT_REFRESH - 1)) == 0) cap = fminf(cap, tc_quantile_cap(p.gthr, p.nq, p.n_splits, q));
                 }
                 const float capn = valid ? next_up(cap) : -INF;  // rows beyond the last query never qualify
                 mbar_wait(&n_full[acc], acc_phase);

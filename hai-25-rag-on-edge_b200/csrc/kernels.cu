@@ -293,8 +293,10 @@ __global__ void __launch_bounds__(128) merge_lists_kernel(const float* __restric
             for (int i = 0; i < list_len; ++i) {
                 const int32_t id = pi[i];
                 if (id < 0) break;
-                const float kk = pk[i];
-                L.insert_any(neg_in ? -kk : kk, id);
+                const float kk = neg_in ? -pk[i] : pk[i];
+                // the partial list is sorted: once an element does not make it, none of the following ones can
+                if (!pair_less(kk, id, L.key[KTOP - 1], L.id[KTOP - 1])) break;
+                L.insert_any(kk, id);
             }
         }
     }

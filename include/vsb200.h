@@ -53,9 +53,9 @@ typedef enum vs_status {
 /* Arithmetic of the exact path's dot products (distances are always combined in fp32 as
  * (qn + bn) - 2*dot, cpu_baseline.cpp:241). */
 typedef enum vs_precision {
-    VS_PREC_AUTO = 0,        /* <= 16 queries -> FFMA stream; k <= 16 -> certified fp16 candidate pass (below);
-                                otherwise 1xTF32 when every operand is exactly representable in TF32 (integer SIFT
-                                data: bit-identical to fp32), else 3xTF32 */
+    VS_PREC_AUTO = 0,        /* <= 8 queries -> FFMA stream; >= 449 queries and k <= 16 -> certified fp16 candidate pass
+                                (below); otherwise 1xTF32 when every operand is exactly representable in TF32 (integer
+                                SIFT data: bit-identical to fp32), else 3xTF32.  Thresholds measured on B200. */
     VS_PREC_FP32_3XTF32 = 1, /* tcgen05 kind::tf32, hi/lo split, 3 products, fp32 accumulate in TMEM */
     VS_PREC_FP32_FFMA = 2,   /* CUDA-core FFMA streaming kernel (HBM-bound; any batch, slow for large ones) */
     VS_PREC_TF32_1X = 3,     /* single TF32 product; exact only for TF32-representable data */

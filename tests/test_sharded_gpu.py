@@ -56,7 +56,7 @@ def _worker(rank, world, port, law, n, nq, k, prec, out_dir):
 
 
 @pytest.mark.timeout(600)
-@pytest.mark.parametrize("law,k,prec_name", [("sift", 10, "auto"), ("cont", 10, "auto"), ("cont", 10, "3xtf32"),
+@pytest.mark.parametrize("law,k,prec_name", [("sift", 10, "auto"), ("cont", 10, "f16cert"), ("cont", 10, "3xtf32"),
                                              ("cont", 100, "auto")])
 def test_nccl_sharded_equals_oracle(gpu_vsb, oracle, tmp_path, law, k, prec_name):
     import torch
@@ -66,7 +66,7 @@ def test_nccl_sharded_equals_oracle(gpu_vsb, oracle, tmp_path, law, k, prec_name
     if world < 2:
         pytest.skip("needs >= 2 GPUs (run under gpurun --gpus 2)")
     vsb = gpu_vsb
-    prec = {"auto": vsb.PREC_AUTO, "3xtf32": vsb.PREC_3XTF32}[prec_name]
+    prec = {"auto": vsb.PREC_AUTO, "3xtf32": vsb.PREC_3XTF32, "f16cert": vsb.PREC_F16_CERT}[prec_name]
     n, nq = 200_003, 300
     mp.spawn(_worker, args=(world, _free_port(), law, n, nq, k, prec, str(tmp_path)), nprocs=world, join=True)
     base = vsb.synth.make(law, 4242, n)
