@@ -149,18 +149,24 @@ static int int8_search_core(vs_int8* h, const float* q_dev, int64_t nq, int k, i
     if (ktop == 0) return fail(VS_ERR_UNSUPPORTED, "INT8 search: k > 32 is not implemented");
     const int64_t nq_pad = ceil_div64(nq, 128) * 128;
     VSB_TRY(h->q_u8.reserve((size_t)nq_pad * 128));
+    // small batches: 4 (2) copies of the quantised queries fill the 128-row tile, one per TMEM lane quadrant (pair)
+    const int rep = nq <= 32 ? 4 : (nq <= 64 ? 2 : 1);
+    if (rep > 1) VSB_CUDA(cudaMemsetAsync(h->q_u8.p, 0, 128 * 128, st));
     VSB_TRY(launch_quantize_u8(q_dev, nq * 128, h->inv_in, h->q_u8.as<uint8_t>(), st));
+    for (int c = 1; c < rep; ++c)
+        VSB_CUDA(cudaMemcpyAsync(h->q_u8.as<uint8_t>() + (size_t)c * (128 / rep) * 128, h->q_u8.p, (size_t)nq * 128,
+                                 cudaMemcpyDeviceToDevice, st));
     const TcPlan plan = tc_make_plan(h->n, nq, h->num_sms);
-    const int n_lists = plan.n_splits * int8_lists_per_split();
+    const int n_lists = plan.n_splits * int8_lists_per_split() * rep;
     VSB_TRY(h->part_key.reserve(sizeof(float) * (size_t)n_lists * nq * ktop));
     VSB_TRY(h->part_id.reserve(sizeof(int32_t) * (size_t)n_lists * nq * ktop));
     VSB_TRY(h->gthr.reserve(sizeof(int32_t) * (size_t)nq));
     VSB_TRY(h->out_keys.reserve(sizeof(float) * (size_t)nq * k));
     VSB_CUDA(cudaMemsetAsync(h->gthr.p, 0x7f, sizeof(int32_t) * (size_t)nq, st));
     CUtensorMap tmA;
-    VSB_TRY(make_tmap_2d(&tmA, h->q_u8.p, (uint64_t)nq, 128, 1, 128));
+    VSB_TRY(make_tmap_2d(&tmA, h->q_u8.p, (uint64_t)(rep > 1 ? 128 : nq), 128, 1, 128));
     if (h->profile) VSB_CUDA(cudaEventRecord(h->ev0, st));
-    VSB_TRY(launch_int8_tc(tmA, h->tmB, h->gthr.as<int32_t>(), h->m, (int)nq, h->n, plan, ktop, h->part_key.as<float>(),
+    VSB_TRY(launch_int8_tc(tmA, h->tmB, h->gthr.as<int32_t>(), h->m, (int)nq, h->n, plan, ktop, rep, h->part_key.as<float>(),
                            h->part_id.as<int32_t>(), st));
     if (h->profile) {
         VSB_CUDA(cudaEventRecord(h->ev1, st));

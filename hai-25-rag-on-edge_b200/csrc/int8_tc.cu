@@ -60,6 +60,9 @@ struct I8Params {
     int nq;
     int64_t n;
     int n_tiles, n_mtiles, n_splits, tiles_per_split;
+    int rep;           // small batches (nq <= 128 / rep): the query tile holds `rep` copies of the queries, copy r folds the
+                       // 32-column chunks c with c % rep == r of every base tile, so all four TMEM lane quadrants (= all
+                       // four SM sub-partitions) share the epilogue instead of one; 1 = no replication
 };
 
 template <int KTOP>
@@ -181,9 +184,11 @@ int8_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int split = unit / p.n_mtiles;
             const int t0 = split * p.tiles_per_split;
             const int t1 = min(t0 + p.tiles_per_split, p.n_tiles);
-            const int q = m_tile * I8_BM + row;
+            const int rows_per_copy = I8_BM / p.rep;
+            const int rix = row / rows_per_copy;                       // which copy of the queries this row belongs to
+            const int q = m_tile * I8_BM + (row - rix * rows_per_copy);
             const bool valid = q < p.nq;
-            const bool quad_live = m_tile * I8_BM + quad * 32 < p.nq;  // small batches: idle quadrants only handshake
+            const bool quad_live = m_tile * I8_BM + (quad * 32) % rows_per_copy < p.nq;  // idle quadrants only handshake
             RegTopK<KTOP> top;
             top.init();
             float cap = INF, thr = INF;
@@ -200,16 +205,10 @@ int8_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * I8_BN + grp * I8_GCOLS);
                 uint32_t r[2][32];
-                if (quad_live) tmem_ld32(taddr, r[0]);
-#pragma unroll
-                for (int c = 0; c < CH; ++c) {
-                    if (!quad_live) break;
-                    tc_wait_ld();
-                    if (c + 1 < CH) tmem_ld32(taddr + (c + 1) * 32, r[(c + 1) & 1]);
-                    const int col0 = t * I8_BN + grp * I8_GCOLS + c * 32;
+                auto fold = [&](const uint32_t (&rr)[32], const int col0) {
                     int32_t a[32];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) a[j] = (int32_t)r[c & 1][j];
+                    for (int j = 0; j < 32; ++j) a[j] = (int32_t)rr[j];
                     int32_t mx[16];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) mx[j] = max(a[j], a[j + 16]);
@@ -235,6 +234,24 @@ int8_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             }
                         }
                     }
+                };
+                if (p.rep == 1) {
+                    if (quad_live) tmem_ld32(taddr, r[0]);
+#pragma unroll
+                    for (int c = 0; c < CH; ++c) {
+                        if (!quad_live) break;
+                        tc_wait_ld();
+                        if (c + 1 < CH) tmem_ld32(taddr + (c + 1) * 32, r[(c + 1) & 1]);
+                        fold(r[c & 1], t * I8_BN + grp * I8_GCOLS + c * 32);
+                    }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < CH; ++c) {  // only the chunks of this copy
+                        if (!quad_live || ((grp * CH + c) & (p.rep - 1)) != rix) continue;
+                        tmem_ld32(taddr + c * 32, r[0]);
+                        tc_wait_ld();
+                        fold(r[0], t * I8_BN + grp * I8_GCOLS + c * 32);
+                    }
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -247,7 +264,7 @@ int8_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             if (valid) {
                 if (top.threshold() < cap) atomicMin(p.gthr + q, float_to_ordered(top.threshold()));
-                const size_t list = (size_t)split * I8_EPI_GROUPS + grp;
+                const size_t list = ((size_t)split * I8_EPI_GROUPS + grp) * p.rep + rix;
                 float* pk = p.part_key + (list * p.nq + q) * KTOP;
                 int32_t* pi = p.part_id + (list * p.nq + q) * KTOP;
 #pragma unroll
@@ -356,8 +373,10 @@ int int8_set_attributes() {
 int int8_lists_per_split() { return I8_EPI_GROUPS; }
 
 int launch_int8_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, int32_t* gthr, float m, int nq, int64_t n, const TcPlan& plan,
-                   int ktop, float* part_key, int32_t* part_id, cudaStream_t st) {
-    I8Params p{gthr, part_key, part_id, m, nq, n, plan.n_tiles, plan.n_mtiles, plan.n_splits, plan.tiles_per_split};
+                   int ktop, int rep, float* part_key, int32_t* part_id, cudaStream_t st) {
+    if (rep != 1 && rep != 2 && rep != 4) return fail(VS_ERR_INVALID, "int8: replication must be 1, 2 or 4");
+    if (rep > 1 && nq > I8_BM / rep) return fail(VS_ERR_INVALID, "int8: too many queries for the replication factor");
+    I8Params p{gthr, part_key, part_id, m, nq, n, plan.n_tiles, plan.n_mtiles, plan.n_splits, plan.tiles_per_split, rep};
     switch (ktop) {
         case 1: int8_tc_kernel<1><<<plan.grid, I8_THREADS, I8_SMEM, st>>>(tmA, tmB, p); break;
         case 5: int8_tc_kernel<5><<<plan.grid, I8_THREADS, I8_SMEM, st>>>(tmA, tmB, p); break;

@@ -93,7 +93,7 @@ int launch_max_f32(const float* x, int64_t count, float* out_zeroed, cudaStream_
 int int8_set_attributes();
 int int8_lists_per_split();
 int launch_int8_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, int32_t* gthr, float m, int nq, int64_t n, const TcPlan& plan,
-                   int ktop, float* part_key, int32_t* part_id, cudaStream_t st);
+                   int ktop, int rep, float* part_key, int32_t* part_id, cudaStream_t st);
 
 // api.cu helpers shared with api_ivf.cu / api_int8.cu
 int make_tmap_2d(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_t cols, int elem_bytes, uint32_t box_rows);
