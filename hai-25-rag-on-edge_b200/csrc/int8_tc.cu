@@ -65,7 +65,7 @@ struct I8Params {
                        // four SM sub-partitions) share the epilogue instead of one; 1 = no replication
 };
 
-template <int KTOP>
+template <int KTOP, int REP>
 __global__ void __launch_bounds__(I8_THREADS, 1)
 int8_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const I8Params p) {
     extern __shared__ uint8_t smem_raw[];
@@ -184,7 +184,7 @@ int8_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int split = unit / p.n_mtiles;
             const int t0 = split * p.tiles_per_split;
             const int t1 = min(t0 + p.tiles_per_split, p.n_tiles);
-            const int rows_per_copy = I8_BM / p.rep;
+            constexpr int rows_per_copy = I8_BM / REP;
             const int rix = row / rows_per_copy;                       // which copy of the queries this row belongs to
             const int q = m_tile * I8_BM + (row - rix * rows_per_copy);
             const bool valid = q < p.nq;
@@ -235,7 +235,7 @@ int8_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         }
                     }
                 };
-                if (p.rep == 1) {
+                if (REP == 1) {
                     if (quad_live) tmem_ld32(taddr, r[0]);
 #pragma unroll
                     for (int c = 0; c < CH; ++c) {
@@ -247,7 +247,7 @@ int8_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 } else {
 #pragma unroll
                     for (int c = 0; c < CH; ++c) {  // only the chunks of this copy
-                        if (!quad_live || ((grp * CH + c) & (p.rep - 1)) != rix) continue;
+                        if (!quad_live || ((grp * CH + c) & (REP - 1)) != rix) continue;
                         tmem_ld32(taddr + c * 32, r[0]);
                         tc_wait_ld();
                         fold(r[0], t * I8_BN + grp * I8_GCOLS + c * 32);
@@ -264,7 +264,7 @@ int8_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             if (valid) {
                 if (top.threshold() < cap) atomicMin(p.gthr + q, float_to_ordered(top.threshold()));
-                const size_t list = ((size_t)split * I8_EPI_GROUPS + grp) * p.rep + rix;
+                const size_t list = ((size_t)split * I8_EPI_GROUPS + grp) * REP + rix;
                 float* pk = p.part_key + (list * p.nq + q) * KTOP;
                 int32_t* pi = p.part_id + (list * p.nq + q) * KTOP;
 #pragma unroll
@@ -362,12 +362,19 @@ int launch_max_f32(const float* x, int64_t count, float* out_zeroed, cudaStream_
     return VS_OK;
 }
 
+template <int KTOP>
+static int int8_set_attr_k() {
+    VSB_CUDA(cudaFuncSetAttribute(int8_tc_kernel<KTOP, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM));
+    VSB_CUDA(cudaFuncSetAttribute(int8_tc_kernel<KTOP, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM));
+    VSB_CUDA(cudaFuncSetAttribute(int8_tc_kernel<KTOP, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM));
+    return VS_OK;
+}
 int int8_set_attributes() {
-    VSB_CUDA(cudaFuncSetAttribute(int8_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM));
-    VSB_CUDA(cudaFuncSetAttribute(int8_tc_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM));
-    VSB_CUDA(cudaFuncSetAttribute(int8_tc_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM));
-    VSB_CUDA(cudaFuncSetAttribute(int8_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM));
-    VSB_CUDA(cudaFuncSetAttribute(int8_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM));
+    VSB_TRY(int8_set_attr_k<1>());
+    VSB_TRY(int8_set_attr_k<5>());
+    VSB_TRY(int8_set_attr_k<10>());
+    VSB_TRY(int8_set_attr_k<16>());
+    VSB_TRY(int8_set_attr_k<32>());
     return VS_OK;
 }
 int int8_lists_per_split() { return I8_EPI_GROUPS; }
@@ -377,14 +384,21 @@ int launch_int8_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, int32_t* gthr
     if (rep != 1 && rep != 2 && rep != 4) return fail(VS_ERR_INVALID, "int8: replication must be 1, 2 or 4");
     if (rep > 1 && nq > I8_BM / rep) return fail(VS_ERR_INVALID, "int8: too many queries for the replication factor");
     I8Params p{gthr, part_key, part_id, m, nq, n, plan.n_tiles, plan.n_mtiles, plan.n_splits, plan.tiles_per_split, rep};
+#define VSB_I8_LAUNCH(KT)                                                                     \
+    case KT:                                                                                  \
+        if (rep == 1) int8_tc_kernel<KT, 1><<<plan.grid, I8_THREADS, I8_SMEM, st>>>(tmA, tmB, p);      \
+        else if (rep == 2) int8_tc_kernel<KT, 2><<<plan.grid, I8_THREADS, I8_SMEM, st>>>(tmA, tmB, p); \
+        else int8_tc_kernel<KT, 4><<<plan.grid, I8_THREADS, I8_SMEM, st>>>(tmA, tmB, p);               \
+        break;
     switch (ktop) {
-        case 1: int8_tc_kernel<1><<<plan.grid, I8_THREADS, I8_SMEM, st>>>(tmA, tmB, p); break;
-        case 5: int8_tc_kernel<5><<<plan.grid, I8_THREADS, I8_SMEM, st>>>(tmA, tmB, p); break;
-        case 10: int8_tc_kernel<10><<<plan.grid, I8_THREADS, I8_SMEM, st>>>(tmA, tmB, p); break;
-        case 16: int8_tc_kernel<16><<<plan.grid, I8_THREADS, I8_SMEM, st>>>(tmA, tmB, p); break;
-        case 32: int8_tc_kernel<32><<<plan.grid, I8_THREADS, I8_SMEM, st>>>(tmA, tmB, p); break;
+        VSB_I8_LAUNCH(1)
+        VSB_I8_LAUNCH(5)
+        VSB_I8_LAUNCH(10)
+        VSB_I8_LAUNCH(16)
+        VSB_I8_LAUNCH(32)
         default: return fail(VS_ERR_UNSUPPORTED, "INT8 search: k > 32 is not implemented");
     }
+#undef VSB_I8_LAUNCH
     VSB_CUDA(cudaGetLastError());
     return VS_OK;
 }
