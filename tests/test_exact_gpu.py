@@ -236,3 +236,31 @@ def test_merge_topk_dev_any_k(gpu_vsb, g, k, smallest):
     assert np.array_equal(oi.cpu().numpy(), want_i)
     valid = want_i >= 0
     assert np.array_equal(ok.cpu().numpy()[valid], want_k[valid])
+
+
+def test_massive_ties_duplicated_rows(gpu_vsb, oracle):
+    """Integer SIFT-law base in which every vector occurs 50 times (shuffled): every distance level is a 50-way tie,
+    the top-10 of every query lies inside one tie group and straddles the next.  Keys must be bit-exact on every
+    precision path, ids may differ from the oracle only inside tie groups (the certified fp16 pass cannot certify
+    tied boundaries and has to fall back), no id may repeat."""
+    vsb = gpu_vsb
+    rng = np.random.default_rng(5)
+    distinct = vsb.synth.make("sift", 4711, 2000)
+    base = np.repeat(distinct, 50, axis=0)[rng.permutation(100_000)].copy()
+    qry = vsb.synth.make("sift", 4712, 200)
+    qry[:20] = distinct[:20]                      # exact hits: distance 0, 50 times each
+    k = 10
+    oi, od = oracle.exact_search(base, qry, k, mode=1)
+    idx = vsb.ExactIndex(base)
+    try:
+        for prec in _precisions(vsb, "sift"):
+            ids, d = idx.search(qry, k, prec)
+            rec = oracle.exact_distances_at(base, qry, ids)
+            assert_topk_matches(ids, d, oi, od, rec, exact=True, what=f"ties {vsb.PREC_NAMES[prec]}")
+            if prec != vsb.PREC_F16_CERT:        # canonical (distance, id) order: identical to the oracle's canonical mode
+                assert np.array_equal(ids, oi)
+        ids, d = idx.search(qry, 64, vsb.PREC_AUTO)   # multi-pass (k > 32) across tie groups
+        oi64, od64 = oracle.exact_search(base, qry, 64, mode=1)
+        assert np.array_equal(d, od64) and np.array_equal(ids, oi64)
+    finally:
+        idx.close()

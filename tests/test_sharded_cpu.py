@@ -90,3 +90,87 @@ def test_two_rank_gloo_merge_equals_single_index(tmp_path):
     for r in range(world):   # identical, complete answer on every rank, equal to the unsharded oracle
         g = np.load(tmp_path / f"rank{r}.npz")
         assert np.array_equal(g["ids"], want_ids) and np.array_equal(g["d"], want_d)
+
+
+# ---------------------------------------------------------------------------------------------- IVF / INT8 sharding
+def _merge_host_desc(ids_all, sc_all, k):
+    """numpy statement of vs_merge_topk_dev(smallest=0): (score desc, id asc), -1 padding last."""
+    g, nq, kk = ids_all.shape
+    ids = ids_all.transpose(1, 0, 2).reshape(nq, g * kk)
+    sc = sc_all.transpose(1, 0, 2).reshape(nq, g * kk).astype(np.float64)
+    key = np.where(ids >= 0, -sc, np.inf)
+    order = np.lexsort((ids.astype(np.uint32), key), axis=1)[:, :k]
+    return np.take_along_axis(ids, order, 1), np.take_along_axis(sc_all.transpose(1, 0, 2).reshape(nq, g * kk), order, 1)
+
+
+def _make_ivf(vsb, oracle, n, nlist, seed=5):
+    base = vsb.synth.make("mix", seed, n)
+    rng = np.random.default_rng(seed)
+    cent = base[rng.choice(n, nlist, replace=False)].copy()
+    lab, _ = oracle.kmeans_assign(base, cent)
+    order = np.argsort(lab, kind="stable").astype(np.int32)
+    offsets = np.concatenate([[0], np.cumsum(np.bincount(lab, minlength=nlist))]).astype(np.int32)
+    return base, cent, order, offsets
+
+
+def _ivf_worker(rank, world, port, n, nlist, nq, k, nprobe, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import vsb200_loader
+    from oracle import oracle
+
+    vsb = vsb200_loader.load()
+    from vsb200 import sharded
+
+    base, cent, order, offsets = _make_ivf(vsb, oracle, n, nlist)
+    qry = vsb.synth.make("mix", 6, nq)
+    owner = sharded.assign_lists(offsets, world)
+    vec, off, idm = sharded.local_ivf_arrays(base[order], offsets, order, owner, rank)
+    coarse = oracle.ivf_coarse(qry, cent)   # replicated coarse stage: identical probe sets on every rank
+    ids, sc, cnt, total = oracle.ivf_search(vec, off, idm, True, coarse, qry, k, nprobe, mode=1)
+    ids_all, sc_all = sharded.allgather_topk(torch.from_numpy(ids), torch.from_numpy(sc))
+    tot = torch.tensor([total], dtype=torch.int64)
+    dist.all_reduce(tot)
+    mi, ms = _merge_host_desc(ids_all.numpy(), sc_all.numpy(), k)
+    np.savez(os.path.join(out_dir, f"ivf{rank}.npz"), ids=mi, sc=ms, total=tot.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_list_assignment_is_a_balanced_partition():
+    sys.path.insert(0, ROOT)
+    import vsb200_loader
+
+    vsb200_loader.load()
+    from vsb200 import sharded
+
+    rng = np.random.default_rng(0)
+    sizes = rng.integers(0, 6000, size=1024)
+    offsets = np.concatenate([[0], np.cumsum(sizes)])
+    for world in (1, 2, 4, 8):
+        owner = sharded.assign_lists(offsets, world)
+        assert owner.min() >= 0 and owner.max() < world
+        loads = np.array([sizes[owner == r].sum() for r in range(world)])
+        assert loads.sum() == sizes.sum() and loads.max() - loads.min() <= sizes.max()
+        vec = np.arange(offsets[-1], dtype=np.float32)[:, None]
+        seen = np.concatenate([sharded.local_ivf_arrays(vec, offsets, np.arange(offsets[-1]), owner, r)[2] for r in range(world)])
+        assert np.array_equal(np.sort(seen), np.arange(offsets[-1]))   # every row owned exactly once
+
+
+@pytest.mark.timeout(180)
+def test_two_rank_gloo_ivf_lists_sharded_equals_single_index(tmp_path):
+    sys.path.insert(0, ROOT)
+    from oracle import oracle
+    import vsb200_loader
+
+    vsb = vsb200_loader.load()
+    n, nlist, nq, k, nprobe, world = 8000, 64, 29, 10, 8, 2
+    mp.spawn(_ivf_worker, args=(world, _free_port(), n, nlist, nq, k, nprobe, str(tmp_path)), nprocs=world, join=True)
+    base, cent, order, offsets = _make_ivf(vsb, oracle, n, nlist)
+    qry = vsb.synth.make("mix", 6, nq)
+    coarse = oracle.ivf_coarse(qry, cent)
+    wi, ws, wc, wt = oracle.ivf_search(base[order], offsets, order, True, coarse, qry, k, nprobe, mode=1)
+    for r in range(world):
+        g = np.load(tmp_path / f"ivf{r}.npz")
+        assert np.array_equal(g["ids"], wi) and np.array_equal(g["sc"], ws) and int(g["total"][0]) == wt
