@@ -98,6 +98,23 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def ncu_dram_bytes(path):
+    """dram__bytes_read.sum + dram__bytes_write.sum of a tools/ncu_summary.py excerpt, or None."""
+    try:
+        tot, seen = 0.0, 0
+        for ln in open(path):
+            f = ln.split()
+            if len(f) >= 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(f[2], None)
+                if mult is None:
+                    return None
+                tot += float(f[1]) * mult
+                seen += 1
+        return tot if seen == 2 else None
+    except OSError:
+        return None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -324,6 +341,11 @@ def main():
                     "unit": "TFLOP/s", "traffic": None, "kernel": "exact_tc_kernel",
                     "tf32_products": split, "algorithmic_fp32_tflops": 2.0 * nq * n_local * DIM / (ms_kernel * 1e-3) / 1e12,
                     "peak_note": f"TF32 dense = MEASURED_PEAKS bf16 burst / 2 ({pk['src']})"}
+        if world == 1 and nq == N_QUERY:
+            # DRAM bytes of one launch of this kernel from the committed `ncu --set full` capture of the same command
+            prof = {vsb.PREC_F16_CERT: "r1e_ncu_full_exact_tc_f16.txt", vsb.PREC_3XTF32: "r1e_ncu_full_exact_tc_3xtf32.txt"}.get(prec_used)
+            roof["traffic"] = ncu_dram_bytes(os.path.join(ROOT, "profiles", prof)) if prof else None
+            roof["traffic_unit"] = "bytes/launch (dram__bytes_read.sum + dram__bytes_write.sum, profiles/%s)" % prof if prof else None
         roof["frac"] = roof["achieved"] / roof["peak"]
         roof["kernel_ms"] = ms_kernel
         line = {

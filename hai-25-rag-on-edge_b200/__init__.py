@@ -115,6 +115,17 @@ class ExactIndex:
         _check(lib().vs_exact_search_dev(self._h, _ptr(q_ptr), C.c_int64(nq), C.c_int(k), C.c_int(precision),
                                          _ptr(ids_ptr), _ptr(dists_ptr), C.c_void_p(stream)))
 
+    def search_dev_begin(self, q_ptr: int, nq: int, k: int, precision: int, ids_ptr: int, dists_ptr: int, stream: int = 0):
+        """First half of search_dev: enqueues only (no host synchronisation); pair with search_dev_finish()."""
+        _check(lib().vs_exact_search_dev_begin(self._h, _ptr(q_ptr), C.c_int64(nq), C.c_int(k), C.c_int(precision),
+                                               _ptr(ids_ptr), _ptr(dists_ptr), C.c_void_p(stream)))
+
+    def search_dev_finish(self) -> int:
+        """Second half: waits for the certification count, redoes uncertified queries; -> result rows rewritten."""
+        n = C.c_int(0)
+        _check(lib().vs_exact_search_dev_finish(self._h, C.byref(n)))
+        return n.value
+
     def set_profile(self, enable: bool = True) -> None:
         _check(lib().vs_exact_set_profile(self._h, C.c_int(int(enable))))
 

@@ -90,6 +90,15 @@ struct vs_exact {
     bool profile = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool ev_valid = false;
+    // certified search split in two (vs_exact_search_dev_begin / _finish): what finish needs to redo uncertified queries
+    cudaEvent_t ev_cert = nullptr;
+    bool cert_pending = false;
+    const float* pend_q = nullptr;
+    int64_t pend_nq = 0;
+    int pend_k = 0;
+    int32_t* pend_ids = nullptr;
+    float* pend_dists = nullptr;
+    cudaStream_t pend_st = nullptr;
 };
 
 static int exact_free(vs_exact* h) {
@@ -107,6 +116,7 @@ static int exact_free(vs_exact* h) {
     if (h->h_flag) cudaFreeHost(h->h_flag);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->ev_cert) cudaEventDestroy(h->ev_cert);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return VS_OK;
@@ -231,7 +241,8 @@ static int exact_create_common(vs_exact_t** out, const float* base, bool on_devi
 }
 
 static int exact_search_core(vs_exact* h, const float* q_dev, int64_t nq, int k, int precision, int32_t* out_ids,
-                             float* out_dists, cudaStream_t st);
+                             float* out_dists, cudaStream_t st, bool defer_certification = false);
+static int exact_certified_finish(vs_exact* h, int* n_redone);
 
 // Certified candidate pass: scaled fp16 tensor-core kernel keeps the 32 best keys per query (error bounded by
 // cert_a*sqrt(qn)+cert_b), the merge kernel recomputes those 32 distances in exact fp32, ranks them and certifies
@@ -245,8 +256,7 @@ static int exact_search_certified(vs_exact* h, const float* q_dev, int64_t nq, i
     VSB_TRY(h->qparams.reserve(sizeof(TcQueryParams)));
     VSB_TRY(h->unc_list.reserve(sizeof(int32_t) * (size_t)nq));
     VSB_CUDA(cudaMemsetAsync(flag + 1, 0, 2 * sizeof(int), st));
-    VSB_TRY(launch_prep_rows(q_dev, nq, 128, h->qnorm.as<float>(), nullptr, nullptr, nullptr, st));
-    VSB_TRY(launch_absmax_f32(q_dev, nq * 128, reinterpret_cast<float*>(flag + 2), st));
+    VSB_TRY(launch_query_prep(q_dev, nq, h->qnorm.as<float>(), reinterpret_cast<float*>(flag + 2), st));
     TcQueryParams* qp = h->qparams.as<TcQueryParams>();
     VSB_TRY(launch_tc_query_params(reinterpret_cast<const float*>(flag + 2), h->s_b, h->bn_max, qp, st));
     VSB_TRY(launch_to_half_scaled(q_dev, nq * 128, 1.f, qp, h->qf16.p, st));
@@ -271,11 +281,36 @@ static int exact_search_certified(vs_exact* h, const float* q_dev, int64_t nq, i
     VSB_TRY(launch_merge_lists(h->part_key.as<float>(), h->part_id.as<int32_t>(), n_lists, nq, ktop, ktop, k, h->id_base, 0, 0,
                                out_dists, out_ids, k, 0, nullptr, nullptr, h->d_base, h->d_norm, q_dev, h->qnorm.as<float>(), st,
                                qp, flag + 1, h->unc_list.as<int32_t>()));
-    h->last_launches = 6;
+    h->last_launches = 5;
     h->last_precision = VS_PREC_F16_CERTIFIED;
+    h->last_fallback = 0;
     VSB_CUDA(cudaMemcpyAsync(h->h_flag + 1, flag + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
-    VSB_CUDA(cudaStreamSynchronize(st));
+    if (!h->ev_cert) VSB_CUDA(cudaEventCreateWithFlags(&h->ev_cert, cudaEventDisableTiming));
+    VSB_CUDA(cudaEventRecord(h->ev_cert, st));
+    h->cert_pending = true;
+    h->pend_q = q_dev;
+    h->pend_nq = nq;
+    h->pend_k = k;
+    h->pend_ids = out_ids;
+    h->pend_dists = out_dists;
+    h->pend_st = st;
+    return VS_OK;
+}
+
+// Second half of the certified search: waits for the 4-byte count of uncertified queries (an event recorded right
+// after its copy: work enqueued later on the stream is not waited for) and redoes those queries on the fp32 path.
+static int exact_certified_finish(vs_exact* h, int* n_redone) {
+    if (n_redone) *n_redone = 0;
+    if (!h->cert_pending) return VS_OK;
+    h->cert_pending = false;
+    const float* q_dev = h->pend_q;
+    const int k = h->pend_k;
+    int32_t* out_ids = h->pend_ids;
+    float* out_dists = h->pend_dists;
+    cudaStream_t st = h->pend_st;
+    VSB_CUDA(cudaEventSynchronize(h->ev_cert));
     const int n_unc = h->h_flag[1];
+    if (n_redone) *n_redone = n_unc;
     h->last_fallback = n_unc;
     if (n_unc > 0) {
         VSB_TRY(h->fb_q.reserve(sizeof(float) * (size_t)n_unc * 128));
@@ -300,7 +335,8 @@ static int exact_search_certified(vs_exact* h, const float* q_dev, int64_t nq, i
 
 // One group of <= 32 results per query: [pass]
 static int exact_search_core(vs_exact* h, const float* q_dev, int64_t nq, int k, int precision, int32_t* out_ids,
-                             float* out_dists, cudaStream_t st) {
+                             float* out_dists, cudaStream_t st, bool defer_certification) {
+    if (h->cert_pending) return fail(VS_ERR_INVALID, "vs_exact_search_dev_finish() of the previous search was not called");
     h->last_launches = 0;
     h->last_fallback = 0;
     if (nq == 0) return VS_OK;
@@ -321,7 +357,10 @@ static int exact_search_core(vs_exact* h, const float* q_dev, int64_t nq, int k,
     if (want_tc && dim != 128) return fail(VS_ERR_UNSUPPORTED, "tensor-core path needs dim == 128");
 
     VSB_TRY(h->qnorm.reserve(sizeof(float) * (size_t)nq));
-    if (prec == VS_PREC_F16_CERTIFIED) return exact_search_certified(h, q_dev, nq, k, out_ids, out_dists, st);
+    if (prec == VS_PREC_F16_CERTIFIED) {
+        VSB_TRY(exact_search_certified(h, q_dev, nq, k, out_ids, out_dists, st));
+        return defer_certification ? VS_OK : exact_certified_finish(h, nullptr);
+    }
     const int passes = (k + kMaxRegK - 1) / kMaxRegK;
     // single pass: keep a couple of spare candidates beyond k so that the exact refine can repair a k-th/k+1-th
     // swap caused by the tensor-core rounding bias
@@ -473,6 +512,23 @@ int vs_exact_search_dev(vs_exact_t* h, const float* queries_dev, int64_t nq, int
     VSB_CUDA(cudaSetDevice(h->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
     return exact_search_core(h, queries_dev, nq, k, precision, out_ids_dev, out_dists_dev, st);
+}
+
+int vs_exact_search_dev_begin(vs_exact_t* h, const float* queries_dev, int64_t nq, int k, int precision,
+                              int32_t* out_ids_dev, float* out_dists_dev, void* stream) {
+    if (!h) return fail(VS_ERR_INVALID, "handle is NULL");
+    if (nq < 0 || k <= 0) return fail(VS_ERR_INVALID, "nq < 0 or k <= 0");
+    if ((int64_t)k > h->n) return fail(VS_ERR_INVALID, "k > n (undefined in the reference, cpu_baseline.cpp:129-131)");
+    if (nq > 0 && (!queries_dev || !out_ids_dev || !out_dists_dev)) return fail(VS_ERR_INVALID, "NULL buffer");
+    VSB_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    return exact_search_core(h, queries_dev, nq, k, precision, out_ids_dev, out_dists_dev, st, true);
+}
+
+int vs_exact_search_dev_finish(vs_exact_t* h, int* n_redone) {
+    if (!h) return fail(VS_ERR_INVALID, "handle is NULL");
+    VSB_CUDA(cudaSetDevice(h->device));
+    return exact_certified_finish(h, n_redone);
 }
 
 int vs_exact_search_f32(vs_exact_t* h, const float* queries, int64_t nq, int k, int precision, int32_t* out_ids,

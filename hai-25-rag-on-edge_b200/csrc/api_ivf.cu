@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <random>
@@ -31,7 +32,8 @@ struct vs_ivf {
     float* d_centroids = nullptr;  // [nlist x 128]
     CUtensorMap tmV;
     cudaStream_t stream = nullptr;
-    DevBuf q, scores, probes, out_ids, out_scores, out_counts, total;
+    DevBuf q, scores, probes, out_ids, out_scores, out_counts, total, lm_ws, part_key, part_id;
+    int num_sms = 148;
     unsigned long long* h_total = nullptr;  // pinned
     bool profile = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -45,7 +47,9 @@ static int ivf_free(vs_ivf* h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (void* p : {(void*)h->d_vectors, (void*)h->d_offsets, (void*)h->d_idmap, (void*)h->d_centroids})
         if (p) cudaFree(p);
-    for (DevBuf* b : {&h->q, &h->scores, &h->probes, &h->out_ids, &h->out_scores, &h->out_counts, &h->total}) b->release();
+    for (DevBuf* b : {&h->q, &h->scores, &h->probes, &h->out_ids, &h->out_scores, &h->out_counts, &h->total, &h->lm_ws,
+                      &h->part_key, &h->part_id})
+        b->release();
     if (h->h_total) cudaFreeHost(h->h_total);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -94,6 +98,8 @@ static int ivf_create_impl(vs_ivf_t** out, const float* vectors, int64_t n, int 
         VSB_CUDA(cudaMemcpyAsync(h->d_centroids, centroids, sizeof(float) * (size_t)nlist * dim, cudaMemcpyHostToDevice, h->stream));
         VSB_TRY(make_tmap_2d(&h->tmV, h->d_vectors, (uint64_t)n + pad_rows, 128, 4, (uint32_t)ivf_scan_rows_per_chunk()));
         VSB_TRY(ivf_set_attributes());
+        VSB_TRY(ivf_lm_set_attributes());
+        cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device);
         VSB_TRY(h->total.reserve(sizeof(unsigned long long)));
         VSB_CUDA(cudaMallocHost((void**)&h->h_total, sizeof(unsigned long long)));
         VSB_CUDA(cudaStreamSynchronize(h->stream));
@@ -119,7 +125,30 @@ static int ivf_search_core(vs_ivf* h, const float* q_dev, int64_t nq, int k, int
     VSB_CUDA(cudaMemsetAsync(h->total.p, 0, sizeof(unsigned long long), st));
     VSB_TRY(launch_ivf_coarse(q_dev, nq, h->d_centroids, h->nlist, h->scores.as<float>(), st));
     VSB_TRY(launch_ivf_probes(h->scores.as<float>(), nq, h->nlist, nprobe, h->probes.as<int32_t>(), st));
+    // large batches: group the (query, list) pairs by list and scan list-major (K8, FFMA-bound) instead of
+    // query-major (K6, bound by streaming each probed list once per query).  VSB_IVF_LM=0/1 forces either path.
+    const char* lm_env = getenv("VSB_IVF_LM");
+    const bool list_major = lm_env ? atoi(lm_env) != 0 : (nq >= 256 && round_up_ktop(k) != 0);
     if (h->profile) VSB_CUDA(cudaEventRecord(h->ev0, st));
+    if (list_major) {
+        const int ktop = round_up_ktop(k);
+        if (ktop == 0) return fail(VS_ERR_UNSUPPORTED, "IVF search: k > 32 is not implemented");
+        VSB_TRY(h->lm_ws.reserve(sizeof(int32_t) * ivf_lm_workspace_ints(nq, nprobe, h->nlist)));
+        VSB_TRY(h->part_key.reserve(sizeof(float) * (size_t)nprobe * nq * ktop));
+        VSB_TRY(h->part_id.reserve(sizeof(int32_t) * (size_t)nprobe * nq * ktop));
+        VSB_TRY(launch_ivf_listmajor(q_dev, h->d_vectors, h->d_offsets, h->d_idmap, h->nlist, h->probes.as<int32_t>(), nq, nprobe,
+                                     k, h->lm_ws.as<int32_t>(), h->part_key.as<float>(), h->part_id.as<int32_t>(), out_counts,
+                                     h->total.as<unsigned long long>(), h->num_sms, st));
+        if (h->profile) {
+            VSB_CUDA(cudaEventRecord(h->ev1, st));
+            h->ev_valid = true;
+        }
+        // keys are -score: merge ascending, store +score (padding: -inf / -1)
+        VSB_TRY(launch_merge_lists(h->part_key.as<float>(), h->part_id.as<int32_t>(), nprobe, nq, ktop, ktop, k, 0, 0, 1, out_scores,
+                                   out_ids, k, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, st));
+        h->last_launches = 8;
+        return VS_OK;
+    }
     VSB_TRY(launch_ivf_scan(h->tmV, q_dev, h->probes.as<int32_t>(), h->d_offsets, h->d_idmap, nq, nprobe, k, out_scores, out_ids,
                             out_counts, h->total.as<unsigned long long>(), st));
     if (h->profile) {

@@ -88,6 +88,43 @@ int launch_prep_rows(const float* x, int64_t rows, int dim, float* norms, float*
     return VS_OK;
 }
 
+// Query prep of the certified path in one pass: ||q||^2 in the reference's order (the eight partial sums of
+// compute_norm_avx2, cpu_baseline.cpp:99-107, kept by ONE thread per row, then added 0..7) and the batch's abs-max.
+// Queries are few (<= a few MB): a thread per row with 16-byte loads beats the 8-threads-per-row base kernel here.
+__global__ void __launch_bounds__(128) query_prep_kernel(const float* __restrict__ x, int64_t rows, float* __restrict__ norms,
+                                                         float* __restrict__ absmax_out) {
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    float mx = 0.f;
+    if (row < rows) {
+        const float4* v = reinterpret_cast<const float4*>(x + row * 128);
+        float acc[8];
+#pragma unroll
+        for (int l = 0; l < 8; ++l) acc[l] = 0.f;
+#pragma unroll 4
+        for (int i = 0; i < 16; ++i) {
+            const float4 a = __ldg(v + 2 * i), b = __ldg(v + 2 * i + 1);
+            acc[0] = fmaf(a.x, a.x, acc[0]); acc[1] = fmaf(a.y, a.y, acc[1]);
+            acc[2] = fmaf(a.z, a.z, acc[2]); acc[3] = fmaf(a.w, a.w, acc[3]);
+            acc[4] = fmaf(b.x, b.x, acc[4]); acc[5] = fmaf(b.y, b.y, acc[5]);
+            acc[6] = fmaf(b.z, b.z, acc[6]); acc[7] = fmaf(b.w, b.w, acc[7]);
+            mx = fmaxf(mx, fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))));
+            mx = fmaxf(mx, fmaxf(fmaxf(fabsf(b.x), fabsf(b.y)), fmaxf(fabsf(b.z), fabsf(b.w))));
+        }
+        float s = acc[0];
+#pragma unroll
+        for (int l = 1; l < 8; ++l) s = __fadd_rn(s, acc[l]);
+        norms[row] = s;
+    }
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0 && mx > 0.f) atomicMax(reinterpret_cast<int*>(absmax_out), __float_as_int(mx));
+}
+int launch_query_prep(const float* x, int64_t rows, float* norms, float* absmax_zeroed, cudaStream_t st) {
+    if (rows <= 0) return VS_OK;
+    query_prep_kernel<<<(unsigned)ceil_div64(rows, 128), 128, 0, st>>>(x, rows, norms, absmax_zeroed);
+    VSB_CUDA(cudaGetLastError());
+    return VS_OK;
+}
+
 __global__ void fill_f32_kernel(float* p, int64_t n, float v) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
 }

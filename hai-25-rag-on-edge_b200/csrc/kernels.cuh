@@ -16,6 +16,8 @@ struct TcQueryParams {
 };
 int launch_absmax_f32(const float* x, int64_t count, float* out_zeroed, cudaStream_t st);
 float f16_scale_host(float absmax);
+// dim == 128 only: norms (reference summation order) + abs-max of the whole batch in one pass
+int launch_query_prep(const float* x, int64_t rows, float* norms, float* absmax_zeroed, cudaStream_t st);
 int launch_tc_query_params(const float* q_absmax, float s_b, float bn_max, TcQueryParams* out, cudaStream_t st);
 int launch_to_half_scaled(const float* x, int64_t count, float scale, const TcQueryParams* scale_dev, void* out_half,
                           cudaStream_t st);
@@ -80,6 +82,13 @@ int launch_ivf_probes(const float* scores, int64_t nq, int nlist, int nprobe, in
 int launch_ivf_scan(const CUtensorMap& tmV, const float* q, const int32_t* probes, const int32_t* offsets,
                     const int32_t* id_map, int64_t nq, int nprobe, int k, float* out_scores, int32_t* out_ids,
                     int32_t* out_counts, unsigned long long* total, cudaStream_t st);
+// K8 list-major scan for large batches (ivf_lm.cu): one sorted list per (query, probe slot) -> part_key/part_id
+// [nprobe][nq][round_up_ktop(k)] (key = -score), counts and total candidates; ws = ivf_lm_workspace_ints() ints
+int ivf_lm_set_attributes();
+size_t ivf_lm_workspace_ints(int64_t nq, int nprobe, int nlist);
+int launch_ivf_listmajor(const float* q, const float* vectors, const int32_t* offsets, const int32_t* id_map, int nlist,
+                         const int32_t* probes, int64_t nq, int nprobe, int k, int32_t* ws, float* part_key, int32_t* part_id,
+                         int32_t* out_counts, unsigned long long* total, int num_sms, cudaStream_t st);
 int ivf_set_attributes();
 int ivf_scan_rows_per_chunk();
 

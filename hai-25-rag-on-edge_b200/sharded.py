@@ -56,14 +56,24 @@ class ShardedExact:
         """Enqueues on `stream` (torch's current stream must be that stream: NCCL orders against it)."""
         if nq != self.nq_max:
             raise ValueError("ShardedExact buffers are sized for nq_max queries per call")
-        self.index.search_dev(q_ptr, nq, self.k, precision, self.ids_loc.data_ptr(), self.d_loc.data_ptr(), stream)
         if self.world == 1:
+            self.index.search_dev(q_ptr, nq, self.k, precision, self.ids_loc.data_ptr(), self.d_loc.data_ptr(), stream)
             return self.ids_loc, self.d_loc
+        # enqueue the local search, the exchange and the merge back to back; only then wait for the certification count
+        # of the local search (the launch latency of the collectives hides behind the fused kernel)
+        self.index.search_dev_begin(q_ptr, nq, self.k, precision, self.ids_loc.data_ptr(), self.d_loc.data_ptr(), stream)
+        self._exchange(nq, stream)
+        redone = torch.tensor([self.index.search_dev_finish()], dtype=torch.int32, device=self.ids_loc.device)
+        dist.all_reduce(redone, op=dist.ReduceOp.MAX, group=self.group)
+        if int(redone.item()) > 0:  # some rank rewrote result rows after the exchange had been enqueued: exchange again
+            self._exchange(nq, stream)
+        return self.ids_out, self.d_out
+
+    def _exchange(self, nq: int, stream: int):
         dist.all_gather_into_tensor(self.ids_all, self.ids_loc, group=self.group)
         dist.all_gather_into_tensor(self.d_all, self.d_loc, group=self.group)
         self.vsb.merge_topk_dev(self.ids_all.data_ptr(), self.d_all.data_ptr(), self.world, nq, self.k, True,
                                 self.ids_out.data_ptr(), self.d_out.data_ptr(), stream)
-        return self.ids_out, self.d_out
 
 
 # ------------------------------------------------------------------------------------------------------------------

@@ -99,6 +99,14 @@ VSB_API int vs_exact_search_f32(vs_exact_t* h, const float* queries, int64_t nq,
 /* Device-pointer variant; asynchronous on `stream`. */
 VSB_API int vs_exact_search_dev(vs_exact_t* h, const float* queries_dev, int64_t nq, int k, int precision,
                         int32_t* out_ids_dev, float* out_dists_dev, void* stream);
+/* The same in two halves, for callers that want to enqueue more work (e.g. the all-gather of a sharded search) before
+ * the host waits for the certification count of VS_PREC_F16_CERTIFIED / AUTO: _begin enqueues and returns without any
+ * host synchronisation; _finish waits for the count only (not for work enqueued after _begin), redoes the uncertified
+ * queries on the same stream and reports how many result rows it rewrote (0 in the common case: whatever consumed the
+ * results in between is still valid).  Exactly one _finish per _begin. */
+VSB_API int vs_exact_search_dev_begin(vs_exact_t* h, const float* queries_dev, int64_t nq, int k, int precision,
+                                      int32_t* out_ids_dev, float* out_dists_dev, void* stream);
+VSB_API int vs_exact_search_dev_finish(vs_exact_t* h, int* n_redone);
 /* Introspection for benchmarks: kernels launched / tensor-core or streaming kernel device time of the last
  * search is measured by the caller with CUDA events on the stream; this returns how many kernels the last
  * search launched and which precision path AUTO resolved to. */

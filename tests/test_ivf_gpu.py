@@ -19,10 +19,15 @@ def make_index(vsb, oracle, n, nlist, seed=3, law="mix"):
     return base, cent, order, offsets
 
 
+@pytest.mark.parametrize("scan", ["query_major", "list_major"])
 @pytest.mark.parametrize("law", ["mix", "cont"])
 @pytest.mark.parametrize("n,nlist,nq,k,nprobe", [(20000, 64, 50, 10, 8), (5000, 16, 33, 5, 16), (3000, 300, 7, 10, 3),
-                                                 (100000, 256, 200, 10, 32), (2000, 8, 5, 32, 100)])
-def test_search_matches_restatement(law, n, nlist, nq, k, nprobe, gpu_vsb, oracle):
+                                                 (100000, 256, 200, 10, 32), (2000, 8, 5, 32, 100), (30000, 40, 700, 16, 5),
+                                                 (9000, 700, 65, 1, 9)])
+def test_search_matches_restatement(scan, law, n, nlist, nq, k, nprobe, gpu_vsb, oracle, monkeypatch):
+    """Both fine-scan kernels (K6 query-major, K8 list-major) against the CPU restatement: same probe sets, bit-identical
+    scores, canonical ids, counts and total candidates."""
+    monkeypatch.setenv("VSB_IVF_LM", "1" if scan == "list_major" else "0")
     vsb = gpu_vsb
     base, cent, order, offsets = make_index(vsb, oracle, n, nlist, law=law)
     qry = vsb.synth.make(law, 99, nq)

@@ -93,11 +93,19 @@ if "ivf" in what:
         e2e = time.perf_counter() - t0
         ms = float(np.median(ts[2:]))
         gb = total * 512 / 1e9
-        print(json.dumps({"path": "ivf nlist=1024 nprobe=%d top-10, 10K queries (ivf_scan_kernel)" % nprobe, "kernel_ms": ms,
+        lm = os.environ.get("VSB_IVF_LM", "1") != "0"   # batches >= 256 queries take the list-major kernel (K8) by default
+        kern = "ivf_lm_kernel, list-major" if lm else "ivf_scan_kernel, query-major"
+        fp32_peak = 148 * 128 * 2 * peaks.get("sm_max_mhz", 1965.0) * 1e6 / 1e12   # FFMA lanes x 2 flop x clock
+        flops = total * 256.0
+        print(json.dumps({"path": "ivf nlist=1024 nprobe=%d top-10, 10K queries (%s)" % (nprobe, kern), "kernel_ms": ms,
                           "search_ms_all_kernels": float(np.median(tot[2:])), "qps_device": NQ / (np.median(tot[2:]) * 1e-3),
                           "qps_e2e_host_buffers": NQ / e2e, "rows_scanned": total,
                           "roofline": {"bound": "hbm", "achieved": gb / (ms * 1e-3), "peak": HBM, "unit": "GB/s",
-                                       "frac": gb / (ms * 1e-3) / HBM, "algorithmic_bytes": total * 512}}))
+                                       "frac": gb / (ms * 1e-3) / HBM, "algorithmic_bytes": total * 512,
+                                       "note": "algorithmic bytes = probed rows x 512 B per query (SURVEY.md 8d); the "
+                                               "list-major kernel reads a list once per 32 queries, hence frac > 1"},
+                          "roofline_fp32": {"bound": "fp32 FFMA", "achieved": flops / (ms * 1e-3) / 1e12, "peak": fp32_peak,
+                                            "unit": "TFLOP/s", "frac": flops / (ms * 1e-3) / 1e12 / fp32_peak}}))
     idx.close()
 
 if "int8" in what:
