@@ -23,13 +23,14 @@ if has bench; then
 fi
 if has paths; then
   timeout 900 python tools/bench_paths.py batch1 ivf int8 > $OUT/${TAG}_paths.jsonl 2> $OUT/${TAG}_paths.err; echo "paths rc=$?"
+  VSB_IVF_LM=0 timeout 600 python tools/bench_paths.py ivf > $OUT/${TAG}_paths_ivf_querymajor.jsonl 2>> $OUT/${TAG}_paths.err; echo "paths (K6) rc=$?"
   cat $OUT/${TAG}_paths.jsonl
 fi
 NCU_L="ncu --metrics gpu__time_duration.sum --clock-control none --csv"
 if has launches; then
   timeout 600 $NCU_L -c 400 --log-file $OUT/${TAG}_launches_bench.csv python bench.py --steps 3 --warmup 3 --no-cpu > $OUT/${TAG}_ncu_bench.log 2>&1
   echo "ncu launches bench rc=$?"
-  timeout 900 $NCU_L -c 600 --log-file $OUT/${TAG}_launches_paths.csv python tools/bench_paths.py batch1 ivf int8 > $OUT/${TAG}_ncu_paths.log 2>&1
+  timeout 900 $NCU_L -c 3000 --log-file $OUT/${TAG}_launches_paths.csv python tools/bench_paths.py ivf int8 > $OUT/${TAG}_ncu_paths.log 2>&1
   echo "ncu launches paths rc=$?"
 fi
 NCU_F="ncu --set full --clock-control none --import-source on"
@@ -41,10 +42,12 @@ if has full; then
   echo "ncu full 3x rc=$?"
   timeout 600 $NCU_F -k regex:exact_stream_kernel -s 4 -c 1 -f -o $OUT/${TAG}_full_exact_stream python tools/bench_paths.py batch1 > $OUT/${TAG}_ncu_full_stream.log 2>&1
   echo "ncu full stream rc=$?"
-  timeout 900 $NCU_F -k regex:ivf_scan_kernel -s 3 -c 1 -f -o $OUT/${TAG}_full_ivf_scan_np8 python tools/bench_paths.py ivf > $OUT/${TAG}_ncu_full_ivf8.log 2>&1
-  echo "ncu full ivf np8 rc=$?"
-  timeout 900 $NCU_F -k regex:ivf_scan_kernel -s 13 -c 1 -f -o $OUT/${TAG}_full_ivf_scan_np32 python tools/bench_paths.py ivf > $OUT/${TAG}_ncu_full_ivf32.log 2>&1
-  echo "ncu full ivf np32 rc=$?"
+  VSB_IVF_LM=0 timeout 900 $NCU_F -k regex:ivf_scan_kernel -s 3 -c 1 -f -o $OUT/${TAG}_full_ivf_scan_np8 python tools/bench_paths.py ivf > $OUT/${TAG}_ncu_full_ivf8.log 2>&1
+  echo "ncu full ivf K6 np8 rc=$?"
+  VSB_IVF_LM=0 timeout 900 $NCU_F -k regex:ivf_scan_kernel -s 13 -c 1 -f -o $OUT/${TAG}_full_ivf_scan_np32 python tools/bench_paths.py ivf > $OUT/${TAG}_ncu_full_ivf32.log 2>&1
+  echo "ncu full ivf K6 np32 rc=$?"
+  timeout 900 $NCU_F -k regex:ivf_lm_kernel -s 13 -c 1 -f -o $OUT/${TAG}_full_ivf_lm_np32 python tools/bench_paths.py ivf > $OUT/${TAG}_ncu_full_ivflm32.log 2>&1
+  echo "ncu full ivf K8 np32 rc=$?"
   timeout 900 $NCU_F -k regex:int8_tc_kernel -s 3 -c 1 -f -o $OUT/${TAG}_full_int8_b32 python tools/bench_paths.py int8 > $OUT/${TAG}_ncu_full_int8_32.log 2>&1
   echo "ncu full int8 b32 rc=$?"
   timeout 900 $NCU_F -k regex:int8_tc_kernel -s 23 -c 1 -f -o $OUT/${TAG}_full_int8_b1024 python tools/bench_paths.py int8 > $OUT/${TAG}_ncu_full_int8_1024.log 2>&1
