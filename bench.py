@@ -343,7 +343,7 @@ def main():
                     "peak_note": f"TF32 dense = MEASURED_PEAKS bf16 burst / 2 ({pk['src']})"}
         if world == 1 and nq == N_QUERY:
             # DRAM bytes of one launch of this kernel from the committed `ncu --set full` capture of the same command
-            prof = {vsb.PREC_F16_CERT: "r1e_ncu_full_exact_tc_f16.txt", vsb.PREC_3XTF32: "r1e_ncu_full_exact_tc_3xtf32.txt"}.get(prec_used)
+            prof = {vsb.PREC_F16_CERT: "r1f_ncu_full_exact_tc_f16.txt", vsb.PREC_3XTF32: "r1f_ncu_full_exact_tc_3xtf32.txt"}.get(prec_used)
             roof["traffic"] = ncu_dram_bytes(os.path.join(ROOT, "profiles", prof)) if prof else None
             roof["traffic_unit"] = "bytes/launch (dram__bytes_read.sum + dram__bytes_write.sum, profiles/%s)" % prof if prof else None
         roof["frac"] = roof["achieved"] / roof["peak"]

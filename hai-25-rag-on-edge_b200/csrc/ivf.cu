@@ -26,7 +26,7 @@ namespace vsb {
 // ------------------------------------------------------------------------------------------------
 // coarse scores
 // ------------------------------------------------------------------------------------------------
-constexpr int CO_QT = 8;     // queries per block
+constexpr int CO_QT = 16;    // queries per block (each block re-reads its 128 centroids: fewer, fatter blocks)
 constexpr int CO_CT = 128;   // centroids per block (one per thread)
 
 __global__ void __launch_bounds__(CO_CT) ivf_coarse_kernel(const float* __restrict__ q, int64_t nq,
