@@ -29,6 +29,7 @@ struct vs_ivf {
     float* d_vectors = nullptr;    // [n x 128] list-contiguous
     int32_t* d_offsets = nullptr;  // [nlist+1]
     int32_t* d_idmap = nullptr;    // [n] list position -> original id
+    int32_t* d_order = nullptr;    // [nlist] lists by descending length (work order of the list-major scan)
     float* d_centroids = nullptr;  // [nlist x 128]
     CUtensorMap tmV;
     cudaStream_t stream = nullptr;
@@ -45,7 +46,7 @@ static int ivf_free(vs_ivf* h) {
     if (!h) return VS_OK;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    for (void* p : {(void*)h->d_vectors, (void*)h->d_offsets, (void*)h->d_idmap, (void*)h->d_centroids})
+    for (void* p : {(void*)h->d_vectors, (void*)h->d_offsets, (void*)h->d_idmap, (void*)h->d_centroids, (void*)h->d_order})
         if (p) cudaFree(p);
     for (DevBuf* b : {&h->q, &h->scores, &h->probes, &h->out_ids, &h->out_scores, &h->out_counts, &h->total, &h->lm_ws,
                       &h->part_key, &h->part_id})
@@ -92,6 +93,15 @@ static int ivf_create_impl(vs_ivf_t** out, const float* vectors, int64_t n, int 
         VSB_CUDA(cudaMalloc((void**)&h->d_offsets, sizeof(int32_t) * ((size_t)nlist + 1)));
         VSB_CUDA(cudaMalloc((void**)&h->d_idmap, sizeof(int32_t) * (size_t)n));
         VSB_CUDA(cudaMalloc((void**)&h->d_centroids, sizeof(float) * (size_t)nlist * dim));
+        VSB_CUDA(cudaMalloc((void**)&h->d_order, sizeof(int32_t) * (size_t)nlist));
+        {
+            std::vector<int32_t> order((size_t)nlist);
+            for (int c = 0; c < nlist; ++c) order[(size_t)c] = c;
+            std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
+                return offsets[a + 1] - offsets[a] > offsets[b + 1] - offsets[b];
+            });
+            VSB_CUDA(cudaMemcpy(h->d_order, order.data(), sizeof(int32_t) * (size_t)nlist, cudaMemcpyHostToDevice));
+        }
         VSB_CUDA(cudaMemcpyAsync(h->d_vectors, vectors, sizeof(float) * (size_t)n * dim, cudaMemcpyHostToDevice, h->stream));
         VSB_CUDA(cudaMemcpyAsync(h->d_offsets, offsets, sizeof(int32_t) * ((size_t)nlist + 1), cudaMemcpyHostToDevice, h->stream));
         VSB_CUDA(cudaMemcpyAsync(h->d_idmap, id_map, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
@@ -136,7 +146,7 @@ static int ivf_search_core(vs_ivf* h, const float* q_dev, int64_t nq, int k, int
         VSB_TRY(h->lm_ws.reserve(sizeof(int32_t) * ivf_lm_workspace_ints(nq, nprobe, h->nlist)));
         VSB_TRY(h->part_key.reserve(sizeof(float) * (size_t)nprobe * nq * ktop));
         VSB_TRY(h->part_id.reserve(sizeof(int32_t) * (size_t)nprobe * nq * ktop));
-        VSB_TRY(launch_ivf_listmajor(q_dev, h->d_vectors, h->d_offsets, h->d_idmap, h->nlist, h->probes.as<int32_t>(), nq, nprobe,
+        VSB_TRY(launch_ivf_listmajor(q_dev, h->d_vectors, h->d_offsets, h->d_idmap, h->nlist, h->d_order, h->probes.as<int32_t>(), nq, nprobe,
                                      k, h->lm_ws.as<int32_t>(), h->part_key.as<float>(), h->part_id.as<int32_t>(), out_counts,
                                      h->total.as<unsigned long long>(), h->num_sms, st));
         if (h->profile) {

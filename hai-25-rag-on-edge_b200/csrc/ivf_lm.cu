@@ -41,7 +41,9 @@ __global__ void lm_count_kernel(const int32_t* __restrict__ probes, int64_t n_pa
 }
 
 // one block: exclusive scan of the pair counts (pair_start), of the item counts (item_start) and the item table
+// `order`: the lists by descending length — the items of long lists come first in the work queue (no long tail)
 __global__ void __launch_bounds__(1024) lm_scan_kernel(const int32_t* __restrict__ list_cnt, int nlist,
+                                                       const int32_t* __restrict__ order,
                                                        const int32_t* __restrict__ offsets, int32_t* __restrict__ pair_start,
                                                        int32_t* __restrict__ cursor, int4* __restrict__ items,
                                                        int32_t* __restrict__ n_items) {
@@ -50,7 +52,8 @@ __global__ void __launch_bounds__(1024) lm_scan_kernel(const int32_t* __restrict
     const int per = (nlist + 1023) / 1024;
     const int c0 = t * per, c1 = min(c0 + per, nlist);
     int np = 0, ni = 0;
-    for (int c = c0; c < c1; ++c) {
+    for (int i = c0; i < c1; ++i) {
+        const int c = order[i];
         np += list_cnt[c];
         ni += (list_cnt[c] + LM_QT - 1) / LM_QT;
     }
@@ -65,7 +68,8 @@ __global__ void __launch_bounds__(1024) lm_scan_kernel(const int32_t* __restrict
         __syncthreads();
     }
     int pp = s_pairs[t] - np, ii = s_items[t] - ni;
-    for (int c = c0; c < c1; ++c) {
+    for (int i = c0; i < c1; ++i) {
+        const int c = order[i];
         pair_start[c] = pp;
         cursor[c] = pp;
         const int cnt = list_cnt[c];
@@ -74,10 +78,7 @@ __global__ void __launch_bounds__(1024) lm_scan_kernel(const int32_t* __restrict
             items[ii++] = make_int4(pp + q0, min(LM_QT, cnt - q0), r0, rl);
         pp += cnt;
     }
-    if (t == 1023) {
-        pair_start[nlist] = s_pairs[1023];
-        *n_items = s_items[1023];
-    }
+    if (t == 1023) *n_items = s_items[1023];
 }
 
 __global__ void lm_fill_kernel(const int32_t* __restrict__ probes, int64_t n_pairs, int32_t* __restrict__ cursor,
@@ -329,7 +330,7 @@ size_t ivf_lm_workspace_ints(int64_t nq, int nprobe, int nlist) {
 
 // ws: ivf_lm_workspace_ints() ints; part_key / part_id: [nprobe][nq][round_up_ktop(k)]
 int launch_ivf_listmajor(const float* q, const float* vectors, const int32_t* offsets, const int32_t* id_map, int nlist,
-                         const int32_t* probes, int64_t nq, int nprobe, int k, int32_t* ws, float* part_key, int32_t* part_id,
+                         const int32_t* list_order, const int32_t* probes, int64_t nq, int nprobe, int k, int32_t* ws, float* part_key, int32_t* part_id,
                          int32_t* out_counts, unsigned long long* total, int num_sms, cudaStream_t st) {
     if (nq <= 0) return VS_OK;
     const int ktop = round_up_ktop(k);
@@ -350,7 +351,7 @@ int launch_ivf_listmajor(const float* q, const float* vectors, const int32_t* of
     VSB_CUDA(cudaMemsetAsync(ws, 0, sizeof(int32_t) * ((size_t)nlist + 2 * (size_t)nq + 2), st));
     const unsigned gb = (unsigned)std::min<int64_t>(ceil_div64(n_pairs, 256), 148 * 8);
     lm_count_kernel<<<gb, 256, 0, st>>>(probes, n_pairs, nprobe, offsets, list_cnt, q_cand);
-    lm_scan_kernel<<<1, 1024, 0, st>>>(list_cnt, nlist, offsets, pair_start, cursor, items, n_items);
+    lm_scan_kernel<<<1, 1024, 0, st>>>(list_cnt, nlist, list_order, offsets, pair_start, cursor, items, n_items);
     lm_fill_kernel<<<gb, 256, 0, st>>>(probes, n_pairs, cursor, pairs);
     LmParams p{q, vectors, offsets, id_map, pairs, items, n_items, next_item, gthr, part_key, part_id, nq, nprobe};
     const int grid = 2 * num_sms;  // two resident CTAs per SM

@@ -87,7 +87,7 @@ int launch_ivf_scan(const CUtensorMap& tmV, const float* q, const int32_t* probe
 int ivf_lm_set_attributes();
 size_t ivf_lm_workspace_ints(int64_t nq, int nprobe, int nlist);
 int launch_ivf_listmajor(const float* q, const float* vectors, const int32_t* offsets, const int32_t* id_map, int nlist,
-                         const int32_t* probes, int64_t nq, int nprobe, int k, int32_t* ws, float* part_key, int32_t* part_id,
+                         const int32_t* list_order /* lists by descending length */, const int32_t* probes, int64_t nq, int nprobe, int k, int32_t* ws, float* part_key, int32_t* part_id,
                          int32_t* out_counts, unsigned long long* total, int num_sms, cudaStream_t st);
 int ivf_set_attributes();
 int ivf_scan_rows_per_chunk();
