@@ -138,7 +138,10 @@ static int ivf_search_core(vs_ivf* h, const float* q_dev, int64_t nq, int k, int
     // large batches: group the (query, list) pairs by list and scan list-major (K8, FFMA-bound) instead of
     // query-major (K6, bound by streaming each probed list once per query).  VSB_IVF_LM=0/1 forces either path.
     const char* lm_env = getenv("VSB_IVF_LM");
-    const bool list_major = lm_env ? atoi(lm_env) != 0 : (nq >= 256 && round_up_ktop(k) != 0);
+    // measured (tools/ivf_crossover.py, 1M x 128, nlist 1024): K8 wins once a list is probed by ~6 queries on average
+    // (nprobe 8: from ~700 queries), and for nprobe >= 16 at any batch (K6 walks a query's lists one after the other)
+    const bool lm_auto = (int64_t)nq * nprobe >= 6 * (int64_t)h->nlist || (nprobe >= 16 && nq >= 8);
+    const bool list_major = lm_env ? atoi(lm_env) != 0 : (lm_auto && round_up_ktop(k) != 0);
     if (h->profile) VSB_CUDA(cudaEventRecord(h->ev0, st));
     if (list_major) {
         const int ktop = round_up_ktop(k);
