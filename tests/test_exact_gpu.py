@@ -264,3 +264,42 @@ def test_massive_ties_duplicated_rows(gpu_vsb, oracle):
         assert np.array_equal(d, od64) and np.array_equal(ids, oi64)
     finally:
         idx.close()
+
+
+def test_search_dev_begin_finish(gpu_vsb, oracle):
+    """vs_exact_search_dev_begin / _finish: same answer as the one-call form, the fallback of uncertified queries runs
+    in _finish (and reports the rows it rewrote), and a second search without _finish is refused."""
+    import torch
+
+    vsb = gpu_vsb
+    rng = np.random.default_rng(3)
+    base = vsb.synth.make("cont", 91, 30_000)
+    centre = base[7].copy()
+    base[2000:2200] = centre[None, :] + rng.uniform(-0.02, 0.02, (200, 128)).astype(np.float32)   # uncertifiable cluster
+    qry = vsb.synth.make("cont", 92, 500)
+    qry[:12] = centre[None, :] + rng.uniform(-0.05, 0.05, (12, 128)).astype(np.float32)
+    dev = torch.device("cuda:0")
+    q_dev = torch.from_numpy(qry).to(dev)
+    ids = torch.empty((500, 10), dtype=torch.int32, device=dev)
+    d = torch.empty((500, 10), dtype=torch.float32, device=dev)
+    st = torch.cuda.Stream()
+    idx = vsb.ExactIndex(base)
+    try:
+        want_ids, want_d = idx.search(qry, 10, vsb.PREC_F16_CERT)
+        nfb = idx.last_fallbacks()
+        assert nfb >= 12
+        idx.search_dev_begin(q_dev.data_ptr(), 500, 10, vsb.PREC_F16_CERT, ids.data_ptr(), d.data_ptr(), st.cuda_stream)
+        with pytest.raises(vsb.VsbError):   # exactly one _finish per _begin
+            idx.search_dev(q_dev.data_ptr(), 500, 10, vsb.PREC_F16_CERT, ids.data_ptr(), d.data_ptr(), st.cuda_stream)
+        assert idx.search_dev_finish() == nfb
+        st.synchronize()
+        assert np.array_equal(ids.cpu().numpy(), want_ids) and np.array_equal(d.cpu().numpy(), want_d)
+        assert idx.search_dev_finish() == 0   # nothing pending: a no-op
+        # precisions without certification: _begin does everything, _finish has nothing to do
+        idx.search_dev_begin(q_dev.data_ptr(), 500, 10, vsb.PREC_3XTF32, ids.data_ptr(), d.data_ptr(), st.cuda_stream)
+        assert idx.search_dev_finish() == 0
+        st.synchronize()
+        oi, od = oracle.exact_search(base, qry, 10, mode=1)
+        assert np.allclose(d.cpu().numpy()[12:], od[12:], rtol=RTOL, atol=0)
+    finally:
+        idx.close()
