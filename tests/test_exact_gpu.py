@@ -303,3 +303,47 @@ def test_search_dev_begin_finish(gpu_vsb, oracle):
         assert np.allclose(d.cpu().numpy()[12:], od[12:], rtol=RTOL, atol=0)
     finally:
         idx.close()
+
+
+@pytest.mark.parametrize("law", ["cont", "sift"])
+def test_full_size_certified_path_equals_3xtf32_and_is_repeatable(law, gpu_vsb):
+    """BASELINE configs[1] at full size (1M x 128, 10 000 queries, top-10) through the headline path — certified fp16
+    candidate pass (queues + list-keeper warps, bound sharing between all 148 CTAs over ~7 rounds of units) + fp32
+    refine — against the independent 3xTF32 kernel (register lists in the epilogue warps).  Both refine the returned
+    candidates with the same fp32 arithmetic, so equal ids give bit-equal distances; ids may differ only inside ties.
+    Repeating the search must give bit-identical results: the candidate SET does not depend on the order in which
+    the concurrent queues are drained (a lost or duplicated queue entry would show up here)."""
+    import torch
+
+    vsb = gpu_vsb
+    n, nq, k = 1_000_000, 10_000, 10
+    dev = torch.device("cuda:0")
+    base_d = torch.empty((n, 128), dtype=torch.float32, device=dev)
+    vsb.synth_fill_dev(base_d.data_ptr(), 0, n, 128, law, 9001)
+    torch.cuda.synchronize()
+    qry = vsb.synth.make(law, 9002, nq)
+    idx = vsb.ExactIndex(base_d.data_ptr(), n=n)
+    try:
+        ids3, d3 = idx.search(qry, k, vsb.PREC_3XTF32)
+        ids, d = idx.search(qry, k, vsb.PREC_F16_CERT)
+        fallbacks = idx.last_fallbacks()
+        assert (np.diff(d, axis=1) >= 0).all() and ids.min() >= 0 and ids.max() < n
+        assert all(len(set(r.tolist())) == k for r in ids[:: 97])
+        if law == "sift":   # integer data: every path is exact, ties are real and resolved by id
+            assert np.array_equal(d, d3)
+            same = ids == ids3
+            tie = np.zeros_like(same)
+            tie[:, 1:] |= d3[:, 1:] == d3[:, :-1]
+            tie[:, :-1] |= d3[:, 1:] == d3[:, :-1]
+            tie[:, -1] = True   # the k-th may tie with the excluded (k+1)-th
+            assert (same | tie).all()
+        else:
+            assert np.allclose(d, d3, rtol=RTOL, atol=0)
+            assert (ids == ids3).mean() > 0.9999
+            assert np.array_equal(d[ids == ids3], d3[ids == ids3])   # same candidate, same fp32 refine
+        assert fallbacks < nq // 100
+        for _ in range(8):   # repeatability under different queue interleavings
+            ids_r, d_r = idx.search(qry, k, vsb.PREC_F16_CERT)
+            assert np.array_equal(ids_r, ids) and np.array_equal(d_r, d)
+    finally:
+        idx.close()

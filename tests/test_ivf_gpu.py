@@ -148,3 +148,28 @@ def test_parity_mode_fixed_centroids_and_numpy_written_dir(tmp_path, gpu_vsb, or
     assert np.array_equal(np.load(os.path.join(d2, "cluster_offsets.npy")), offsets)
     with pytest.raises(vsb.VsbError):
         vsb.IvfIndex(str(tmp_path / "missing"))  # ctor throws on missing files, like IVFIndex.cpp:184-197
+
+
+def test_full_size_list_major_equals_query_major(tmp_path, gpu_vsb, monkeypatch):
+    """BASELINE configs[2] at full size (1M x 128, nlist 1024, 10 000 queries, nprobe 8 / 32, top-10): the list-major
+    kernel (K8: pairs grouped by list, cross-list bounds, 296 CTAs pulling work items) must return exactly what the
+    query-major kernel (K6) returns — same ids, bit-identical scores, same counts and total — and do so repeatably."""
+    vsb = gpu_vsb
+    n, nlist, nq, k = 1_000_000, 1024, 10_000, 10
+    base = vsb.synth.make("mix", 2025, n)
+    d_ = str(tmp_path / "idx")
+    os.makedirs(d_)
+    vsb.ivf_build(base, nlist, d_, max_iter=4, seed=42, reordered=True)
+    qry = vsb.synth.make("mix", 2026, nq)
+    idx = vsb.IvfIndex(d_)
+    try:
+        for nprobe in (8, 32):
+            monkeypatch.setenv("VSB_IVF_LM", "0")
+            want = idx.search_batch(qry, k, nprobe)
+            monkeypatch.setenv("VSB_IVF_LM", "1")
+            for _ in range(3):
+                got = idx.search_batch(qry, k, nprobe)
+                assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
+                assert np.array_equal(got[2], want[2]) and got[3] == want[3]
+    finally:
+        idx.close()
