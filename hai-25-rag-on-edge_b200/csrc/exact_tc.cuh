@@ -126,20 +126,6 @@ __device__ __forceinline__ float ldsv_f32(const void* p) { return __uint_as_floa
 __device__ __forceinline__ void stsv_u32(void* p, uint32_t x) {
     asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(x) : "memory");
 }
-__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
-    uint32_t v;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
-    return v;
-}
-__device__ __forceinline__ void sts32(uint32_t addr, uint32_t x) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(x) : "memory"); }
-__device__ __forceinline__ uint2 lds64(uint32_t addr) {
-    uint2 v;
-    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
-    return v;
-}
-__device__ __forceinline__ void sts64(uint32_t addr, uint32_t x, uint32_t y) {
-    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(x), "r"(y) : "memory");
-}
 __device__ __forceinline__ uint2 lds64_volatile(uint32_t addr) {
     uint2 v;
     asm volatile("ld.volatile.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
