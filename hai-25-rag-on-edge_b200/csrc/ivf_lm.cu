@@ -27,7 +27,7 @@ constexpr int LM_RT = 128;       // list rows per chunk (32 lanes x 4)
 constexpr int LM_THREADS = 256;
 constexpr int LM_V_BYTES = LM_RT * 512;   // one chunk of rows: 64 KB
 // one chunk buffer per CTA: two CTAs share an SM (16 warps), one CTA's load overlaps the other's arithmetic
-constexpr int LM_SMEM = LM_V_BYTES + LM_QT * 512 + LM_QT * LM_RT * 4 + LM_RT * 4 + LM_QT * 4 + 64;
+constexpr int LM_SMEM = LM_V_BYTES + LM_QT * 512 + LM_RT * 4 + LM_QT * 4 + 64;
 
 // ---- pair grouping -------------------------------------------------------------------------------------------------
 // per list: number of (query, probe) pairs; per query: candidates = sum of the probed lists' lengths
@@ -134,9 +134,9 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
 }
 
 // scores of 4 queries (shared-memory rows at qbase, +512 B each) x NJ*32 list rows (this lane's rows lane + 32*j at vbase,
-// 16-byte units XOR-swizzled with the lane) -> srow[u*128 + 32*j]; the reference's summation order per score
+// 16-byte units XOR-swizzled with the lane) -> out[u][j] (row lane + 32*j); the reference's summation order per score
 template <int NJ>
-__device__ __forceinline__ void lm_scores(uint32_t qbase, uint32_t vbase, int lane, float* srow) {
+__device__ __forceinline__ void lm_scores(uint32_t qbase, uint32_t vbase, int lane, float (&out)[4][4]) {
     float acc[4][NJ][4];
 #pragma unroll
     for (int u = 0; u < 4; ++u)
@@ -167,7 +167,7 @@ __device__ __forceinline__ void lm_scores(uint32_t qbase, uint32_t vbase, int la
     for (int u = 0; u < 4; ++u)
 #pragma unroll
         for (int j = 0; j < NJ; ++j)
-            srow[u * LM_RT + 32 * j] = __fadd_rn(__fadd_rn(acc[u][j][0], acc[u][j][1]), __fadd_rn(acc[u][j][2], acc[u][j][3]));
+            out[u][j] = __fadd_rn(__fadd_rn(acc[u][j][0], acc[u][j][1]), __fadd_rn(acc[u][j][2], acc[u][j][3]));
 }
 
 template <int KTOP>
@@ -176,10 +176,9 @@ __global__ void __launch_bounds__(LM_THREADS, 2) ivf_lm_kernel(const LmParams p)
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
     uint8_t* sV = smem;                                   // [128 rows][32 float4, slot c4 ^ (row & 31)]
     float* sQ = (float*)(smem + LM_V_BYTES);              // [32 queries][128]
-    float* sS = sQ + LM_QT * 128;                         // [32 queries][128 rows] scores of the current chunk
-    int32_t* sId = (int32_t*)(sS + LM_QT * LM_RT);        // [128] original ids of the chunk's rows
+    int32_t* sId = (int32_t*)(sQ + LM_QT * 128);          // [128] original ids of the chunk's rows
     int32_t* sPair = sId + LM_RT;                         // [32] pair index of each query slot, -1 = unused
-    int32_t* sItem = sPair + LM_QT;                       // [1]
+    int32_t* sItem = sPair + LM_QT;                       // [1] index of the next work item, [4..7] its record
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -187,14 +186,22 @@ __global__ void __launch_bounds__(LM_THREADS, 2) ivf_lm_kernel(const LmParams p)
     const uint32_t sV_u = smem_u32(sV), sQ_u = smem_u32(sQ);
     const float NINF = __int_as_float(0xff800000);
 
+    const int n_items = __ldg(p.n_items);
+    if (tid == 0) {
+        const int first = atomicAdd(p.next_item, 1);
+        sItem[0] = first;
+        if (first < n_items) *reinterpret_cast<int4*>(sItem + 4) = __ldg(p.items + first);
+    }
     for (;;) {
-        __syncthreads();  // the previous item's shared memory is no longer read
-        if (tid == 0) *sItem = atomicAdd(p.next_item, 1);
-        __syncthreads();
-        const int item = *sItem;
-        if (item >= __ldg(p.n_items)) break;
-        const int4 rec = __ldg(p.items + item);
+        __syncthreads();  // the previous item's shared memory is no longer read; the next item's record is in place
+        const int item = sItem[0];
+        if (item >= n_items) break;
+        const int4 rec = *reinterpret_cast<const int4*>(sItem + 4);
         const int pair0 = rec.x, nqt = rec.y, r_start = rec.z, r_len = rec.w;
+        __syncthreads();  // everyone holds the record: thread 0 may overwrite it at the end of this item
+        // claim the item after this one now: the atomic's round trip overlaps this item's loads and arithmetic
+        int nxt = 0;
+        if (tid == 0) nxt = atomicAdd(p.next_item, 1);
         const int n_chunks = (r_len + LM_RT - 1) / LM_RT;
 
         auto load_chunk = [&](int c) {  // rows [c*128, +128) of the list -> sV (swizzled), ids -> sId
@@ -244,14 +251,13 @@ __global__ void __launch_bounds__(LM_THREADS, 2) ivf_lm_kernel(const LmParams p)
             // ---- scores: queries 4*warp+u, rows lane + 32*j for the 32-row groups that exist in this chunk
             const uint32_t vbase = sV_u + (uint32_t)lane * 512u;
             const uint32_t qbase = sQ_u + (uint32_t)(4 * warp) * 512u;
-            float* srow = sS + (4 * warp) * LM_RT + lane;
+            float scv[4][4];  // scores stay in registers: lane = row within the 32-row group j, as the selection needs them
             switch ((min(LM_RT, r_len - c * LM_RT) + 31) >> 5) {
-                case 1: lm_scores<1>(qbase, vbase, lane, srow); break;
-                case 2: lm_scores<2>(qbase, vbase, lane, srow); break;
-                case 3: lm_scores<3>(qbase, vbase, lane, srow); break;
-                default: lm_scores<4>(qbase, vbase, lane, srow); break;
+                case 1: lm_scores<1>(qbase, vbase, lane, scv); break;
+                case 2: lm_scores<2>(qbase, vbase, lane, scv); break;
+                case 3: lm_scores<3>(qbase, vbase, lane, scv); break;
+                default: lm_scores<4>(qbase, vbase, lane, scv); break;
             }
-            __syncwarp();  // the 4 x 128 scores of this warp's queries were all written by this warp
             // ---- selection
             const int rows = min(LM_RT, r_len - c * LM_RT);
 #pragma unroll
@@ -259,9 +265,11 @@ __global__ void __launch_bounds__(LM_THREADS, 2) ivf_lm_kernel(const LmParams p)
                 if (4 * warp + u >= nqt) break;  // warp-uniform
                 float thr_s = __shfl_sync(0xffffffffu, ls[u], KTOP - 1);
                 int32_t thr_i = __shfl_sync(0xffffffffu, li[u], KTOP - 1);
-                for (int s0 = 0; s0 < rows; s0 += 32) {
-                    const int r = s0 + lane;
-                    const float sc = sS[(4 * warp + u) * LM_RT + r];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (32 * j >= rows) break;  // warp-uniform
+                    const int r = 32 * j + lane;
+                    const float sc = scv[u][j];
                     const int32_t id = sId[r];
                     // canonical order: larger score first, equal scores by smaller id; an empty k-th entry admits all
                     unsigned m = __ballot_sync(0xffffffffu, r < rows && sc >= gs[u] &&
@@ -295,6 +303,10 @@ __global__ void __launch_bounds__(LM_THREADS, 2) ivf_lm_kernel(const LmParams p)
             }
             }
             __syncthreads();  // everyone is done with sV / sId before the next load overwrites them
+        }
+        if (tid == 0) {
+            sItem[0] = nxt;
+            if (nxt < n_items) *reinterpret_cast<int4*>(sItem + 4) = __ldg(p.items + nxt);
         }
         // ---- one sorted list per (query, probe slot)
 #pragma unroll
