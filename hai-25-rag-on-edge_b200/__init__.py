@@ -194,13 +194,17 @@ class IvfIndex:
         except Exception:
             pass
 
-    def search_batch(self, queries, k: int, nprobe: int):
-        """-> (ids [nq,k] int32 (-1 padded), scores [nq,k] f32 descending, counts [nq], total candidates)."""
+    def search_batch(self, queries, k: int, nprobe: int, out=None):
+        """-> (ids [nq,k] int32 (-1 padded), scores [nq,k] f32 descending, counts [nq], total candidates).
+        `out` = (ids, scores, counts) arrays to fill, e.g. views of pinned host memory (vs_host_alloc)."""
         q = np.ascontiguousarray(queries, dtype=np.float32)
         nq = q.shape[0]
-        ids = np.empty((nq, k), dtype=np.int32)
-        sc = np.empty((nq, k), dtype=np.float32)
-        cnt = np.empty(nq, dtype=np.int32)
+        if out is not None:
+            ids, sc, cnt = out
+        else:
+            ids = np.empty((nq, k), dtype=np.int32)
+            sc = np.empty((nq, k), dtype=np.float32)
+            cnt = np.empty(nq, dtype=np.int32)
         total = C.c_uint64(0)
         _check(lib().vs_ivf_search(self._h, _ptr(q), C.c_int64(nq), C.c_int(k), C.c_int(nprobe), _ptr(ids), _ptr(sc),
                                    _ptr(cnt), C.byref(total)))
