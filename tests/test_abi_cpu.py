@@ -5,6 +5,7 @@ import os
 import re
 
 import numpy as np
+import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -50,3 +51,37 @@ def test_product_does_not_reference_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp")) or f == "Makefile":
                 txt = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "oracle" not in txt.lower().replace("no cpu fallback", ""), f"{f} mentions the oracle"
+
+
+def test_header_is_plain_c_and_cxx(tmp_path):
+    """include/vsb200.h is the drop-in boundary: it must compile on its own as C99 and as C++17 (no torch / CUDA types)."""
+    import subprocess
+
+    inc = os.path.join(ROOT, "include")
+    c = tmp_path / "t.c"
+    c.write_text('#include "vsb200.h"\nint main(void) { vs_exact_t* h = 0; (void)h; return VS_OK; }\n')
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", inc, "-c", str(c), "-o", str(tmp_path / "t_c.o")],
+                   check=True)
+    cc = tmp_path / "t.cpp"
+    cc.write_text('#include "vsb200.h"\nint main() { vs_ivf_t* h = nullptr; (void)h; return VS_OK; }\n')
+    subprocess.run(["g++", "-std=c++17", "-Wall", "-Werror", "-I", inc, "-c", str(cc), "-o", str(tmp_path / "t_cc.o")],
+                   check=True)
+
+
+def test_host_programs_fail_loudly_without_a_gpu(tmp_path, vsb):
+    """The cpu_baseline-compatible executable has no CPU fallback: on a machine without a CUDA device it must exit
+    non-zero with a message instead of computing anything (skipped where a device is visible)."""
+    import subprocess
+
+    exe = os.path.join(ROOT, "hai-25-rag-on-edge_b200", "bin", "cpu_baseline")
+    if not os.path.exists(exe):
+        pytest.skip("host programs not built")
+    if vsb.device_count() > 0:
+        pytest.skip("a CUDA device is visible")
+    base, qry = tmp_path / "b.fvecs", tmp_path / "q.fvecs"
+    vsb.synth.write_fvecs(str(base), vsb.synth.make("sift", 1, 64))
+    vsb.synth.write_fvecs(str(qry), vsb.synth.make("sift", 2, 4))
+    r = subprocess.run([exe, str(base), str(qry), "5", str(tmp_path / "out.txt")], capture_output=True, text=True)
+    assert r.returncode != 0
+    assert "CUDA" in (r.stderr + r.stdout) or "device" in (r.stderr + r.stdout).lower()
+    assert not os.path.exists(tmp_path / "out.txt") or os.path.getsize(tmp_path / "out.txt") == 0

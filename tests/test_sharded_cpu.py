@@ -174,3 +174,47 @@ def test_two_rank_gloo_ivf_lists_sharded_equals_single_index(tmp_path):
     for r in range(world):
         g = np.load(tmp_path / f"ivf{r}.npz")
         assert np.array_equal(g["ids"], wi) and np.array_equal(g["sc"], ws) and int(g["total"][0]) == wt
+
+
+def _int8_worker(rank, world, port, n, nq, k, w_scale, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import vsb200_loader
+    from oracle import oracle
+
+    vsb = vsb200_loader.load()
+    from vsb200 import sharded
+
+    base = vsb.synth.make("sift", 808, n)
+    qry = vsb.synth.make("sift", 809, nq)
+    r0, r1 = sharded.shard_range(n, rank, world)
+    m = oracle.int8_multiplier(vsb.QNN_INPUT_SCALE, w_scale, vsb.QNN_OUTPUT_SCALE)
+    ids, sc = oracle.int8_search(oracle.quantize_u8(base[r0:r1], w_scale), oracle.quantize_u8(qry, vsb.QNN_INPUT_SCALE), k, m, mode=1)
+    ids = ids + r0
+    ids_all, sc_all = sharded.allgather_topk(torch.from_numpy(ids), torch.from_numpy(sc.astype(np.float32)))
+    mi, ms = _merge_host_desc(ids_all.numpy(), sc_all.numpy(), k)
+    np.savez(os.path.join(out_dir, f"i8{rank}.npz"), ids=mi, sc=ms.astype(np.uint8))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_two_rank_gloo_int8_rows_sharded_equals_single_index(tmp_path):
+    """INT8 row sharding: one weight scale for all shards, u8 scores merged largest-first with ids ascending inside
+    the (massive) score ties — the merged answer equals the unsharded CPU twin's."""
+    sys.path.insert(0, ROOT)
+    from oracle import oracle
+    import vsb200_loader
+
+    vsb = vsb200_loader.load()
+    n, nq, k, world = 7001, 23, 10, 2
+    base = vsb.synth.make("sift", 808, n)
+    qry = vsb.synth.make("sift", 809, nq)
+    w_scale = float(np.float32(base.max()) / np.float32(255.0))
+    mp.spawn(_int8_worker, args=(world, _free_port(), n, nq, k, w_scale, str(tmp_path)), nprocs=world, join=True)
+    m = oracle.int8_multiplier(vsb.QNN_INPUT_SCALE, w_scale, vsb.QNN_OUTPUT_SCALE)
+    wi, ws = oracle.int8_search(oracle.quantize_u8(base, w_scale), oracle.quantize_u8(qry, vsb.QNN_INPUT_SCALE), k, m, mode=1)
+    for r in range(world):
+        g = np.load(tmp_path / f"i8{r}.npz")
+        assert np.array_equal(g["ids"], wi) and np.array_equal(g["sc"], ws)
