@@ -173,3 +173,44 @@ def test_full_size_list_major_equals_query_major(tmp_path, gpu_vsb, monkeypatch)
                 assert np.array_equal(got[2], want[2]) and got[3] == want[3]
     finally:
         idx.close()
+
+
+def _hp2_cases():
+    from util import golden_cases
+
+    return golden_cases("hp2_")
+
+
+@pytest.mark.parametrize("scan", ["query_major", "list_major"])
+@pytest.mark.parametrize("path", _hp2_cases(), ids=lambda p: p.split("/")[-1][:-4])
+def test_gpu_matches_reference_ivfsearcher_golden(path, scan, tmp_path, gpu_vsb, oracle, monkeypatch):
+    """HP2 pin on the GPU: tests/golden/hp2_*.npz hold what the reference's OWN searcher (IVFSearcher.search,
+    qidk_ivf/prepare/benchmark_ivf.py:96-140, imported unmodified) returned on a scattered-layout directory.  The same
+    directory is written here by vs_ivf_build (parity mode: fixed centroids), must equal the one the reference consumed
+    array by array, and searching it must give the reference's scores bit for bit, its candidate counts, its ids outside
+    ties and its recall@k."""
+    from util import assert_ivf_matches_golden, load_golden_ivf
+
+    monkeypatch.setenv("VSB_IVF_LM", "1" if scan == "list_major" else "0")
+    vsb = gpu_vsb
+    g, base, qry, cent, labels, offsets, indices = load_golden_ivf(path, vsb.synth)
+    k, nlist = int(g["k"]), int(g["nlist"])
+    d = str(tmp_path / "idx")
+    info = vsb.ivf_build(base, nlist, d, max_iter=0, init_centroids=cent, reordered=False)
+    assert info["nlist"] == nlist and info["iters"] == 0
+    assert np.array_equal(np.load(os.path.join(d, "centroids.npy")), cent)
+    assert np.array_equal(np.load(os.path.join(d, "cluster_ids.npy")), labels)
+    assert np.array_equal(np.load(os.path.join(d, "cluster_offsets.npy")), offsets)
+    assert np.array_equal(np.load(os.path.join(d, "cluster_indices.npy")), indices)
+    assert np.array_equal(np.load(os.path.join(d, "vectors.npy")), base)
+    for how in ("dir", "arrays"):
+        idx = vsb.IvfIndex(d) if how == "dir" else vsb.IvfIndex(vectors=base[indices], offsets=offsets, id_map=indices,
+                                                                  centroids=cent)
+        try:
+            for nprobe in g["nprobes"]:
+                ids, sc, cnt, total = idx.search_batch(qry, k, int(nprobe))
+                rec = oracle.ivf_scores_at(base, qry, ids)
+                assert_ivf_matches_golden(g, int(nprobe), ids, sc, cnt, total, rec, g["gt"],
+                                          what=f"{path} {how} nprobe={nprobe} {scan}")
+        finally:
+            idx.close()

@@ -89,3 +89,26 @@ def test_ivf_restatement_selfconsistent(vsb, oracle):
     want = np.argsort(-ip, axis=1, kind="stable")[:, :10]
     assert np.array_equal(np.sort(full[0], 1), np.sort(want, 1))
     assert full[3] == 20 * 4000
+
+
+@pytest.mark.parametrize("path", golden_cases("hp2_"), ids=lambda p: p.split("/")[-1][:-4])
+def test_ivf_restatement_matches_reference_golden(path, vsb, oracle):
+    """HP2 pin: the C restatement of IVFIndex::searchBatch (oracle/vs_oracle.c) against what the reference's own
+    IVFSearcher (qidk_ivf/prepare/benchmark_ivf.py:53-140, run unmodified by tests/golden/gen_golden_ivf.py) returned
+    on the same scattered-layout index: scores bit-exact, candidate counts equal, ids equal outside ties, recall equal."""
+    from util import assert_ivf_matches_golden, load_golden_ivf
+
+    g, base, qry, cent, labels, offsets, indices = load_golden_ivf(path, vsb.synth)
+    k = int(g["k"])
+    # the directory the reference consumed was assigned by exact nearest centroid: the restatement agrees
+    olab, _ = oracle.kmeans_assign(base, cent)
+    assert np.array_equal(olab, labels)
+    coarse = oracle.ivf_coarse(qry, cent)
+    assert np.array_equal(coarse, (qry.astype(np.float64) @ cent.astype(np.float64).T).astype(np.float32))
+    for nprobe in g["nprobes"]:
+        for reordered, vec in ((False, base), (True, base[indices])):
+            for mode in (0, 1):
+                ids, sc, cnt, total = oracle.ivf_search(vec, offsets, indices, reordered, coarse, qry, k, int(nprobe), mode=mode)
+                rec = oracle.ivf_scores_at(base, qry, ids)
+                assert_ivf_matches_golden(g, int(nprobe), ids, sc, cnt, total, rec, g["gt"],
+                                          what=f"{path} nprobe={nprobe} reordered={reordered} mode={mode}")

@@ -52,3 +52,33 @@ def assert_topk_matches(ids, keys, ref_ids, ref_keys, recomputed, *, exact: bool
     # a mismatching id must not appear twice in a row
     for r in np.unique(np.argwhere(mism)[:, 0]):
         assert len(set(ids[r].tolist())) == k, f"{what}: duplicate ids in row {r}"
+
+
+def load_golden_ivf(path, synth):
+    """hp2_*.npz (tests/golden/gen_golden_ivf.py: the reference's IVFSearcher run on a scattered-layout directory)
+    -> (golden, base, queries, centroids, labels, offsets, cluster_indices)."""
+    g = np.load(path)
+    base = synth.make("mix", int(g["base_seed"]), int(g["n"]))
+    qry = synth.make("mix", int(g["query_seed"]), int(g["nq"]))
+    cent = g["centroids"].astype(np.float32)
+    labels = g["labels"].astype(np.int32)
+    nlist = int(g["nlist"])
+    # create_ivf_model.py:112-119: list i = np.where(cluster_ids == i) -> ascending original ids inside a list
+    indices = np.argsort(labels, kind="stable").astype(np.int32)
+    offsets = np.concatenate([[0], np.cumsum(np.bincount(labels, minlength=nlist))]).astype(np.int32)
+    return g, base, qry, cent, labels, offsets, indices
+
+
+def assert_ivf_matches_golden(g, nprobe, ids, scores, counts, total, recomputed, gt, what=""):
+    """Reference (benchmark_ivf.IVFSearcher.search) vs ours on integer data: scores bit-exact position by position,
+    candidate counts and their sum equal, ids equal outside score ties, recall@k equal per query set-wise whenever the
+    k-th and (k+1)-th scores are not tied (ids of a tie group are interchangeable in the reference's argpartition)."""
+    k = int(g["k"])
+    rids, rsc, rcand = g[f"ids_np{nprobe}"], g[f"scores_np{nprobe}"], g[f"cand_np{nprobe}"]
+    assert total == int(rcand.sum()), what
+    assert np.array_equal(counts, np.minimum(rcand, k)), what
+    assert_topk_matches(ids, scores, rids, rsc, recomputed, exact=True, what=what)
+    rec = np.array([len(set(ids[i][ids[i] >= 0].tolist()) & set(gt[i][:k].tolist())) / k for i in range(ids.shape[0])])
+    same_set = np.array([set(ids[i].tolist()) == set(rids[i].tolist()) for i in range(ids.shape[0])])
+    assert np.array_equal(rec[same_set], g[f"recall_np{nprobe}"][same_set]), what
+    assert same_set.mean() > 0.9, what
