@@ -3,10 +3,14 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-One "step" = one pass of the hot path over one batch: 10 000 queries against the whole base, top-10,
-fp32-faithful (3xTF32 tcgen05 kernel + exact fp32 refine of the candidates).
-N > 1 (torchrun, one rank per GPU): base rows sharded across ranks, queries replicated, per-rank local top-k,
-one NCCL all-gather of [nq x k] (ids, dists) + merge kernel — strong scaling on the fixed 1M x 128 problem.
+One "step" = one pass of the hot path over one batch: 10 000 queries against the whole base, top-10, fp32-faithful.
+Default precision AUTO = certified fp16 tcgen05 candidate pass + exact fp32 refine of the candidates + per-query
+certificate (uncertified queries are redone in 3xTF32); the pure 3xTF32 tcgen05 path is timed in the same run and
+printed beside it (`fp32_3xtf32_path`).
+N > 1 (torchrun, one rank per GPU): base rows sharded across ranks, queries replicated (every rank uploads 1/N of
+them, one all-gather replicates the slices over NVLink), per-rank local top-k written in place into the rank's slot
+of the gathered buffer, ONE in-place NCCL all-gather of the exchange blocks (ids | dists | uncertified count) + merge
+kernel — strong scaling on the fixed 1M x 128 problem.
 
 Prints ONE JSON line (rank 0):
   value        whole-job QPS, queries already resident in HBM when the timed region starts
@@ -236,19 +240,31 @@ def main():
     searcher = vsb_sharded.ShardedExact(vsb, index, nq, k, dev)
 
     def device_step(q_ptr):
-        # local fused search; for N > 1: NCCL all-gather of the [nq x k] candidates + merge kernel
-        return searcher.search(q_ptr, nq, prec, sptr)
+        # local fused search; for N > 1: ONE in-place NCCL all-gather of the exchange blocks + merge kernel; finish()
+        # waits for the 4-byte total of the uncertified counts (0 on this data: nothing to redo)
+        out = searcher.enqueue(q_ptr, nq, prec, sptr)
+        searcher.finish()
+        return out
 
-    q_stage = torch.empty_like(q_dev)
+    # N > 1: every rank uploads ITS 1/N of the queries (they cross PCIe once in total) and one all-gather replicates
+    # the slices over NVLink
+    q_rows = (nq + world - 1) // world
+    q_stage = torch.empty((q_rows * world, DIM), dtype=torch.float32, device=dev)
+    q_r0, q_r1 = min(nq, q_rows * rank), min(nq, q_rows * (rank + 1))
 
     def e2e_step():
         if world == 1:
             # the reference-facing C-ABI call with HOST buffers: H2D + search + D2H inside
             index.search(q_host.numpy(), k, prec, out_ids=ids_h.numpy(), out_dists=d_h.numpy())
         else:
-            q_stage.copy_(q_host, non_blocking=True)
-            oi, od = device_step(q_stage.data_ptr())
+            if q_r1 > q_r0:
+                q_stage[q_r0:q_r1].copy_(q_host[q_r0:q_r1], non_blocking=True)
+            dist.all_gather_into_tensor(q_stage, q_stage[q_rows * rank:q_rows * (rank + 1)])   # in place
+            oi, od = searcher.enqueue(q_stage.data_ptr(), nq, prec, sptr)
             if rank == 0:
+                ids_h.copy_(oi, non_blocking=True)
+                d_h.copy_(od, non_blocking=True)
+            if searcher.finish() and rank == 0:   # rare: something was redone and merged again
                 ids_h.copy_(oi, non_blocking=True)
                 d_h.copy_(od, non_blocking=True)
             stream.synchronize()
@@ -315,7 +331,8 @@ def main():
     alt = None
     if prec == vsb.PREC_AUTO:
         def alt_fn():
-            searcher.search(q_dev.data_ptr(), nq, vsb.PREC_3XTF32, sptr)
+            searcher.enqueue(q_dev.data_ptr(), nq, vsb.PREC_3XTF32, sptr)
+            searcher.finish()
         for _ in range(3):
             alt_fn()
         barrier()
@@ -370,12 +387,12 @@ def main():
                                          "recomputed in fp32 and the top-k is certified complete per query (else redone in "
                                          "3xTF32): results equal the fp32 path's (tests/test_exact_gpu.py)" if prec_used == vsb.PREC_F16_CERT else "",
                        "base_rows_per_gpu": n_local,
-                       "parallelism": f"base rows sharded x{world}, queries replicated, all-gather + merge" if world > 1 else "single GPU",
+                       "parallelism": f"base rows sharded x{world}, queries replicated, one in-place all-gather of (ids|dists|count) blocks + merge" if world > 1 else "single GPU",
                        "cache": "L2 flushed (256 MB write) between timed steps; operands (0.5-1 GB) exceed the 126 MB L2"},
             "e2e": {"value": nq / (ms_e2e * 1e-3), "unit": "queries/s", "ms_per_step": ms_e2e,
-                    "h2d_bytes_per_step": int(q_host.numel() * 4) * world,
+                    "h2d_bytes_per_step": int(q_host.numel() * 4),
                     "d2h_bytes_per_step": int(nq * k * 8),
-                    "api": "vs_exact_search_f32 (host buffers)" if world == 1 else "H2D + vs_exact_search_dev + NCCL all-gather + vs_merge_topk_dev + D2H"},
+                    "api": "vs_exact_search_f32 (host buffers)" if world == 1 else "H2D of 1/N of the queries per rank + all-gather of the slices + vs_exact_group_begin + ONE in-place NCCL all-gather of the exchange blocks + vs_exact_group_merge + D2H + vs_exact_group_finish"},
             "gpu_launches": int(launches + (1 if world > 1 else 0)) * args.steps,
             "roofline": roof,
             "clocks": clocks,

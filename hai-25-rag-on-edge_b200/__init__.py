@@ -46,6 +46,7 @@ def lib() -> C.CDLL:
         L = C.CDLL(LIB_PATH)
         L.vs_last_error.restype = C.c_char_p
         L.vs_exact_size.restype = C.c_int64
+        L.vs_topk_block_bytes.restype = C.c_size_t
         _lib = L
     return _lib
 
@@ -150,6 +151,100 @@ def merge_topk_dev(ids_ptr: int, keys_ptr: int, n_shards: int, nq: int, k: int, 
                    out_keys_ptr: int, stream: int = 0) -> None:
     _check(lib().vs_merge_topk_dev(_ptr(ids_ptr), _ptr(keys_ptr), C.c_int(n_shards), C.c_int64(nq), C.c_int(k),
                                    C.c_int(int(smallest)), _ptr(out_ids_ptr), _ptr(out_keys_ptr), C.c_void_p(stream)))
+
+
+def topk_block_bytes(nq: int, k: int) -> int:
+    """bytes of one shard's exchange block: ids [nq,k] i32 | keys [nq,k] f32 | 16-byte trailer (uncertified count)"""
+    return int(lib().vs_topk_block_bytes(C.c_int64(nq), C.c_int(k)))
+
+
+def merge_blocks_dev(blocks_ptr: int, n_shards: int, stride: int, nq: int, k: int, smallest: bool, out_ids_ptr: int,
+                     out_keys_ptr: int, total_ptr: int = 0, stream: int = 0) -> None:
+    _check(lib().vs_merge_blocks_dev(_ptr(blocks_ptr), C.c_int(n_shards), C.c_size_t(stride), C.c_int64(nq), C.c_int(k),
+                                     C.c_int(int(smallest)), _ptr(out_ids_ptr), _ptr(out_keys_ptr),
+                                     _ptr(total_ptr) if total_ptr else None, C.c_void_p(stream)))
+
+
+class ExactGroup:
+    """The exact-search shards of ONE device as one participant of the row-sharded search (vs_exact_group_*):
+    begin -> [the caller's exchange of the gathered buffer] -> merge -> finish."""
+
+    def __init__(self, shards, n_slots: int, first_slot: int):
+        self._h = C.c_void_p()
+        self._shards = list(shards)  # keep the ExactIndex objects alive: the group does not own them
+        arr = (C.c_void_p * len(self._shards))(*[s._h for s in self._shards])
+        _check(lib().vs_exact_group_create_from(C.byref(self._h), C.c_int(len(self._shards)), arr, C.c_int(n_slots),
+                                                C.c_int(first_slot)))
+
+    def close(self) -> None:
+        if self._h:
+            lib().vs_exact_group_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def begin(self, q_ptr: int, nq: int, k: int, precision: int, gathered_ptr: int, stream: int = 0) -> None:
+        _check(lib().vs_exact_group_begin(self._h, _ptr(q_ptr), C.c_int64(nq), C.c_int(k), C.c_int(precision),
+                                          _ptr(gathered_ptr), C.c_void_p(stream)))
+
+    def merge(self, out_ids_ptr: int, out_dists_ptr: int) -> None:
+        _check(lib().vs_exact_group_merge(self._h, _ptr(out_ids_ptr), _ptr(out_dists_ptr)))
+
+    def finish(self) -> bool:
+        """-> True when some shard redid uncertified queries: exchange, merge and finish again."""
+        need = C.c_int(0)
+        _check(lib().vs_exact_group_finish(self._h, C.byref(need)))
+        return bool(need.value)
+
+
+class ExactMultiGpu:
+    """Single-process multi-GPU exact search (vs_exact_mgpu_*): host buffers in, host buffers out."""
+
+    def __init__(self, base: np.ndarray, n_gpus: int = 0, shards_per_gpu: int = 1):
+        self._h = C.c_void_p()
+        base = np.ascontiguousarray(base, dtype=np.float32)
+        _check(lib().vs_exact_mgpu_create(C.byref(self._h), _ptr(base), C.c_int64(base.shape[0]), C.c_int(base.shape[1]),
+                                          C.c_int(n_gpus), C.c_int(shards_per_gpu)))
+        self.n_gpus = int(lib().vs_exact_mgpu_num_gpus(self._h))
+        self.n_shards = int(lib().vs_exact_mgpu_num_shards(self._h))
+
+    def close(self) -> None:
+        if self._h:
+            lib().vs_exact_mgpu_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def search(self, queries: np.ndarray, k: int, precision: int = PREC_AUTO, out_ids=None, out_dists=None):
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        nq = q.shape[0]
+        ids = out_ids if out_ids is not None else np.empty((nq, k), dtype=np.int32)
+        d = out_dists if out_dists is not None else np.empty((nq, k), dtype=np.float32)
+        _check(lib().vs_exact_mgpu_search_f32(self._h, _ptr(q), C.c_int64(nq), C.c_int(k), C.c_int(precision), _ptr(ids),
+                                              _ptr(d)))
+        return ids, d
+
+    def last_stats(self):
+        """-> (exchanges of the last search, whether any shard redid uncertified queries)"""
+        a, b = C.c_int(0), C.c_int(0)
+        _check(lib().vs_exact_mgpu_last_stats(self._h, C.byref(a), C.byref(b)))
+        return a.value, bool(b.value)
+
+    def set_profile(self, enable: bool = True) -> None:
+        _check(lib().vs_exact_mgpu_set_profile(self._h, C.c_int(int(enable))))
+
+    def last_kernel_ms(self) -> float:
+        ms = C.c_float(0)
+        _check(lib().vs_exact_mgpu_last_kernel_ms(self._h, C.byref(ms)))
+        return float(ms.value)
 
 
 def synth_fill_dev(out_ptr: int, row0: int, nrows: int, dim: int, law: str, seed: int, centre_seed: int = 7,

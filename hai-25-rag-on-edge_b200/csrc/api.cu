@@ -10,6 +10,7 @@
 #include <string>
 #include <vector>
 
+#include "exact_handle.cuh"
 #include "kernels.cuh"
 #include "vsb_common.cuh"
 
@@ -61,47 +62,7 @@ int make_tmap_2d(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_t col
 
 using namespace vsb;
 
-struct vs_exact {
-    int device = 0;
-    int num_sms = 148;
-    int64_t n = 0;
-    int dim = 0;
-    int64_t id_base = 0;
-    bool owns_base = false;
-    const float* d_base = nullptr;  // [n x dim] fp32
-    float* d_hi = nullptr;          // TF32 split, built on first use (dim == 128 only); d_hi aliases d_base when the
-    float* d_lo = nullptr;          // base is TF32-exact
-    bool split_ready = false;
-    void* d_f16 = nullptr;          // [n x 128] fp16 copy scaled by s_b (candidate pass)
-    float s_b = 1.f;                // power-of-two scale of the fp16 copy
-    float bn_max = 0.f;             // max ||x||^2
-    float* d_norm = nullptr;        // [n_tiles*128] +inf padded
-    bool base_exact = false;
-    CUtensorMap tmB_hi, tmB_lo, tmB_f16;
-    cudaStream_t stream = nullptr;
-    // workspace (grow-only)
-    DevBuf q, qhi, qlo, qf16, qnorm, part_key, part_id, lbk, lbi, out_ids, out_keys, flag, gthr, qparams, unc_list, fb_q,
-        fb_ids, fb_keys;
-    int* h_flag = nullptr;  // pinned: [0] exactness flag, [1] uncertified count
-    int last_launches = 0;
-    int last_precision = 0;
-    int last_fallback = 0;
-    // optional CUDA-event timing of the dominant kernel (bench.py's roofline line)
-    bool profile = false;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    bool ev_valid = false;
-    // certified search split in two (vs_exact_search_dev_begin / _finish): what finish needs to redo uncertified queries
-    cudaEvent_t ev_cert = nullptr;
-    bool cert_pending = false;
-    const float* pend_q = nullptr;
-    int64_t pend_nq = 0;
-    int pend_k = 0;
-    int32_t* pend_ids = nullptr;
-    float* pend_dists = nullptr;
-    cudaStream_t pend_st = nullptr;
-};
-
-static int exact_free(vs_exact* h) {
+int exact_free(vs_exact* h) {
     if (!h) return VS_OK;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
@@ -183,7 +144,7 @@ static int exact_ensure_split(vs_exact* h, bool need_lo, cudaStream_t st) {
     return VS_OK;
 }
 
-static int exact_create_common(vs_exact_t** out, const float* base, bool on_device, int64_t n, int dim, int device,
+int exact_create_common(vs_exact_t** out, const float* base, bool on_device, int64_t n, int dim, int device,
                                int64_t id_base) {
     if (!out) return fail(VS_ERR_INVALID, "out handle is NULL");
     *out = nullptr;
@@ -240,18 +201,17 @@ static int exact_create_common(vs_exact_t** out, const float* base, bool on_devi
     return VS_OK;
 }
 
-static int exact_search_core(vs_exact* h, const float* q_dev, int64_t nq, int k, int precision, int32_t* out_ids,
-                             float* out_dists, cudaStream_t st, bool defer_certification = false);
-static int exact_certified_finish(vs_exact* h, int* n_redone);
 
 // Certified candidate pass: scaled fp16 tensor-core kernel keeps the 32 best keys per query (error bounded by
 // cert_a*sqrt(qn)+cert_b), the merge kernel recomputes those 32 distances in exact fp32, ranks them and certifies
 // the top k; the (rare) uncertified queries are redone on the 3xTF32 / FFMA path.  Synchronises `st` once (4-byte
 // count of uncertified queries).
 static int exact_search_certified(vs_exact* h, const float* q_dev, int64_t nq, int k, int32_t* out_ids, float* out_dists,
-                                  cudaStream_t st) {
+                                  cudaStream_t st, int32_t* unc_dev) {
     const int ktop = kMaxRegK;
     int* flag = h->flag.as<int>();
+    // count of uncertified queries: the handle's own word, or the caller's (trailer of an exchange block, already zeroed)
+    int32_t* unc = unc_dev ? unc_dev : flag + 1;
     VSB_TRY(h->qf16.reserve(2 * (size_t)nq * 128));
     VSB_TRY(h->qparams.reserve(sizeof(TcQueryParams)));
     VSB_TRY(h->unc_list.reserve(sizeof(int32_t) * (size_t)nq));
@@ -280,11 +240,11 @@ static int exact_search_certified(vs_exact* h, const float* q_dev, int64_t nq, i
     }
     VSB_TRY(launch_merge_lists(h->part_key.as<float>(), h->part_id.as<int32_t>(), n_lists, nq, ktop, ktop, k, h->id_base, 0, 0,
                                out_dists, out_ids, k, 0, nullptr, nullptr, h->d_base, h->d_norm, q_dev, h->qnorm.as<float>(), st,
-                               qp, flag + 1, h->unc_list.as<int32_t>()));
+                               qp, unc, h->unc_list.as<int32_t>()));
     h->last_launches = 5;
     h->last_precision = VS_PREC_F16_CERTIFIED;
     h->last_fallback = 0;
-    VSB_CUDA(cudaMemcpyAsync(h->h_flag + 1, flag + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+    VSB_CUDA(cudaMemcpyAsync(h->h_flag + 1, unc, sizeof(int), cudaMemcpyDeviceToHost, st));
     if (!h->ev_cert) VSB_CUDA(cudaEventCreateWithFlags(&h->ev_cert, cudaEventDisableTiming));
     VSB_CUDA(cudaEventRecord(h->ev_cert, st));
     h->cert_pending = true;
@@ -299,7 +259,7 @@ static int exact_search_certified(vs_exact* h, const float* q_dev, int64_t nq, i
 
 // Second half of the certified search: waits for the 4-byte count of uncertified queries (an event recorded right
 // after its copy: work enqueued later on the stream is not waited for) and redoes those queries on the fp32 path.
-static int exact_certified_finish(vs_exact* h, int* n_redone) {
+int exact_certified_finish(vs_exact* h, int* n_redone) {
     if (n_redone) *n_redone = 0;
     if (!h->cert_pending) return VS_OK;
     h->cert_pending = false;
@@ -334,9 +294,10 @@ static int exact_certified_finish(vs_exact* h, int* n_redone) {
 }
 
 // One group of <= 32 results per query: [pass]
-static int exact_search_core(vs_exact* h, const float* q_dev, int64_t nq, int k, int precision, int32_t* out_ids,
-                             float* out_dists, cudaStream_t st, bool defer_certification) {
+int exact_search_core(vs_exact* h, const float* q_dev, int64_t nq, int k, int precision, int32_t* out_ids,
+                      float* out_dists, cudaStream_t st, bool defer_certification, int32_t* unc_dev) {
     if (h->cert_pending) return fail(VS_ERR_INVALID, "vs_exact_search_dev_finish() of the previous search was not called");
+    if (h->broken) return fail(VS_ERR_INVALID, "the handle is unusable: vs_exact_refresh() failed");
     h->last_launches = 0;
     h->last_fallback = 0;
     if (nq == 0) return VS_OK;
@@ -358,7 +319,7 @@ static int exact_search_core(vs_exact* h, const float* q_dev, int64_t nq, int k,
 
     VSB_TRY(h->qnorm.reserve(sizeof(float) * (size_t)nq));
     if (prec == VS_PREC_F16_CERTIFIED) {
-        VSB_TRY(exact_search_certified(h, q_dev, nq, k, out_ids, out_dists, st));
+        VSB_TRY(exact_search_certified(h, q_dev, nq, k, out_ids, out_dists, st, unc_dev));
         return defer_certification ? VS_OK : exact_certified_finish(h, nullptr);
     }
     const int passes = (k + kMaxRegK - 1) / kMaxRegK;
@@ -497,7 +458,9 @@ int vs_exact_refresh(vs_exact_t* h) {
     h->d_hi = h->d_lo = h->d_norm = nullptr;
     h->d_f16 = nullptr;
     h->split_ready = false;
-    return exact_build(h);
+    const int rc = exact_build(h);
+    h->broken = rc != VS_OK;  // a failed rebuild leaves no usable buffers: every later search is refused
+    return rc;
 }
 int64_t vs_exact_size(const vs_exact_t* h) { return h ? h->n : 0; }
 int vs_exact_dim(const vs_exact_t* h) { return h ? h->dim : 0; }

@@ -224,6 +224,10 @@ int vs_ivf_open(vs_ivf_t** out, const char* index_dir, int device) {
     if (!(e = vsb_io::read_text(dir + "/ivf_config.json", json)).empty()) return fail(VS_ERR_IO, e);
     vsb_io::IvfConfig cfg;
     if (!(e = vsb_io::parse_ivf_config(json, cfg)).empty()) return fail(VS_ERR_IO, e);
+    // the values become int / int32 ids below: refuse what does not fit before any array is sized from them
+    if (cfg.n_vectors == 0 || cfg.n_vectors > 0x7fffffffull || cfg.n_clusters == 0 || cfg.n_clusters > 0x7fffffffull ||
+        cfg.dim == 0 || cfg.dim > 65536)
+        return fail(VS_ERR_IO, "ivf_config.json: n_vectors / n_clusters / dim out of range");
     std::vector<size_t> shape;
     std::vector<int32_t> offsets, idx;
     std::vector<float> vectors, centroids;

@@ -76,9 +76,14 @@ __global__ void __launch_bounds__(128) ivf_probe_kernel(const float* __restrict_
     const int64_t q = (int64_t)blockIdx.x * 4 + wib;
     if (q >= nq) return;
     float* sc = s_sc + (size_t)wib * nlist;
-    for (int c = lane; c < nlist; c += 32) sc[c] = scores[q * nlist + c];
-    __syncwarp();
     const float NINF = __int_as_float(0xff800000);
+    // NaN scores (a non-finite query or centroid; undefined in the reference's nth_element) rank last, like -inf: the
+    // consumed-entry marker below is NaN, so a NaN input must not reach the selection
+    for (int c = lane; c < nlist; c += 32) {
+        const float v = scores[q * nlist + c];
+        sc[c] = v == v ? v : NINF;
+    }
+    __syncwarp();
     for (int r = 0; r < nprobe; ++r) {
         float bv = NINF;
         int bc = 0x7fffffff;  // none yet
@@ -99,7 +104,7 @@ __global__ void __launch_bounds__(128) ivf_probe_kernel(const float* __restrict_
             }
         }
         if (lane == 0) {
-            probes[q * nprobe + r] = bc;
+            probes[q * nprobe + r] = bc;  // always a valid list: nprobe <= nlist unconsumed non-NaN entries exist
             sc[bc] = __int_as_float(0x7fc00000);  // NaN: never compares greater/equal again
         }
         __syncwarp();

@@ -259,6 +259,15 @@ int launch_scatter_results(const float* key, const int32_t* id, const int32_t* i
 // — and are re-sorted by (distance, id).  Reported distances are then fp32-faithful regardless of which
 // kernel generated the candidates.
 // ------------------------------------------------------------------------------------------------
+// Lists that live in per-shard exchange blocks (block = ids [nq x k] | keys [nq x k] | 16-byte trailer, see
+// vs_topk_block_bytes): list l starts list_stride 4-byte words after list l-1 (0 = densely packed [list][nq][len]);
+// trailer != nullptr: word 0 of every block's trailer (the shard's uncertified-query count) is summed into *total_out.
+struct BlockArgs {
+    size_t list_stride;
+    const int32_t* trailer;
+    int32_t* total_out;
+};
+
 struct RefineArgs {
     const float* base;   // [n x 128] fp32, or nullptr = no refine
     const float* bnorm;
@@ -302,19 +311,25 @@ __global__ void __launch_bounds__(128) merge_lists_kernel(const float* __restric
                                                           int neg_out, float* __restrict__ out_key,
                                                           int32_t* __restrict__ out_id, int out_stride, int out_off,
                                                           float* __restrict__ lb_key_out, int32_t* __restrict__ lb_id_out,
-                                                          RefineArgs rf) {
+                                                          RefineArgs rf, BlockArgs ba) {
     __shared__ float s_key[4][32];
     __shared__ int32_t s_id[4][32];
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
     const int64_t q = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
+    if (ba.trailer && blockIdx.x == 0 && threadIdx.x == 0) {  // exchange blocks: total of the shards' uncertified counts
+        int32_t tot = 0;
+        for (int l = 0; l < n_lists; ++l) tot += ba.trailer[(size_t)l * ba.list_stride];
+        *ba.total_out = tot;
+    }
     if (q >= nq) return;
+    const size_t lstride = ba.list_stride ? ba.list_stride : (size_t)nq * list_len;
     RegTopK<KTOP> L;
     L.init();
     bool first = true;
     for (int l = lane; l < n_lists; l += 32) {
-        const float* pk = part_key + ((size_t)l * nq + q) * list_len;
-        const int32_t* pi = part_id + ((size_t)l * nq + q) * list_len;
+        const float* pk = part_key + (size_t)l * lstride + (size_t)q * list_len;
+        const int32_t* pi = part_id + (size_t)l * lstride + (size_t)q * list_len;
         if (first) {  // lists are already sorted: adopt the first one as is
 #pragma unroll
             for (int i = 0; i < KTOP; ++i) {
@@ -423,17 +438,19 @@ int launch_merge_lists(const float* part_key, const int32_t* part_id, int n_list
                        int k, int64_t id_base, int neg_in, int neg_out, float* out_key, int32_t* out_id, int out_stride,
                        int out_off, float* lb_key_out, int32_t* lb_id_out, const float* rf_base, const float* rf_bnorm,
                        const float* rf_q, const float* rf_qnorm, cudaStream_t st, const TcQueryParams* cert_qp,
-                       int32_t* uncert_count, int32_t* uncert_list) {
+                       int32_t* uncert_count, int32_t* uncert_list, size_t list_stride, const int32_t* trailer,
+                       int32_t* trailer_total_out) {
     if (nq <= 0) return VS_OK;
     if (nsel > list_len || k > nsel || nsel > 32) return fail(VS_ERR_INVALID, "merge: need k <= nsel <= list length <= 32");
     if (cert_qp && (!rf_base || !uncert_count || !uncert_list)) return fail(VS_ERR_INVALID, "merge: certification needs the refine");
     const unsigned blocks = (unsigned)ceil_div64(nq, 4);
     RefineArgs rf{rf_base, rf_bnorm, rf_q, rf_qnorm, cert_qp, uncert_count, uncert_list};
+    BlockArgs ba{list_stride, trailer, trailer_total_out};
 #define VSB_MERGE_CASE(KT)                                                                                            \
     case KT:                                                                                                          \
         merge_lists_kernel<KT><<<blocks, 128, 0, st>>>(part_key, part_id, n_lists, nq, list_len, nsel, k, id_base,    \
                                                        neg_in, neg_out, out_key, out_id, out_stride, out_off,         \
-                                                       lb_key_out, lb_id_out, rf);                                    \
+                                                       lb_key_out, lb_id_out, rf, ba);                                \
         break;
     switch (round_up_ktop(list_len)) {
         VSB_MERGE_CASE(1)
@@ -454,13 +471,20 @@ int launch_merge_lists(const float* part_key, const int32_t* part_id, int n_list
 // query, lane g walks list g; every round the warp picks the best head with a shuffle arg-min and that lane advances.
 __global__ void __launch_bounds__(128) merge_shards_kernel(const float* __restrict__ in_key, const int32_t* __restrict__ in_id,
                                                            int n_shards, int64_t nq, int k, int neg,
-                                                           float* __restrict__ out_key, int32_t* __restrict__ out_id) {
+                                                           float* __restrict__ out_key, int32_t* __restrict__ out_id,
+                                                           BlockArgs ba) {
     const int lane = threadIdx.x & 31;
     const int64_t q = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (ba.trailer && blockIdx.x == 0 && threadIdx.x == 0) {
+        int32_t tot = 0;
+        for (int l = 0; l < n_shards; ++l) tot += ba.trailer[(size_t)l * ba.list_stride];
+        *ba.total_out = tot;
+    }
     if (q >= nq) return;
     const float INF = __int_as_float(0x7f800000);
-    const float* pk = in_key + ((size_t)min(lane, n_shards - 1) * nq + q) * k;
-    const int32_t* pi = in_id + ((size_t)min(lane, n_shards - 1) * nq + q) * k;
+    const size_t lstride = ba.list_stride ? ba.list_stride : (size_t)nq * k;
+    const float* pk = in_key + (size_t)min(lane, n_shards - 1) * lstride + (size_t)q * k;
+    const int32_t* pi = in_id + (size_t)min(lane, n_shards - 1) * lstride + (size_t)q * k;
     int pos = lane < n_shards ? 0 : k;
     float hk = INF;
     int32_t hid = -1;
@@ -496,10 +520,11 @@ __global__ void __launch_bounds__(128) merge_shards_kernel(const float* __restri
 }
 
 int launch_merge_shards(const float* in_key, const int32_t* in_id, int n_shards, int64_t nq, int k, int neg, float* out_key,
-                        int32_t* out_id, cudaStream_t st) {
+                        int32_t* out_id, cudaStream_t st, size_t list_stride, const int32_t* trailer, int32_t* trailer_total_out) {
     if (nq <= 0) return VS_OK;
     if (n_shards > 32) return fail(VS_ERR_UNSUPPORTED, "merge: more than 32 shards");
-    merge_shards_kernel<<<(unsigned)ceil_div64(nq, 4), 128, 0, st>>>(in_key, in_id, n_shards, nq, k, neg, out_key, out_id);
+    BlockArgs ba{list_stride, trailer, trailer_total_out};
+    merge_shards_kernel<<<(unsigned)ceil_div64(nq, 4), 128, 0, st>>>(in_key, in_id, n_shards, nq, k, neg, out_key, out_id, ba);
     VSB_CUDA(cudaGetLastError());
     return VS_OK;
 }

@@ -66,11 +66,15 @@ int launch_merge_lists(const float* part_key, const int32_t* part_id, int n_list
                        int k, int64_t id_base, int neg_in, int neg_out, float* out_key, int32_t* out_id, int out_stride,
                        int out_off, float* lb_key_out, int32_t* lb_id_out, const float* rf_base, const float* rf_bnorm,
                        const float* rf_q, const float* rf_qnorm, cudaStream_t st, const TcQueryParams* cert_qp = nullptr,
-                       int32_t* uncert_count = nullptr, int32_t* uncert_list = nullptr);
+                       int32_t* uncert_count = nullptr, int32_t* uncert_list = nullptr,
+                       // lists inside per-shard exchange blocks: list l starts list_stride 4-byte words after list l-1
+                       // (0 = dense [list][nq][len]); trailer: word 0 of each block's trailer, summed into *trailer_total_out
+                       size_t list_stride = 0, const int32_t* trailer = nullptr, int32_t* trailer_total_out = nullptr);
 int launch_sort_rows(float* key, int32_t* id, int64_t nq, int k, cudaStream_t st);
 // G <= 32 sorted per-shard lists [G][nq][k] of any k -> the k best per query, canonical order (neg: largest key first)
 int launch_merge_shards(const float* in_key, const int32_t* in_id, int n_shards, int64_t nq, int k, int neg, float* out_key,
-                        int32_t* out_id, cudaStream_t st);
+                        int32_t* out_id, cudaStream_t st, size_t list_stride = 0, const int32_t* trailer = nullptr,
+                        int32_t* trailer_total_out = nullptr);
 
 // synth.cu --------------------------------------------------------------------------------------
 int launch_synth(float* out, int64_t row0, int64_t nrows, int dim, int law, uint64_t seed, uint64_t centre_seed,

@@ -87,6 +87,14 @@ static std::string load_npy(const std::string& path, const char* want, size_t el
     if (s0 == std::string::npos) return "NPY header has no shape: " + path;
     s0 += 10;
     const size_t s1 = hdr.find(')', s0);
+    if (s1 == std::string::npos) return "NPY shape tuple is not closed: " + path;
+    // the payload cannot be larger than what is left of the file: a corrupt header must not drive the allocation
+    const std::streampos data_pos = f.tellg();
+    f.seekg(0, std::ios::end);
+    const std::streampos end_pos = f.tellg();
+    f.seekg(data_pos);
+    if (!f || end_pos < data_pos) return "cannot size " + path;
+    const size_t avail = (size_t)(end_pos - data_pos);
     shape.clear();
     size_t total = 1;
     for (size_t i = s0; i < s1;) {
@@ -95,9 +103,11 @@ static std::string load_npy(const std::string& path, const char* want, size_t el
         char* end = nullptr;
         const size_t d = std::strtoull(hdr.c_str() + i, &end, 10);
         shape.push_back(d);
+        if (d != 0 && total > avail / d) return "NPY shape exceeds the file size: " + path;  // also catches overflow
         total *= d;
         i = (size_t)(end - hdr.c_str());
     }
+    if (total > avail / elem) return "NPY shape exceeds the file size: " + path;
     raw.resize(total * elem);
     f.read((char*)raw.data(), (std::streamsize)raw.size());
     if ((size_t)f.gcount() != raw.size()) return "truncated NPY data in " + path;

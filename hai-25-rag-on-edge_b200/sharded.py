@@ -1,7 +1,7 @@
 """Sharded multi-GPU search: one process per GPU (torch.distributed).  Exact / INT8: base rows partitioned
 contiguously across ranks; IVF: inverted lists partitioned across ranks.  Queries are replicated, every rank computes
-its local top-k, and there is ONE exchange step — an all-gather of the [nq x k] (id, key) candidates over NCCL /
-NVLink — followed by the merge kernel (vs_merge_topk_dev) on every rank.
+its local top-k, and there is ONE exchange step — ONE in-place all-gather over NCCL / NVLink of the per-shard exchange
+blocks (ids | keys | trailer, vs_topk_block_bytes) — followed by the merge kernel (vs_merge_blocks_dev) on every rank.
 
 The reference has no multi-device code; this is the sharding BASELINE.json's north_star asks for.
 The canonical (key, id) order of every local result makes the merged answer independent of the number of shards.
@@ -34,46 +34,74 @@ def allgather_topk(ids_loc: torch.Tensor, keys_loc: torch.Tensor, group=None):
 
 
 class ShardedExact:
-    """Exact L2 kNN over a base sharded by rows across the ranks of a process group.
+    """Exact L2 kNN over a base sharded by rows: this process holds `index` (one vsb200.ExactIndex, or a list of them —
+    several shards on one device) created with id_base = first row of the shard; the other ranks of the process group
+    hold the other shards.  One exchange step: every shard writes its exchange block (ids | dists | uncertified count,
+    vsb200.topk_block_bytes) IN PLACE into its slot of the gathered buffer, ONE in-place all-gather replicates the
+    slots, the merge kernel reads them all.  The begin / merge / finish sequence is the C ABI's (vs_exact_group_*);
+    `exchange` replaces the collective (tests: all shards local -> nothing to do).
 
-    index      this rank's vsb200.ExactIndex, created with id_base = first row of the shard
     search()   device query pointer -> (ids, dists) tensors on this rank's device holding the GLOBAL top-k
+    enqueue() + finish()   the same in two halves: enqueue() never blocks the host; finish() waits for the 4-byte
+               total of the uncertified counts and, when some shard had to redo queries, exchanges and merges again.
     """
 
-    def __init__(self, vsb, index, nq_max: int, k: int, device: torch.device, group=None):
-        self.vsb, self.index, self.k, self.group = vsb, index, k, group
+    def __init__(self, vsb, index, nq_max: int, k: int, device: torch.device, group=None, exchange=None):
+        self.vsb, self.k, self.group = vsb, k, group
+        self.shards = list(index) if isinstance(index, (list, tuple)) else [index]
+        self.index = self.shards[0]
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.n_local = len(self.shards)
+        self.n_slots = self.world * self.n_local
+        self.first_slot = self.rank * self.n_local
+        self.nq_max = nq_max
+        self.exchanges = 0
         self.ids_loc = torch.empty((nq_max, k), dtype=torch.int32, device=device)
         self.d_loc = torch.empty((nq_max, k), dtype=torch.float32, device=device)
-        if self.world > 1:
-            self.ids_all = torch.empty((self.world * nq_max, k), dtype=torch.int32, device=device)  # [G][nq][k]
-            self.d_all = torch.empty((self.world * nq_max, k), dtype=torch.float32, device=device)
-            self.ids_out = torch.empty((nq_max, k), dtype=torch.int32, device=device)
-            self.d_out = torch.empty((nq_max, k), dtype=torch.float32, device=device)
-        self.nq_max = nq_max
+        self._exchange = exchange if exchange is not None else self._allgather
+        if self.n_slots > 1:
+            self.block = vsb.topk_block_bytes(nq_max, k)
+            self.gathered = torch.zeros(self.n_slots * self.block, dtype=torch.uint8, device=device)  # [slot][block]
+            self.grp = vsb.ExactGroup(self.shards, self.n_slots, self.first_slot)
 
-    def search(self, q_ptr: int, nq: int, precision: int, stream: int):
+    def close(self):
+        if self.n_slots > 1:
+            self.grp.close()
+
+    def _allgather(self):
+        if self.world > 1:
+            mine = self.gathered[self.first_slot * self.block:(self.first_slot + self.n_local) * self.block]
+            dist.all_gather_into_tensor(self.gathered, mine, group=self.group)  # in place: slot s comes from its owner
+
+    def enqueue(self, q_ptr: int, nq: int, precision: int, stream: int):
         """Enqueues on `stream` (torch's current stream must be that stream: NCCL orders against it)."""
         if nq != self.nq_max:
             raise ValueError("ShardedExact buffers are sized for nq_max queries per call")
-        if self.world == 1:
+        if self.n_slots == 1:
             self.index.search_dev(q_ptr, nq, self.k, precision, self.ids_loc.data_ptr(), self.d_loc.data_ptr(), stream)
             return self.ids_loc, self.d_loc
-        # enqueue the local search, the exchange and the merge back to back; only then wait for the certification count
-        # of the local search (the launch latency of the collectives hides behind the fused kernel)
-        self.index.search_dev_begin(q_ptr, nq, self.k, precision, self.ids_loc.data_ptr(), self.d_loc.data_ptr(), stream)
-        self._exchange(nq, stream)
-        redone = torch.tensor([self.index.search_dev_finish()], dtype=torch.int32, device=self.ids_loc.device)
-        dist.all_reduce(redone, op=dist.ReduceOp.MAX, group=self.group)
-        if int(redone.item()) > 0:  # some rank rewrote result rows after the exchange had been enqueued: exchange again
-            self._exchange(nq, stream)
-        return self.ids_out, self.d_out
+        self.grp.begin(q_ptr, nq, self.k, precision, self.gathered.data_ptr(), stream)
+        self._exchange()
+        self.exchanges = 1
+        self.grp.merge(self.ids_loc.data_ptr(), self.d_loc.data_ptr())
+        return self.ids_loc, self.d_loc
 
-    def _exchange(self, nq: int, stream: int):
-        dist.all_gather_into_tensor(self.ids_all, self.ids_loc, group=self.group)
-        dist.all_gather_into_tensor(self.d_all, self.d_loc, group=self.group)
-        self.vsb.merge_topk_dev(self.ids_all.data_ptr(), self.d_all.data_ptr(), self.world, nq, self.k, True,
-                                self.ids_out.data_ptr(), self.d_out.data_ptr(), stream)
+    def finish(self) -> int:
+        """-> number of extra exchanges (0 unless a shard could not certify some queries and redid them in fp32)."""
+        extra = 0
+        if self.n_slots > 1:
+            while self.grp.finish():
+                self._exchange()
+                self.grp.merge(self.ids_loc.data_ptr(), self.d_loc.data_ptr())
+                extra += 1
+                self.exchanges += 1
+        return extra
+
+    def search(self, q_ptr: int, nq: int, precision: int, stream: int):
+        out = self.enqueue(q_ptr, nq, precision, stream)
+        self.finish()
+        return out
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -113,17 +141,21 @@ def local_ivf_arrays(vectors_list_order, offsets, id_map, owner, rank: int):
 
 class ShardedIvf:
     """IVF search over lists partitioned across the ranks.  index = this rank's vsb200.IvfIndex built from
-    local_ivf_arrays(); search() -> (ids, scores, counts) tensors holding the GLOBAL answer on every rank."""
+    local_ivf_arrays(); search() -> (ids, scores, counts) tensors holding the GLOBAL answer on every rank.
+    One collective: a rank's slot = exchange block (ids | scores | trailer) followed by its candidate counts [nq]."""
 
     def __init__(self, vsb, index, nq_max: int, k: int, device: torch.device, group=None):
         self.vsb, self.index, self.k, self.group = vsb, index, k, group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
-        self.ids_loc = torch.empty((nq_max, k), dtype=torch.int32, device=device)
-        self.sc_loc = torch.empty((nq_max, k), dtype=torch.float32, device=device)
-        self.cnt_loc = torch.empty((nq_max,), dtype=torch.int32, device=device)
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.block = vsb.topk_block_bytes(nq_max, k)
+        self.slot = (self.block + 4 * nq_max + 15) // 16 * 16
+        self.gathered = torch.zeros((self.world, self.slot), dtype=torch.uint8, device=device)
+        mine = self.gathered[self.rank]
+        self.ids_loc = mine[:4 * nq_max * k].view(torch.int32).view(nq_max, k)
+        self.sc_loc = mine[4 * nq_max * k:8 * nq_max * k].view(torch.float32).view(nq_max, k)
+        self.cnt_loc = mine[self.block:self.block + 4 * nq_max].view(torch.int32)
         if self.world > 1:
-            self.ids_all = torch.empty((self.world * nq_max, k), dtype=torch.int32, device=device)
-            self.sc_all = torch.empty((self.world * nq_max, k), dtype=torch.float32, device=device)
             self.ids_out = torch.empty((nq_max, k), dtype=torch.int32, device=device)
             self.sc_out = torch.empty((nq_max, k), dtype=torch.float32, device=device)
         self.nq_max = nq_max
@@ -135,27 +167,30 @@ class ShardedIvf:
                               self.cnt_loc.data_ptr(), stream)
         if self.world == 1:
             return self.ids_loc, self.sc_loc, self.cnt_loc
-        dist.all_gather_into_tensor(self.ids_all, self.ids_loc, group=self.group)
-        dist.all_gather_into_tensor(self.sc_all, self.sc_loc, group=self.group)
-        cnt = self.cnt_loc.clone()
-        dist.all_reduce(cnt, group=self.group)  # candidates found over all ranks; the answer holds min(k, that)
-        self.vsb.merge_topk_dev(self.ids_all.data_ptr(), self.sc_all.data_ptr(), self.world, nq, self.k, False,
-                                self.ids_out.data_ptr(), self.sc_out.data_ptr(), stream)
+        dist.all_gather_into_tensor(self.gathered.view(-1), self.gathered[self.rank], group=self.group)  # in place
+        self.vsb.merge_blocks_dev(self.gathered.data_ptr(), self.world, self.slot, nq, self.k, False,
+                                  self.ids_out.data_ptr(), self.sc_out.data_ptr(), 0, stream)
+        # candidates found over all ranks; the answer holds min(k, that)
+        cnt = self.gathered[:, self.block:self.block + 4 * nq].contiguous().view(torch.int32).sum(0, dtype=torch.int32)
         return self.ids_out, self.sc_out, torch.clamp(cnt, max=self.k)
 
 
 class ShardedInt8:
     """INT8 brute force over base rows partitioned contiguously across the ranks (every rank must be created with the
-    SAME weight scale, e.g. the all-reduced max of the base / 255).  search() -> (ids, u8 scores) on every rank."""
+    SAME weight scale, e.g. the all-reduced max of the base / 255).  search() -> (ids, u8 scores) on every rank.
+    One collective: the exchange block of a rank holds its ids and its scores widened to fp32 (the merge's key type)."""
 
     def __init__(self, vsb, index, nq_max: int, k: int, device: torch.device, group=None):
         self.vsb, self.index, self.k, self.group = vsb, index, k, group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
-        self.ids_loc = torch.empty((nq_max, k), dtype=torch.int32, device=device)
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.block = vsb.topk_block_bytes(nq_max, k)
+        self.gathered = torch.zeros((self.world, self.block), dtype=torch.uint8, device=device)
+        mine = self.gathered[self.rank]
+        self.ids_loc = mine[:4 * nq_max * k].view(torch.int32).view(nq_max, k)
+        self.key_loc = mine[4 * nq_max * k:8 * nq_max * k].view(torch.float32).view(nq_max, k)
         self.sc_loc = torch.empty((nq_max, k), dtype=torch.uint8, device=device)
         if self.world > 1:
-            self.ids_all = torch.empty((self.world * nq_max, k), dtype=torch.int32, device=device)
-            self.sc_all = torch.empty((self.world * nq_max, k), dtype=torch.float32, device=device)
             self.ids_out = torch.empty((nq_max, k), dtype=torch.int32, device=device)
             self.sc_out = torch.empty((nq_max, k), dtype=torch.float32, device=device)
         self.nq_max = nq_max
@@ -166,8 +201,8 @@ class ShardedInt8:
         self.index.search_dev(q_ptr, nq, self.k, self.ids_loc.data_ptr(), self.sc_loc.data_ptr(), stream)
         if self.world == 1:
             return self.ids_loc, self.sc_loc
-        dist.all_gather_into_tensor(self.ids_all, self.ids_loc, group=self.group)
-        dist.all_gather_into_tensor(self.sc_all, self.sc_loc.to(torch.float32), group=self.group)  # merge keys are fp32
-        self.vsb.merge_topk_dev(self.ids_all.data_ptr(), self.sc_all.data_ptr(), self.world, nq, self.k, False,
-                                self.ids_out.data_ptr(), self.sc_out.data_ptr(), stream)
+        self.key_loc.copy_(self.sc_loc)  # u8 -> fp32 keys inside the block
+        dist.all_gather_into_tensor(self.gathered.view(-1), self.gathered[self.rank], group=self.group)  # in place
+        self.vsb.merge_blocks_dev(self.gathered.data_ptr(), self.world, self.block, nq, self.k, False,
+                                  self.ids_out.data_ptr(), self.sc_out.data_ptr(), 0, stream)
         return self.ids_out, self.sc_out.to(torch.uint8)

@@ -56,7 +56,10 @@ typedef enum vs_precision {
     VS_PREC_AUTO = 0,        /* <= 8 queries -> FFMA stream; >= 449 queries and k <= 16 -> certified fp16 candidate pass
                                 (below); otherwise 1xTF32 when every operand is exactly representable in TF32 (integer
                                 SIFT data: bit-identical to fp32), else 3xTF32.  Thresholds measured on B200. */
-    VS_PREC_FP32_3XTF32 = 1, /* tcgen05 kind::tf32, hi/lo split, 3 products, fp32 accumulate in TMEM */
+    VS_PREC_FP32_3XTF32 = 1, /* tcgen05 kind::tf32, hi/lo split, 3 products, fp32 accumulate in TMEM.  The tensor-core keys
+                                rank the candidates (k + 2 of them when k <= 30, exactly k beyond), every returned
+                                distance is recomputed in plain fp32: ids equal the fp32 reference's except inside
+                                distance ties within 1e-5 relative (the north star's tolerance; not certified) */
     VS_PREC_FP32_FFMA = 2,   /* CUDA-core FFMA streaming kernel (HBM-bound; any batch, slow for large ones) */
     VS_PREC_TF32_1X = 3,     /* single TF32 product; exact only for TF32-representable data */
     VS_PREC_F16_CERTIFIED = 4 /* fp32-faithful results from a cheaper tensor-core pass: tcgen05 kind::f16 on power-of-two
@@ -78,8 +81,8 @@ typedef struct vs_exact vs_exact_t;
 
 /* Builds the device-resident index for base[n x dim] (row-major fp32, host memory): copies the rows,
  * precomputes ||x||^2 in the reference's summation order (cpu_baseline.cpp:95-114) and the TF32 hi/lo split.
- * device = CUDA ordinal; id_base is added to every returned id (row-sharded multi-GPU use). dim must be 128
- * for the tensor-core path (any dim multiple of 4 up to 1024 for FFMA). */
+ * device = CUDA ordinal; id_base is added to every returned id (row-sharded multi-GPU use).  dim must be 128 (the
+ * SIFT shape of every BASELINE config): any other dim fails with VS_ERR_UNSUPPORTED. */
 VSB_API int vs_exact_create(vs_exact_t** out, const float* base, int64_t n, int dim, int device, int64_t id_base);
 /* Same, base already resident on `device` (not copied; must outlive the handle). */
 VSB_API int vs_exact_create_dev(vs_exact_t** out, const float* base_dev, int64_t n, int dim, int device, int64_t id_base);
@@ -123,6 +126,56 @@ VSB_API int vs_exact_last_kernel_ms(vs_exact_t* h, float* ms);
  * (L2); smallest==0: keys descending (inner product). Device pointers, asynchronous on `stream`. */
 VSB_API int vs_merge_topk_dev(const int32_t* ids_dev, const float* keys_dev, int n_shards, int64_t nq, int k,
                       int smallest, int32_t* out_ids_dev, float* out_keys_dev, void* stream);
+
+/* ---------------------------------------------------------------------------------------------- */
+/* Row-sharded exact search (SURVEY.md §8b "n_gpus", §8e): base rows partitioned into shards, queries    */
+/* replicated, every shard returns its local top-k, ONE exchange step, merge.  The canonical (distance, id) */
+/* order makes the merged answer independent of the number of shards.                                  */
+/* ---------------------------------------------------------------------------------------------- */
+/* Exchange block of one shard for nq queries x k results: ids [nq x k] int32 | keys [nq x k] fp32 | 16-byte trailer
+ * (word 0 = number of queries the shard could not certify).  ids and keys travel in ONE collective and the trailer
+ * carries the "was anything redone" information, so the exchange needs no second collective and no host round trip. */
+VSB_API size_t vs_topk_block_bytes(int64_t nq, int k);
+/* Merge n_shards blocks (block s at blocks_dev + s*block_stride) into the global top-k per query; total_dev (may be
+ * NULL) receives the sum of the trailers' counts.  Any k; device pointers, asynchronous on `stream`. */
+VSB_API int vs_merge_blocks_dev(const void* blocks_dev, int n_shards, size_t block_stride, int64_t nq, int k, int smallest,
+                                int32_t* out_ids_dev, float* out_keys_dev, int32_t* total_dev, void* stream);
+
+/* The shards that live on ONE device, as one participant of the exchange (one process per GPU: bench.py / torchrun;
+ * or several shards on one GPU).  The group does not own the shard handles.  Slots first_slot .. first_slot+n_local-1
+ * of the gathered buffer [n_slots][vs_topk_block_bytes(nq, k)] belong to this group.
+ *   begin   enqueues the local searches; every shard writes its block IN PLACE into its slot (no host synchronisation)
+ *   <the caller's exchange: an in-place all-gather of the slots; nothing when every shard is local>
+ *   merge   enqueues the merge of all slots and the 4-byte total of the uncertified counts on its way to the host
+ *   finish  waits for that total only.  0 in the common case.  Otherwise the local shards redo their uncertified queries
+ *           on the fp32 path (rewriting rows of their blocks) and *need_reexchange = 1: exchange, merge and finish again.
+ *           Every participant sees the same total, so all of them take the same decision without a collective. */
+typedef struct vs_exact_group vs_exact_group_t;
+VSB_API int vs_exact_group_create_from(vs_exact_group_t** out, int n_local, vs_exact_t* const* shards, int n_slots,
+                                       int first_slot);
+VSB_API int vs_exact_group_destroy(vs_exact_group_t* g);
+VSB_API int vs_exact_group_begin(vs_exact_group_t* g, const float* queries_dev, int64_t nq, int k, int precision,
+                                 void* gathered_dev, void* stream);
+VSB_API int vs_exact_group_merge(vs_exact_group_t* g, int32_t* out_ids_dev, float* out_dists_dev);
+VSB_API int vs_exact_group_finish(vs_exact_group_t* g, int* need_reexchange);
+
+/* Single process, n_gpus devices (0 = all visible), shards_per_gpu shards on each (>= 1; > 1 is for tests and for
+ * bases whose per-GPU share should be searched in pieces): the drop-in for run_benchmark()'s hot triple
+ * (cpu/cpu_baseline.cpp:177-257) on a multi-GPU box.  Contiguous row ranges, one worker thread and one stream per GPU,
+ * ncclCommInitAll + one grouped ncclAllGather of the exchange blocks over NVLink (NCCL is loaded with dlopen at the
+ * first multi-GPU create; n_gpus = 1 needs no NCCL), device 0 merges and returns.  Host buffers in and out; the
+ * queries cross PCIe once (every GPU uploads its slice, the slices are replicated over NVLink). */
+typedef struct vs_exact_mgpu vs_exact_mgpu_t;
+VSB_API int vs_exact_mgpu_create(vs_exact_mgpu_t** out, const float* base, int64_t n, int dim, int n_gpus, int shards_per_gpu);
+VSB_API int vs_exact_mgpu_destroy(vs_exact_mgpu_t* m);
+VSB_API int vs_exact_mgpu_num_gpus(const vs_exact_mgpu_t* m);
+VSB_API int vs_exact_mgpu_num_shards(const vs_exact_mgpu_t* m);
+VSB_API int vs_exact_mgpu_search_f32(vs_exact_mgpu_t* m, const float* queries, int64_t nq, int k, int precision,
+                                     int32_t* out_ids, float* out_dists);
+/* exchanges of the last search (1 unless a shard had to redo uncertified queries) / whether anything was redone */
+VSB_API int vs_exact_mgpu_last_stats(const vs_exact_mgpu_t* m, int* n_exchanges, int* redone);
+VSB_API int vs_exact_mgpu_set_profile(vs_exact_mgpu_t* m, int enable);
+VSB_API int vs_exact_mgpu_last_kernel_ms(vs_exact_mgpu_t* m, float* ms);   /* slowest shard's fused kernel */
 
 /* ---------------------------------------------------------------------------------------------- */
 /* IVF two-stage search (inner-product metric, like the reference)                                 */

@@ -25,7 +25,9 @@ def run(cmd, cwd=None, expect_rc=0):
 
 
 @pytest.mark.parametrize("law,k,extra", [("sift", 5, []), ("cont", 10, []), ("sift", 5, ["--batch", "1"]),
-                                         ("cont", 10, ["--precision", "3xtf32", "--batch", "32"])])
+                                         ("cont", 10, ["--precision", "3xtf32", "--batch", "32"]),
+                                         ("cont", 10, ["--gpus", "1", "--shards-per-gpu", "4"]),   # vs_exact_mgpu_* path
+                                         ("sift", 5, ["--gpus", "0"])])                             # every visible GPU
 def test_cpu_baseline_cli_matches_reference_text(law, k, extra, tmp_path, gpu_vsb, oracle):
     vsb = gpu_vsb
     assert os.path.exists(os.path.join(BIN, "cpu_baseline")), "run __graft_entry__.build()"
@@ -76,7 +78,7 @@ def test_cpu_baseline_no_argument_mode_and_errors(tmp_path, gpu_vsb, oracle):
     raw = open(tmp_path / "siftsmall" / "siftsmall_base.fvecs", "rb").read()
     open(tmp_path / "trunc.fvecs", "wb").write(raw[:-7])
     r = run([os.path.join(BIN, "cpu_baseline"), str(tmp_path / "trunc.fvecs"),
-             str(tmp_path / "siftsmall" / "siftsmall_query.fvecs"), "5", str(tmp_path / "x.txt")])
+             str(tmp_path / "siftsmall" / "siftsmall_query.fvecs"), "5", str(tmp_path / "x.txt")], expect_rc=1)
     assert "File seems truncated." in r.stderr and not os.path.exists(tmp_path / "x.txt")
     run([os.path.join(BIN, "cpu_baseline"), "a", "b"], expect_rc=1)
 

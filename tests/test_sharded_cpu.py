@@ -218,3 +218,55 @@ def test_two_rank_gloo_int8_rows_sharded_equals_single_index(tmp_path):
     for r in range(world):
         g = np.load(tmp_path / f"i8{r}.npz")
         assert np.array_equal(g["ids"], wi) and np.array_equal(g["sc"], ws)
+
+
+def _block_worker(rank, world, port, n, nq, k, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import vsb200_loader
+    from oracle import oracle
+
+    vsb = vsb200_loader.load()
+    from vsb200 import sharded
+
+    base = vsb.synth.make("sift", 77, n)
+    qry = vsb.synth.make("sift", 78, nq)
+    r0, r1 = sharded.shard_range(n, rank, world)
+    ids, d = oracle.exact_search(base[r0:r1], qry, k, mode=1)
+    B = vsb.topk_block_bytes(nq, k)
+    gathered = torch.zeros((world, B), dtype=torch.uint8)
+    mine = gathered[rank]                                     # the shard's slot: ids | keys | trailer
+    mine[:4 * nq * k].view(torch.int32).view(nq, k).copy_(torch.from_numpy(ids + r0))
+    mine[4 * nq * k:8 * nq * k].view(torch.float32).view(nq, k).copy_(torch.from_numpy(d))
+    mine[B - 16:B - 12].view(torch.int32)[0] = 3 + rank       # "uncertified count" of this shard
+    dist.all_gather_into_tensor(gathered.view(-1), gathered[rank])   # ONE collective, in place
+    g = gathered.numpy()
+    ids_all = np.stack([g[s, :4 * nq * k].view(np.int32).reshape(nq, k) for s in range(world)])
+    d_all = np.stack([g[s, 4 * nq * k:8 * nq * k].view(np.float32).reshape(nq, k) for s in range(world)])
+    total = sum(int(g[s, B - 16:B - 12].view(np.int32)[0]) for s in range(world))
+    mi, md = _merge_host(ids_all, d_all, k)
+    np.savez(os.path.join(out_dir, f"blk{rank}.npz"), ids=mi, d=md, total=np.array([total]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_two_rank_gloo_block_exchange_in_place(tmp_path):
+    """The exchange of the row-sharded search as sharded.ShardedExact runs it: every rank fills ITS slot of the gathered
+    buffer with an exchange block (vs_topk_block_bytes layout: ids | keys | trailer) and ONE in-place all-gather
+    replicates the slots; ids, keys and the uncertified counts arrive together."""
+    sys.path.insert(0, ROOT)
+    from oracle import oracle
+    import vsb200_loader
+
+    vsb = vsb200_loader.load()
+    n, nq, k, world = 5003, 31, 10, 2
+    assert vsb.topk_block_bytes(nq, k) == (nq * k * 8 + 15) // 16 * 16 + 16
+    mp.spawn(_block_worker, args=(world, _free_port(), n, nq, k, str(tmp_path)), nprocs=world, join=True)
+    base = vsb.synth.make("sift", 77, n)
+    qry = vsb.synth.make("sift", 78, nq)
+    wi, wd = oracle.exact_search(base, qry, k, mode=1)
+    for r in range(world):
+        g = np.load(tmp_path / f"blk{r}.npz")
+        assert np.array_equal(g["ids"], wi) and np.array_equal(g["d"], wd) and int(g["total"][0]) == 3 + 4
