@@ -127,6 +127,17 @@ class ExactIndex:
         _check(lib().vs_exact_search_dev_finish(self._h, C.byref(n)))
         return n.value
 
+    def debug_f16_candidates(self, queries: np.ndarray):
+        """Test hook: the fp16 candidate pass alone -> (ids [nq,32] local, keys [nq,32] as the kernel ranked them,
+        bound [nq] = the certificate's E_q)."""
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        nq = q.shape[0]
+        ids = np.empty((nq, 32), dtype=np.int32)
+        keys = np.empty((nq, 32), dtype=np.float32)
+        bound = np.empty(nq, dtype=np.float32)
+        _check(lib().vs_exact_debug_f16_candidates(self._h, _ptr(q), C.c_int64(nq), _ptr(ids), _ptr(keys), _ptr(bound)))
+        return ids, keys, bound
+
     def set_profile(self, enable: bool = True) -> None:
         _check(lib().vs_exact_set_profile(self._h, C.c_int(int(enable))))
 

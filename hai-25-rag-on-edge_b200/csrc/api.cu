@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -201,20 +202,15 @@ int exact_create_common(vs_exact_t** out, const float* base, bool on_device, int
     return VS_OK;
 }
 
-
-// Certified candidate pass: scaled fp16 tensor-core kernel keeps the 32 best keys per query (error bounded by
-// cert_a*sqrt(qn)+cert_b), the merge kernel recomputes those 32 distances in exact fp32, ranks them and certifies
-// the top k; the (rare) uncertified queries are redone on the 3xTF32 / FFMA path.  Synchronises `st` once (4-byte
-// count of uncertified queries).
-static int exact_search_certified(vs_exact* h, const float* q_dev, int64_t nq, int k, int32_t* out_ids, float* out_dists,
-                                  cudaStream_t st, int32_t* unc_dev) {
+// The candidate pass of the certified search: query prep (norms, abs-max -> power-of-two scale, fp16 copy, bound
+// constants) and the fused fp16 tensor-core kernel.  Leaves n_lists sorted partial lists of 32 (key, local id) per query
+// in h->part_key / h->part_id.
+static int exact_f16_candidate_pass(vs_exact* h, const float* q_dev, int64_t nq, cudaStream_t st, int* n_lists_out) {
     const int ktop = kMaxRegK;
     int* flag = h->flag.as<int>();
-    // count of uncertified queries: the handle's own word, or the caller's (trailer of an exchange block, already zeroed)
-    int32_t* unc = unc_dev ? unc_dev : flag + 1;
+    VSB_TRY(h->qnorm.reserve(sizeof(float) * (size_t)nq));
     VSB_TRY(h->qf16.reserve(2 * (size_t)nq * 128));
     VSB_TRY(h->qparams.reserve(sizeof(TcQueryParams)));
-    VSB_TRY(h->unc_list.reserve(sizeof(int32_t) * (size_t)nq));
     VSB_CUDA(cudaMemsetAsync(flag + 1, 0, 2 * sizeof(int), st));
     VSB_TRY(launch_query_prep(q_dev, nq, h->qnorm.as<float>(), reinterpret_cast<float*>(flag + 2), st));
     TcQueryParams* qp = h->qparams.as<TcQueryParams>();
@@ -238,6 +234,25 @@ static int exact_search_certified(vs_exact* h, const float* q_dev, int64_t nq, i
         VSB_CUDA(cudaEventRecord(h->ev1, st));
         h->ev_valid = true;
     }
+    *n_lists_out = n_lists;
+    return VS_OK;
+}
+
+// Certified candidate pass: scaled fp16 tensor-core kernel keeps the 32 best keys per query (error bounded by
+// cert_a*sqrt(qn)+cert_b), the merge kernel recomputes those 32 distances in exact fp32, ranks them and certifies
+// the top k; the (rare) uncertified queries are redone on the 3xTF32 / FFMA path.  Synchronises `st` once (4-byte
+// count of uncertified queries).
+static int exact_search_certified(vs_exact* h, const float* q_dev, int64_t nq, int k, int32_t* out_ids, float* out_dists,
+                                  cudaStream_t st, int32_t* unc_dev) {
+    const int ktop = kMaxRegK;
+    int* flag = h->flag.as<int>();
+    VSB_TRY(h->unc_list.reserve(sizeof(int32_t) * (size_t)nq));
+    int n_lists = 0;
+    VSB_TRY(exact_f16_candidate_pass(h, q_dev, nq, st, &n_lists));
+    TcQueryParams* qp = h->qparams.as<TcQueryParams>();
+    // count of uncertified queries: the handle's own word (zeroed by the candidate pass), or the caller's (trailer of an
+    // exchange block, already zeroed)
+    int32_t* unc = unc_dev ? unc_dev : flag + 1;
     VSB_TRY(launch_merge_lists(h->part_key.as<float>(), h->part_id.as<int32_t>(), n_lists, nq, ktop, ktop, k, h->id_base, 0, 0,
                                out_dists, out_ids, k, 0, nullptr, nullptr, h->d_base, h->d_norm, q_dev, h->qnorm.as<float>(), st,
                                qp, unc, h->unc_list.as<int32_t>()));
@@ -511,6 +526,36 @@ int vs_exact_search_f32(vs_exact_t* h, const float* queries, int64_t nq, int k, 
     VSB_CUDA(cudaMemcpyAsync(out_ids, h->out_ids.p, sizeof(int32_t) * (size_t)nq * k, cudaMemcpyDeviceToHost, st));
     VSB_CUDA(cudaMemcpyAsync(out_dists, h->out_keys.p, sizeof(float) * (size_t)nq * k, cudaMemcpyDeviceToHost, st));
     VSB_CUDA(cudaStreamSynchronize(st));
+    return VS_OK;
+}
+
+int vs_exact_debug_f16_candidates(vs_exact_t* h, const float* queries, int64_t nq, int32_t* out_ids, float* out_keys,
+                                  float* out_bound) {
+    if (!h || !queries || !out_ids || !out_keys || !out_bound) return fail(VS_ERR_INVALID, "NULL argument");
+    if (nq <= 0 || nq > 0x7fffffff / 128) return fail(VS_ERR_INVALID, "bad nq");
+    if (h->dim != 128) return fail(VS_ERR_UNSUPPORTED, "tensor-core path needs dim == 128");
+    if (h->cert_pending) return fail(VS_ERR_INVALID, "a search is in flight");
+    VSB_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    const int ktop = kMaxRegK;
+    VSB_TRY(h->q.reserve(sizeof(float) * (size_t)nq * 128));
+    VSB_TRY(h->out_ids.reserve(sizeof(int32_t) * (size_t)nq * ktop));
+    VSB_TRY(h->out_keys.reserve(sizeof(float) * (size_t)nq * ktop));
+    VSB_CUDA(cudaMemcpyAsync(h->q.p, queries, sizeof(float) * (size_t)nq * 128, cudaMemcpyHostToDevice, st));
+    int n_lists = 0;
+    VSB_TRY(exact_f16_candidate_pass(h, h->q.as<float>(), nq, st, &n_lists));
+    // the 32 best candidate keys per query exactly as the tensor-core pass ranked them: no refine, no certification
+    VSB_TRY(launch_merge_lists(h->part_key.as<float>(), h->part_id.as<int32_t>(), n_lists, nq, ktop, ktop, ktop, 0, 0, 0,
+                               h->out_keys.as<float>(), h->out_ids.as<int32_t>(), ktop, 0, nullptr, nullptr, nullptr, nullptr,
+                               nullptr, nullptr, st));
+    std::vector<float> qn((size_t)nq);
+    TcQueryParams qp;
+    VSB_CUDA(cudaMemcpyAsync(out_ids, h->out_ids.p, sizeof(int32_t) * (size_t)nq * ktop, cudaMemcpyDeviceToHost, st));
+    VSB_CUDA(cudaMemcpyAsync(out_keys, h->out_keys.p, sizeof(float) * (size_t)nq * ktop, cudaMemcpyDeviceToHost, st));
+    VSB_CUDA(cudaMemcpyAsync(qn.data(), h->qnorm.p, sizeof(float) * (size_t)nq, cudaMemcpyDeviceToHost, st));
+    VSB_CUDA(cudaMemcpyAsync(&qp, h->qparams.p, sizeof(qp), cudaMemcpyDeviceToHost, st));
+    VSB_CUDA(cudaStreamSynchronize(st));
+    for (int64_t i = 0; i < nq; ++i) out_bound[i] = qp.cert_a * sqrtf(qn[(size_t)i]) + qp.cert_b;
     return VS_OK;
 }
 

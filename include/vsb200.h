@@ -121,6 +121,14 @@ VSB_API int vs_exact_last_fallbacks(const vs_exact_t* h, int* n_queries);
 VSB_API int vs_exact_set_profile(vs_exact_t* h, int enable);
 VSB_API int vs_exact_last_kernel_ms(vs_exact_t* h, float* ms);
 
+/* Test hook for the certification bound of VS_PREC_F16_CERTIFIED: runs ONLY the fp16 tensor-core candidate pass and
+ * returns, per query, its 32 candidates as the kernel ranked them — out_ids[nq x 32] (local row ids, -1 padded),
+ * out_keys[nq x 32] (the kernel's keys  ||x||^2 - 2 q.x  in distance units, ascending) — and out_bound[nq], the bound
+ * E_q = cert_a*sqrt(||q||^2) + cert_b the certificate assumes for |key - exact key| (tests/test_exact_gpu.py measures
+ * the actual error against float64). Host buffers. */
+VSB_API int vs_exact_debug_f16_candidates(vs_exact_t* h, const float* queries, int64_t nq, int32_t* out_ids,
+                                          float* out_keys, float* out_bound);
+
 /* Merge per-shard results gathered from G shards (layout [G][nq][k], as produced by an all-gather of every
  * rank's out_ids/out_dists) into the global top-k per query, canonical order. smallest!=0: keys ascending
  * (L2); smallest==0: keys descending (inner product). Device pointers, asynchronous on `stream`. */

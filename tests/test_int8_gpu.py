@@ -143,3 +143,60 @@ def test_argument_errors(gpu_vsb):
         assert ids.shape == (0, 5)
     finally:
         idx.close()
+
+
+def test_full_size_10m_parity(gpu_vsb, oracle):
+    """BASELINE configs[3] at its full size: 10M x 128 rows (generated on the device), batches of 1024 and 32 queries,
+    top-10.  Exactness is established in three links, each bit-exact:
+      1. a 1M-row window of the base, searched through its own handle, equals the CPU twin's top-10 on the same rows
+         (ids and u8 scores, canonical order) for 96 queries;
+      2. the 10M answer equals the merge of the ten 1M-window handles' answers (row sharding is invisible);
+      3. every score the 10M handle returns equals the CPU twin's score of that (query, row) pair, for all 1024 queries;
+    plus batch 32 == the first 32 rows of batch 1024 and descending order."""
+    import torch
+
+    vsb = gpu_vsb
+    n, k, W = 10_000_000, 10, 1_000_000
+    dev = torch.device("cuda:0")
+    base_d = torch.empty((n, 128), dtype=torch.float32, device=dev)
+    for c0 in range(0, n, 1 << 22):
+        vsb.synth_fill_dev(base_d.data_ptr() + c0 * 512, c0, min(1 << 22, n - c0), 128, "mix", 99)
+    torch.cuda.synchronize()
+    qry = vsb.synth.make("mix", 98, 1024)
+    s_in, s_w, s_out = 218.0 / 255.0, 218.0 / 255.0, 9000.0
+    one = vsb.Int8Index(base_d.data_ptr(), s_in, s_w, s_out, n=n)
+    try:
+        ids, sc = one.search(qry, k)
+        ids32, sc32 = one.search(qry[:32], k)
+        m, in_scale, w_scale = one.multiplier, one.in_scale, one.w_scale
+    finally:
+        one.close()
+    assert np.array_equal(ids32, ids[:32]) and np.array_equal(sc32, sc[:32])
+    assert (np.diff(sc.astype(np.int32), axis=1) <= 0).all() and ids.min() >= 0 and ids.max() < n
+    q8 = oracle.quantize_u8(qry, in_scale)
+    # 2. merge of the ten window handles
+    parts_i, parts_s = [], []
+    for w0 in range(0, n, W):
+        h = vsb.Int8Index(base_d.data_ptr() + w0 * 512, s_in, s_w, s_out, n=W, id_base=w0)
+        try:
+            wi, ws = h.search(qry, k)
+        finally:
+            h.close()
+        parts_i.append(wi)
+        parts_s.append(ws)
+        if w0 == 3 * W:   # 1. this window against the CPU twin
+            rows = base_d[w0:w0 + W].cpu().numpy()
+            ti, ts = oracle.int8_search(oracle.quantize_u8(rows, w_scale), q8[:96], k, m, mode=1)
+            assert np.array_equal(wi[:96], ti + w0) and np.array_equal(ws[:96], ts)
+    cat_i = np.concatenate(parts_i, 1)
+    cat_s = np.concatenate(parts_s, 1).astype(np.int32)
+    order = np.lexsort((cat_i, -cat_s), axis=1)[:, :k]
+    assert np.array_equal(np.take_along_axis(cat_i, order, 1), ids)
+    assert np.array_equal(np.take_along_axis(cat_s, order, 1), sc.astype(np.int32))
+    # 3. every returned score recomputed by the CPU twin
+    uniq, inv = np.unique(ids.ravel(), return_inverse=True)
+    rows_u8 = oracle.quantize_u8(base_d[torch.from_numpy(uniq.astype(np.int64)).to(dev)].cpu().numpy(), w_scale)
+    assert np.array_equal(rows_u8[:64], oracle.quantize_u8(np.concatenate([vsb.synth.rows("mix", 99, int(i), 1) for i in uniq[:64]]), w_scale))
+    pos = inv.reshape(ids.shape)
+    want = np.stack([oracle.int8_scores(rows_u8[pos[r]], q8[r:r + 1], m)[0] for r in range(ids.shape[0])])
+    assert np.array_equal(want, sc)
