@@ -114,7 +114,10 @@ static int exact_build(vs_exact* h) {
         VSB_TRY(launch_to_half_scaled(h->d_base, n * dim, h->s_b, nullptr, h->d_f16, h->stream));
         VSB_CUDA(cudaStreamSynchronize(h->stream));
         memcpy(&h->bn_max, &h->h_flag[3], sizeof(float));
-        VSB_TRY(make_tmap_2d(&h->tmB_f16, h->d_f16, (uint64_t)n, 128, 2, 128));
+        VSB_TRY(make_tmap_2d(&h->tmB16.hi, h->d_f16, (uint64_t)n, 128, 2, 128));
+        VSB_TRY(make_tmap_2d(&h->tmB16.hi_half, h->d_f16, (uint64_t)n, 128, 2, 64));
+        h->tmB16.lo = h->tmB16.hi;
+        h->tmB16.lo_half = h->tmB16.hi_half;
         VSB_TRY(tc_set_attributes());
     } else {
         VSB_CUDA(cudaStreamSynchronize(h->stream));
@@ -131,16 +134,22 @@ static int exact_ensure_split(vs_exact* h, bool need_lo, cudaStream_t st) {
             VSB_CUDA(cudaMalloc((void**)&h->d_hi, sizeof(float) * (size_t)h->n * 128));
             VSB_CUDA(cudaMalloc((void**)&h->d_lo, sizeof(float) * (size_t)h->n * 128));
             VSB_TRY(launch_prep_rows(h->d_base, h->n, 128, nullptr, h->d_hi, h->d_lo, nullptr, st));
-            VSB_TRY(make_tmap_2d(&h->tmB_lo, h->d_lo, (uint64_t)h->n, 128, 4, 128));
+            VSB_TRY(make_tmap_2d(&h->tmB32.lo, h->d_lo, (uint64_t)h->n, 128, 4, 128));
+            VSB_TRY(make_tmap_2d(&h->tmB32.lo_half, h->d_lo, (uint64_t)h->n, 128, 4, 64));
         }
-        VSB_TRY(make_tmap_2d(&h->tmB_hi, h->d_hi, (uint64_t)h->n, 128, 4, 128));
-        if (!h->d_lo) h->tmB_lo = h->tmB_hi;
+        VSB_TRY(make_tmap_2d(&h->tmB32.hi, h->d_hi, (uint64_t)h->n, 128, 4, 128));
+        VSB_TRY(make_tmap_2d(&h->tmB32.hi_half, h->d_hi, (uint64_t)h->n, 128, 4, 64));
+        if (!h->d_lo) {
+            h->tmB32.lo = h->tmB32.hi;
+            h->tmB32.lo_half = h->tmB32.hi_half;
+        }
         h->split_ready = true;
     }
     if (need_lo && !h->d_lo) {  // 3x search over a TF32-exact base: a real zero lo operand keeps the arithmetic honest
         VSB_CUDA(cudaMalloc((void**)&h->d_lo, sizeof(float) * (size_t)h->n * 128));
         VSB_CUDA(cudaMemsetAsync(h->d_lo, 0, sizeof(float) * (size_t)h->n * 128, st));
-        VSB_TRY(make_tmap_2d(&h->tmB_lo, h->d_lo, (uint64_t)h->n, 128, 4, 128));
+        VSB_TRY(make_tmap_2d(&h->tmB32.lo, h->d_lo, (uint64_t)h->n, 128, 4, 128));
+        VSB_TRY(make_tmap_2d(&h->tmB32.lo_half, h->d_lo, (uint64_t)h->n, 128, 4, 64));
     }
     return VS_OK;
 }
@@ -228,7 +237,7 @@ static int exact_f16_candidate_pass(vs_exact* h, const float* q_dev, int64_t nq,
     CUtensorMap tmA;
     VSB_TRY(make_tmap_2d(&tmA, h->qf16.p, (uint64_t)nq, 128, 2, 128));
     if (h->profile) VSB_CUDA(cudaEventRecord(h->ev0, st));
-    VSB_TRY(launch_exact_tc(tmA, tmA, h->tmB_f16, h->tmB_f16, h->d_norm, h->gthr.as<int32_t>(), (int)nq, plan, ktop, 2,
+    VSB_TRY(launch_exact_tc(tmA, tmA, h->tmB16, h->d_norm, h->gthr.as<int32_t>(), (int)nq, plan, ktop, 2,
                             &qp->key_scale, nullptr, nullptr, h->part_key.as<float>(), h->part_id.as<int32_t>(), st));
     if (h->profile) {
         VSB_CUDA(cudaEventRecord(h->ev1, st));
@@ -379,7 +388,7 @@ int exact_search_core(vs_exact* h, const float* q_dev, int64_t nq, int k, int pr
             // shared per-query thresholds start at a huge finite value (0x7f7f7f7f in the ordered-int encoding)
             VSB_CUDA(cudaMemsetAsync(h->gthr.p, 0x7f, sizeof(int32_t) * (size_t)nq, st));
             if (h->profile && pass == 0) VSB_CUDA(cudaEventRecord(h->ev0, st));
-            VSB_TRY(launch_exact_tc(tmA_hi, tmA_lo, h->tmB_hi, h->tmB_lo, h->d_norm, h->gthr.as<int32_t>(), (int)nq, plan,
+            VSB_TRY(launch_exact_tc(tmA_hi, tmA_lo, h->tmB32, h->d_norm, h->gthr.as<int32_t>(), (int)nq, plan,
                                     ktop, split3 ? 1 : 0, nullptr, lb ? h->lbk.as<float>() : nullptr,
                                     lb ? h->lbi.as<int32_t>() : nullptr, h->part_key.as<float>(), h->part_id.as<int32_t>(), st));
             if (h->profile && pass == 0) {

@@ -401,6 +401,7 @@ int vs_exact_mgpu_create(vs_exact_mgpu_t** out, const float* base, int64_t n, in
     if (!out) return fail(VS_ERR_INVALID, "out handle is NULL");
     *out = nullptr;
     if (!base || n <= 0) return fail(VS_ERR_INVALID, "base is NULL or n <= 0");
+    DeviceGuard guard;  // the caller's current device is left as it was
     int cnt = 0;
     if (cudaGetDeviceCount(&cnt) != cudaSuccess || cnt == 0) {
         cudaGetLastError();
@@ -463,7 +464,10 @@ int vs_exact_mgpu_create(vs_exact_mgpu_t** out, const float* base, int64_t n, in
     return VS_OK;
 }
 
-int vs_exact_mgpu_destroy(vs_exact_mgpu_t* m) { return mgpu_free(m); }
+int vs_exact_mgpu_destroy(vs_exact_mgpu_t* m) {
+    DeviceGuard guard;
+    return mgpu_free(m);
+}
 int vs_exact_mgpu_num_gpus(const vs_exact_mgpu_t* m) { return m ? m->n_gpus : 0; }
 int vs_exact_mgpu_num_shards(const vs_exact_mgpu_t* m) { return m ? m->n_slots : 0; }
 
@@ -473,6 +477,7 @@ int vs_exact_mgpu_search_f32(vs_exact_mgpu_t* m, const float* queries, int64_t n
     if (nq < 0 || k <= 0) return fail(VS_ERR_INVALID, "nq < 0 or k <= 0");
     if (nq == 0) return VS_OK;
     if (!queries || !out_ids || !out_dists) return fail(VS_ERR_INVALID, "NULL buffer");
+    DeviceGuard guard;
     const int G = m->n_gpus;
     const int dim = m->dim;
     const size_t B = block_bytes(nq, k);

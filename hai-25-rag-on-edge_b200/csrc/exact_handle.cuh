@@ -4,6 +4,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include "kernels.cuh"
 #include "vsb_common.cuh"
 
 using vsb::DevBuf;
@@ -25,7 +26,8 @@ struct vs_exact {
     float* d_norm = nullptr;        // [n_tiles*128] +inf padded
     bool base_exact = false;
     bool broken = false;            // vs_exact_refresh() failed half-way
-    CUtensorMap tmB_hi, tmB_lo, tmB_f16;
+    vsb::TcBaseMaps tmB32;          // TF32 hi / lo operand maps (fp32 containers)
+    vsb::TcBaseMaps tmB16;          // scaled fp16 copy (hi == lo)
     cudaStream_t stream = nullptr;
     // workspace (grow-only)
     DevBuf q, qhi, qlo, qf16, qnorm, part_key, part_id, lbk, lbi, out_ids, out_keys, flag, gthr, qparams, unc_list, fb_q,

@@ -16,17 +16,25 @@ TcPlan tc_make_plan(int64_t n, int64_t nq, int num_sms) {
     TcPlan pl{};
     pl.n_tiles = (int)ceil_div64(n, TC_BN);
     pl.n_mtiles = (int)ceil_div64(nq, TC_BM);
-    // few query tiles (small batches): allow enough splits for two units per SM; many query tiles: cap the number of
+    // CTA pairs (two query tiles share every base tile through TMA multicast, VSB_TC_CL=2) are implemented and give
+    // identical results, but measured no gain on B200 (tools/tc_cluster_ab.py, profiles/r2_tc_cluster_ab.txt: the sweep is
+    // bound by shared-memory bandwidth and the epilogue, not by L2 reads) and couple the two CTAs' stalls: independent CTAs
+    // stay the default
+    pl.cl = 1;
+    if (const char* e = getenv("VSB_TC_CL")) pl.cl = atoi(e) == 2 && num_sms >= 2 ? 2 : 1;
+    const int cols = pl.cl == 2 ? (pl.n_mtiles + 1) / 2 : pl.n_mtiles;   // unit columns
+    const int workers = pl.cl == 2 ? num_sms / 2 : num_sms;              // CTAs or CTA pairs
+    // few query tiles (small batches): allow enough splits for two units per worker; many query tiles: cap the number of
     // partial lists per query
-    const int want = std::max(64, (int)ceil_div64(2 * (int64_t)num_sms, pl.n_mtiles));
+    const int want = std::max(64, (int)ceil_div64(2 * (int64_t)workers, cols));
     const int max_splits = std::max(1, std::min(pl.n_tiles / 16, want));
     int best_s = 1;
     double best_cost = 1e30;
     for (int s = 1; s <= std::max(1, max_splits); ++s) {
         const int tps = (pl.n_tiles + s - 1) / s;
         const int s_eff = (pl.n_tiles + tps - 1) / tps;
-        const int64_t units = (int64_t)pl.n_mtiles * s_eff;
-        const int64_t rounds = ceil_div64(units, num_sms);
+        const int64_t units = (int64_t)cols * s_eff;
+        const int64_t rounds = ceil_div64(units, workers);
         // time ~ rounds * tiles per unit (+ a small per-unit overhead measured in tiles)
         const double cost = (double)rounds * (tps + 2.0);
         if (cost < best_cost - 1e-9) {
@@ -36,14 +44,37 @@ TcPlan tc_make_plan(int64_t n, int64_t nq, int num_sms) {
     }
     pl.tiles_per_split = (pl.n_tiles + best_s - 1) / best_s;
     pl.n_splits = (pl.n_tiles + pl.tiles_per_split - 1) / pl.tiles_per_split;
-    pl.grid = (int)std::min<int64_t>((int64_t)pl.n_mtiles * pl.n_splits, num_sms);
+    pl.grid = (int)std::min<int64_t>((int64_t)cols * pl.n_splits, workers) * pl.cl;
     return pl;
 }
 
 template <int KTOP, int MODE, bool HAS_LB>
 static int set_attr_one() {
-    VSB_CUDA(cudaFuncSetAttribute(exact_tc_kernel<KTOP, MODE, HAS_LB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    VSB_CUDA(cudaFuncSetAttribute(exact_tc_kernel<KTOP, MODE, HAS_LB, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   TcSmem<MODE>::TOTAL));
+    VSB_CUDA(cudaFuncSetAttribute(exact_tc_kernel<KTOP, MODE, HAS_LB, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  TcSmem<MODE>::TOTAL));
+    return VS_OK;
+}
+
+// one launch: CL == 2 as clusters of two CTAs (the pair shares the streamed base tiles)
+template <int KTOP, int MODE, bool HAS_LB>
+static int launch_one(const TcPlan& plan, const CUtensorMap& tmA_hi, const CUtensorMap& tmA_lo, const CUtensorMap& tmB_hi,
+                      const CUtensorMap& tmB_lo, const TcParams& p, cudaStream_t st) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)plan.grid);
+    cfg.blockDim = dim3((unsigned)TcSmem<MODE>::THREADS);
+    cfg.dynamicSmemBytes = TcSmem<MODE>::TOTAL;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)plan.cl;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (plan.cl == 2) VSB_CUDA(cudaLaunchKernelEx(&cfg, exact_tc_kernel<KTOP, MODE, HAS_LB, 2>, tmA_hi, tmA_lo, tmB_hi, tmB_lo, p));
+    else VSB_CUDA(cudaLaunchKernelEx(&cfg, exact_tc_kernel<KTOP, MODE, HAS_LB, 1>, tmA_hi, tmA_lo, tmB_hi, tmB_lo, p));
     return VS_OK;
 }
 
@@ -67,9 +98,9 @@ int tc_set_attributes() {
 }
 
 // mode: TC_TF32X1 / TC_TF32X3 (tmA_lo / tmB_lo used by X3 only) / TC_F16 (tmA_hi / tmB_hi are the fp16 maps,
-// *key_scale_dev = -2 / (s_q * s_b); list sizes 16 and 32 only)
-int launch_exact_tc(const CUtensorMap& tmA_hi, const CUtensorMap& tmA_lo, const CUtensorMap& tmB_hi,
-                    const CUtensorMap& tmB_lo, const float* bnorm, int32_t* gthr, int nq, const TcPlan& plan,
+// *key_scale_dev = -2 / (s_q * s_b); list sizes 16 and 32 only).  tmB: full-tile boxes (128 rows) and half-tile boxes
+// (64 rows, used when plan.cl == 2)
+int launch_exact_tc(const CUtensorMap& tmA_hi, const CUtensorMap& tmA_lo, const TcBaseMaps& tmB, const float* bnorm, int32_t* gthr, int nq, const TcPlan& plan,
                     int ktop, int mode, const float* key_scale_dev, const float* lb_key, const int32_t* lb_id, float* part_key,
                     int32_t* part_id, cudaStream_t st) {
     TcParams p{};
@@ -101,8 +132,9 @@ int launch_exact_tc(const CUtensorMap& tmA_hi, const CUtensorMap& tmA_lo, const 
     }
     if (lb_key && ktop != 32) return fail(VS_ERR_INVALID, "tc: lower bound needs the 32-entry list");
     if (lb_key && mode == TC_F16) return fail(VS_ERR_INVALID, "tc: the fp16 candidate pass has no multi-pass mode");
-#define VSB_TC_LAUNCH(KT, MD, LB)                                                                                \
-    exact_tc_kernel<KT, MD, LB><<<plan.grid, TcSmem<MD>::THREADS, TcSmem<MD>::TOTAL, st>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, p)
+    const CUtensorMap& tmB_hi = plan.cl == 2 ? tmB.hi_half : tmB.hi;
+    const CUtensorMap& tmB_lo = plan.cl == 2 ? tmB.lo_half : tmB.lo;
+#define VSB_TC_LAUNCH(KT, MD, LB) VSB_TRY((launch_one<KT, MD, LB>(plan, tmA_hi, tmA_lo, tmB_hi, tmB_lo, p, st)))
 #define VSB_TC_CASE(KT)                              \
     case KT:                                         \
         if (mode == TC_TF32X3)                       \

@@ -35,11 +35,11 @@ constexpr int TC_EPI_GROUPS = 3;  // epilogue warpgroups; tiles rotate over them
 constexpr int TC_THREADS = 128 + 128 * TC_EPI_GROUPS;  // warpgroup 0: TMA producer, MMA issuer, two idle warps
 constexpr int TC_REGS_CTRL = 80, TC_REGS_EPI = 144;   // setmaxnreg budgets: 128*80 + 384*144 == 64K registers
 // TC_F16 adds a fifth warpgroup of four list-keeper warps (one per TMEM lane quadrant): 640 threads start with 96
-// registers (61440); control drops to 24, the keepers rise to 104 (a 32-entry register list per lane), the three
-// epilogue warpgroups to 112 (128*24 + 128*104 + 384*112 = 59392 <= 61440: setmaxnreg.inc can only take what the CTA
-// itself released)
+// registers (61440); control drops to 40, the keepers rise to 104 (a 32-entry register list per lane), the three
+// epilogue warpgroups to 112 (128*40 + 128*104 + 384*112 = 61440: setmaxnreg.inc can only take what the CTA itself
+// released)
 constexpr int TC_THREADS_Q = TC_THREADS + 128;
-constexpr int TC_REGS_CTRL_Q = 24, TC_REGS_KEEP_Q = 104, TC_REGS_EPI_Q = 112;
+constexpr int TC_REGS_CTRL_Q = 40, TC_REGS_KEEP_Q = 104, TC_REGS_EPI_Q = 112;
 constexpr int TC_QN = 128;            // candidate-queue entries per quadrant
 constexpr int TC_QBATCH = 24;         // queued rows that make a batch worth folding
 constexpr int TC_QUANT_REFRESH = 16;  // tiles of one group between reads of the finished units' quantile posts (power of two)
@@ -168,7 +168,13 @@ __device__ __forceinline__ float tc_quantile_cap(const int32_t* gthr, int nq, in
     return c < BIG ? c : __int_as_float(0x7f800000);
 }
 
-template <int KTOP, int MODE, bool HAS_LB>
+// CL = CTAs per cluster (1 or 2).  CL == 2: the two CTAs of a pair work on two DIFFERENT query tiles and the SAME base
+// tiles; each CTA fetches half of every base k-block (64 rows) and TMA multicasts it into both CTAs' rings, so the
+// L2 -> SM traffic of the streamed operand halves (with one query tile per CTA the fp16 / 1xTF32 sweeps are bound by the
+// chip-wide L2 read rate, not by the tensor pipe).  A ring stage is refilled only when BOTH CTAs' MMAs have read it:
+// the `empty` barriers take two arrivals, the second one being the peer's multicast tcgen05.commit.  tmB_* are then the
+// 64-row-box tensor maps.
+template <int KTOP, int MODE, bool HAS_LB, int CL>
 __global__ void __launch_bounds__(TcSmem<MODE>::THREADS, 1)
 exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                 const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
@@ -204,11 +210,15 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     const int lane = threadIdx.x & 31;
+    const int cta_rank = CL == 2 ? (int)cluster_ctarank() : 0;
+    const int worker = CL == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;      // a CTA, or a CTA pair
+    const int n_workers = CL == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int n_mt = CL == 2 ? (p.n_mtiles + 1) >> 1 : p.n_mtiles;               // unit columns: query tiles or tile pairs
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < NSTAGE; ++i) {
             mbar_init(&full[i], 1);
-            mbar_init(&empty[i], 1);
+            mbar_init(&empty[i], CL);
         }
         for (int i = 0; i < TC_NACC; ++i) {
             mbar_init(&acc_full[i], 1);
@@ -235,10 +245,13 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
     }
     tc_fence_before();
     __syncthreads();
+    if (CL == 2) cluster_sync_all();  // the peer's barriers are initialised before anything of ours can signal them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int n_units = p.n_mtiles * p.n_splits;
+    // unit = (query tile [pair], base split), split-major; the odd tile out of an odd tile count is paired with a ghost
+    // (all rows beyond nq: the TMA fills zeros, nothing is written)
+    const int n_units = n_mt * p.n_splits;
 
     if (warp < 4) {
       if constexpr (S::SMEM_LIST)
@@ -262,9 +275,9 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
             int stage = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0;
             int it = 0;
-            for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++it) {
-                const int m_tile = unit % p.n_mtiles;
-                const int split = unit / p.n_mtiles;
+            for (int unit = worker; unit < n_units; unit += n_workers, ++it) {
+                const int m_tile = (unit % n_mt) * CL + cta_rank;
+                const int split = unit / n_mt;
                 mbar_wait(a_empty, (uint32_t)((it & 1) ^ 1));
                 if (leader) {
                     mbar_expect_tx(a_full, (uint32_t)S::A_BYTES);
@@ -292,7 +305,11 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
                                 mbar_arrive(&full[stage]);
                             } else {
                                 mbar_expect_tx(&full[stage], (uint32_t)TC_KB_BYTES);
-                                tma_load_2d(sB + stage * TC_KB_BYTES, &tmB_hi, &full[stage], kb * KB_ELEMS, t * TC_BN);
+                                if (CL == 2)
+                                    tma_load_2d_mcast(sB + stage * TC_KB_BYTES + cta_rank * (TC_KB_BYTES / 2), &tmB_hi, &full[stage],
+                                                      kb * KB_ELEMS, t * TC_BN + cta_rank * (TC_BN / 2), (uint16_t)3);
+                                else
+                                    tma_load_2d(sB + stage * TC_KB_BYTES, &tmB_hi, &full[stage], kb * KB_ELEMS, t * TC_BN);
                             }
                         }
                         if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
@@ -303,7 +320,11 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
                                     mbar_arrive(&full[stage]);
                                 } else {
                                     mbar_expect_tx(&full[stage], (uint32_t)TC_KB_BYTES);
-                                    tma_load_2d(sB + stage * TC_KB_BYTES, &tmB_lo, &full[stage], kb * 32, t * TC_BN);
+                                    if (CL == 2)
+                                        tma_load_2d_mcast(sB + stage * TC_KB_BYTES + cta_rank * (TC_KB_BYTES / 2), &tmB_lo, &full[stage],
+                                                          kb * 32, t * TC_BN + cta_rank * (TC_BN / 2), (uint16_t)3);
+                                    else
+                                        tma_load_2d(sB + stage * TC_KB_BYTES, &tmB_lo, &full[stage], kb * 32, t * TC_BN);
                                 }
                             }
                             if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
@@ -322,8 +343,8 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
             int stage = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0;
             int it = 0;
-            for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++it) {
-                const int split = unit / p.n_mtiles;
+            for (int unit = worker; unit < n_units; unit += n_workers, ++it) {
+                const int split = unit / n_mt;
                 const int t0 = split * p.tiles_per_split;
                 const int t1 = min(t0 + p.tiles_per_split, p.n_tiles);
                 mbar_wait(a_full, (uint32_t)(it & 1));
@@ -356,7 +377,7 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
                                 }
                             }
                         }
-                        if (leader) tc_commit(&empty[stage]);
+                        if (leader) { if (CL == 2) tc_commit_mcast(&empty[stage], (uint16_t)3); else tc_commit(&empty[stage]); }
                         if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
                         if (SPLIT3) {
                             // ---- stage holding x_lo[kb]
@@ -368,7 +389,7 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
                                 for (int ks = 0; ks < 4; ++ks)    // q_hi . x_lo
                                     tc_mma_tf32(d_tmem, a_hi + 2 * ks, b + 2 * ks, idesc, 1u);
                             }
-                            if (leader) tc_commit(&empty[stage]);
+                            if (leader) { if (CL == 2) tc_commit_mcast(&empty[stage], (uint16_t)3); else tc_commit(&empty[stage]); }
                             if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
                         }
                     }
@@ -404,9 +425,9 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         const int qbatch = p.qbatch > 0 ? p.qbatch : TC_QBATCH;
         int next = 0;  // entries consumed so far (monotonic over the whole kernel)
         int it = 0;
-        for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++it) {
-            const int m_tile = unit % p.n_mtiles;
-            const int split = unit / p.n_mtiles;
+        for (int unit = worker; unit < n_units; unit += n_workers, ++it) {
+            const int m_tile = (unit % n_mt) * CL + cta_rank;
+            const int split = unit / n_mt;
             RegTopK<32> top;
             top.init();
             stsv_u32(my_worst, __float_as_uint(INF));
@@ -542,9 +563,9 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         const uint32_t queue_u = smem_u32(sQueue + quad * TC_QN * TC_QENTRY);
         int tcount = 0;
         int it = 0;
-        for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++it) {
-            const int m_tile = unit % p.n_mtiles;
-            const int split = unit / p.n_mtiles;
+        for (int unit = worker; unit < n_units; unit += n_workers, ++it) {
+            const int m_tile = (unit % n_mt) * CL + cta_rank;
+            const int split = unit / n_mt;
             const int t0 = split * p.tiles_per_split;
             const int t1 = min(t0 + p.tiles_per_split, p.n_tiles);
             const int q = m_tile * TC_BM + row;
@@ -591,6 +612,7 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
                     const float thr = fminf(ldsv_f32(sWorst + row), capn);  // kept fresh by the keeper
                     tc_wait_ld();
                     if (c + 1 < CH) tmem_ld32(taddr + (c + 1) * 32, r[(c + 1) & 1]);
+                    if (p.dbg & 16) continue;                // timing experiment: TMEM loads without the arithmetic
                     float d[32];
 #pragma unroll
                     for (int j4 = 0; j4 < 8; ++j4) {
@@ -661,9 +683,9 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         constexpr int CH = TC_BN / 32;        // 32-column chunks per thread per tile
         constexpr bool DB = KTOP <= 16;       // double-buffered TMEM loads while the register budget allows
         int tcount = 0;                       // tiles this CTA has gone through before the current unit
-        for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
-            const int m_tile = unit % p.n_mtiles;
-            const int split = unit / p.n_mtiles;
+        for (int unit = worker; unit < n_units; unit += n_workers) {
+            const int m_tile = (unit % n_mt) * CL + cta_rank;
+            const int split = unit / n_mt;
             const int t0 = split * p.tiles_per_split;
             const int t1 = min(t0 + p.tiles_per_split, p.n_tiles);
             const int q = m_tile * TC_BM + row;
@@ -810,6 +832,7 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
     }
     tc_fence_before();
     __syncthreads();
+    if (CL == 2) cluster_sync_all();  // no CTA leaves while its peer's multicasts / arrivals may still target it
     if (warp == 1) tmem_dealloc(tmem_base, TC_NACC * TC_BN);
 }
 

@@ -44,11 +44,17 @@ int launch_exact_stream(const float* base, const float* bnorm, int64_t n, const 
 // exact_tc.cu -----------------------------------------------------------------------------------
 struct TcPlan {
     int n_tiles, n_mtiles, n_splits, tiles_per_split, grid;
+    int cl;  // CTAs per cluster: 2 = CTA pairs sharing the streamed base tiles (TMA multicast), 1 = independent CTAs
+};
+// tensor maps of a streamed base operand: hi (or the only) part and lo part, as full-tile boxes (128 rows) and as
+// half-tile boxes (64 rows: each CTA of a pair fetches one half and multicasts it)
+struct TcBaseMaps {
+    CUtensorMap hi, lo, hi_half, lo_half;
 };
 TcPlan tc_make_plan(int64_t n, int64_t nq, int num_sms);
 // mode: 0 = 1xTF32, 1 = 3xTF32, 2 = scaled fp16 candidate pass (exact_tc.cuh TcMode); key = bn + (*key_scale_dev) * acc
-int launch_exact_tc(const CUtensorMap& tmA_hi, const CUtensorMap& tmA_lo, const CUtensorMap& tmB_hi,
-                    const CUtensorMap& tmB_lo, const float* bnorm, int32_t* gthr, int nq, const TcPlan& plan,
+int launch_exact_tc(const CUtensorMap& tmA_hi, const CUtensorMap& tmA_lo, const TcBaseMaps& tmB, const float* bnorm,
+                    int32_t* gthr, int nq, const TcPlan& plan,
                     int ktop, int mode, const float* key_scale_dev, const float* lb_key, const int32_t* lb_id, float* part_key,
                     int32_t* part_id, cudaStream_t st);
 int tc_lists_per_split(int mode);  // partial lists written per (split, query): 1 (TC_F16, mode 2) or 3

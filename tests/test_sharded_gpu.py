@@ -325,7 +325,9 @@ def test_ivf_list_shards_and_int8_row_shards_on_one_gpu(G, gpu_vsb, oracle):
     from vsb200 import sharded
 
     dev = torch.device("cuda:0")
-    sptr = torch.cuda.current_stream().cuda_stream
+    st = torch.cuda.Stream()          # a real stream: handle 0 would mean "the handle's own stream" to the C ABI
+    torch.cuda.set_stream(st)
+    sptr = st.cuda_stream
     # ---- IVF
     n, nlist, nq, k, nprobe = 60_000, 128, 257, 10, 16
     base, cent, order, offsets = _make_ivf(vsb, oracle, n, nlist)
@@ -373,6 +375,7 @@ def test_ivf_list_shards_and_int8_row_shards_on_one_gpu(G, gpu_vsb, oracle):
             idx.close()
     vsb.merge_blocks_dev(gathered.data_ptr(), G, B, nq, k, False, oi[:nq].data_ptr(), osc[:nq].data_ptr(), 0, sptr)
     torch.cuda.synchronize()
+    torch.cuda.set_stream(torch.cuda.default_stream())
     m = oracle.int8_multiplier(vsb.QNN_INPUT_SCALE, w_scale, vsb.QNN_OUTPUT_SCALE)
     wi, ws = oracle.int8_search(oracle.quantize_u8(base, w_scale), oracle.quantize_u8(qry, vsb.QNN_INPUT_SCALE), k, m, mode=1)
     assert np.array_equal(oi[:nq].cpu().numpy(), wi) and np.array_equal(osc[:nq].cpu().numpy().astype(np.uint8), ws)

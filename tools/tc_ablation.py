@@ -25,7 +25,8 @@ torch.cuda.synchronize()
 idx = vsb.ExactIndex(base.data_ptr(), n=n)
 idx.set_profile(True)
 st = torch.cuda.Stream()
-for prec, name in ((vsb.PREC_F16_CERT, "f16"),):
+PRECS = {"f16": vsb.PREC_F16_CERT, "1x": vsb.PREC_TF32_1X, "3x": vsb.PREC_3XTF32}
+for prec, name in ((PRECS[os.environ.get("PREC", "f16")], os.environ.get("PREC", "f16")),):
     for dbg in flags:
         os.environ["VSB_TC_DBG"] = str(dbg)
         ts = []
