@@ -43,6 +43,20 @@ static encode_tiled_fn get_encode_fn() {
 }
 
 // 2D row-major [rows x cols] matrix of `elem_bytes` elements, box = 128 B x box_rows, 128-B swizzle, OOB -> 0
+int make_tmap_fold(CUtensorMap* out, const void* gptr, uint64_t rows, uint32_t box_rows) {
+    encode_tiled_fn fn = get_encode_fn();
+    if (!fn) return fail(VS_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t gdim[2] = {(cuuint64_t)TC_FOLD_COLS, rows};
+    cuuint64_t gstr[1] = {(cuuint64_t)TC_FOLD_COLS * 2};
+    cuuint32_t box[2] = {(cuuint32_t)TC_FOLD_COLS, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(gptr), gdim, gstr, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(VS_ERR_CUDA, "cuTensorMapEncodeTiled (norm block) failed with code " + std::to_string((int)r));
+    return VS_OK;
+}
+
 int make_tmap_2d(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_t cols, int elem_bytes, uint32_t box_rows) {
     encode_tiled_fn fn = get_encode_fn();
     if (!fn) return fail(VS_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
@@ -71,9 +85,10 @@ int exact_free(vs_exact* h) {
     if (h->d_hi && h->d_hi != h->d_base) cudaFree(h->d_hi);
     if (h->d_lo) cudaFree(h->d_lo);
     if (h->d_f16) cudaFree(h->d_f16);
+    if (h->d_fold) cudaFree(h->d_fold);
     if (h->d_norm) cudaFree(h->d_norm);
     for (DevBuf* b : {&h->q, &h->qhi, &h->qlo, &h->qf16, &h->qnorm, &h->part_key, &h->part_id, &h->lbk, &h->lbi, &h->out_ids,
-                      &h->out_keys, &h->flag, &h->gthr, &h->qparams, &h->unc_list, &h->fb_q, &h->fb_ids, &h->fb_keys})
+                      &h->out_keys, &h->flag, &h->gthr, &h->qparams, &h->qfold, &h->unc_list, &h->fb_q, &h->fb_ids, &h->fb_keys})
         b->release();
     if (h->h_flag) cudaFreeHost(h->h_flag);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -112,12 +127,15 @@ static int exact_build(vs_exact* h) {
         VSB_CUDA(cudaMemcpyAsync(&h->h_flag[3], scratch, sizeof(float), cudaMemcpyDeviceToHost, h->stream));
         VSB_CUDA(cudaMalloc(&h->d_f16, 2 * (size_t)n * dim));
         VSB_TRY(launch_to_half_scaled(h->d_base, n * dim, h->s_b, nullptr, h->d_f16, h->stream));
+        // the norm term as an extra K = 16 operand block: three fp16 pieces of s_b^2 ||x||^2 / 2 per row
+        VSB_CUDA(cudaMalloc(&h->d_fold, (size_t)n_pad * TC_FOLD_COLS * 2));
+        VSB_TRY(launch_norm_pieces(h->d_norm, n, n_pad, h->s_b, h->d_fold, h->stream));
         VSB_CUDA(cudaStreamSynchronize(h->stream));
         memcpy(&h->bn_max, &h->h_flag[3], sizeof(float));
         VSB_TRY(make_tmap_2d(&h->tmB16.hi, h->d_f16, (uint64_t)n, 128, 2, 128));
-        VSB_TRY(make_tmap_2d(&h->tmB16.hi_half, h->d_f16, (uint64_t)n, 128, 2, 64));
-        h->tmB16.lo = h->tmB16.hi;
-        h->tmB16.lo_half = h->tmB16.hi_half;
+        VSB_TRY(make_tmap_fold(&h->tmB16.lo, h->d_fold, (uint64_t)n_pad, 128));
+        h->tmB16.hi_half = h->tmB16.hi;  // CTA pairs are not used by the fp16 pass
+        h->tmB16.lo_half = h->tmB16.lo;
         VSB_TRY(tc_set_attributes());
     } else {
         VSB_CUDA(cudaStreamSynchronize(h->stream));
@@ -220,12 +238,13 @@ static int exact_f16_candidate_pass(vs_exact* h, const float* q_dev, int64_t nq,
     VSB_TRY(h->qnorm.reserve(sizeof(float) * (size_t)nq));
     VSB_TRY(h->qf16.reserve(2 * (size_t)nq * 128));
     VSB_TRY(h->qparams.reserve(sizeof(TcQueryParams)));
+    VSB_TRY(h->qfold.reserve((size_t)128 * TC_FOLD_COLS * 2));
     VSB_CUDA(cudaMemsetAsync(flag + 1, 0, 2 * sizeof(int), st));
     VSB_TRY(launch_query_prep(q_dev, nq, h->qnorm.as<float>(), reinterpret_cast<float*>(flag + 2), st));
     TcQueryParams* qp = h->qparams.as<TcQueryParams>();
-    VSB_TRY(launch_tc_query_params(reinterpret_cast<const float*>(flag + 2), h->s_b, h->bn_max, qp, st));
-    VSB_TRY(launch_to_half_scaled(q_dev, nq * 128, 1.f, qp, h->qf16.p, st));
-    const TcPlan plan = tc_make_plan(h->n, nq, h->num_sms);
+    VSB_TRY(launch_tc_query_params(reinterpret_cast<const float*>(flag + 2), h->s_b, h->bn_max, qp, h->qfold.p, st));
+    VSB_TRY(launch_to_half_scaled(q_dev, nq * 128, 1.f, qp, h->qf16.p, st));  // the NEGATED scaled copy
+    const TcPlan plan = tc_make_plan(h->n, nq, h->num_sms, 2);
     const int n_lists = plan.n_splits * tc_lists_per_split(2);
     VSB_TRY(h->part_key.reserve(sizeof(float) * (size_t)n_lists * nq * ktop));
     VSB_TRY(h->part_id.reserve(sizeof(int32_t) * (size_t)n_lists * nq * ktop));
@@ -234,11 +253,12 @@ static int exact_f16_candidate_pass(vs_exact* h, const float* q_dev, int64_t nq,
     const size_t gthr_words = (size_t)nq * (1 + 2 * (size_t)plan.n_splits);
     VSB_TRY(h->gthr.reserve(sizeof(int32_t) * gthr_words));
     VSB_CUDA(cudaMemsetAsync(h->gthr.p, 0x7f, sizeof(int32_t) * gthr_words, st));
-    CUtensorMap tmA;
+    CUtensorMap tmA, tmAe;
     VSB_TRY(make_tmap_2d(&tmA, h->qf16.p, (uint64_t)nq, 128, 2, 128));
+    VSB_TRY(make_tmap_fold(&tmAe, h->qfold.p, 128, 128));
     if (h->profile) VSB_CUDA(cudaEventRecord(h->ev0, st));
-    VSB_TRY(launch_exact_tc(tmA, tmA, h->tmB16, h->d_norm, h->gthr.as<int32_t>(), (int)nq, plan, ktop, 2,
-                            &qp->key_scale, nullptr, nullptr, h->part_key.as<float>(), h->part_id.as<int32_t>(), st));
+    VSB_TRY(launch_exact_tc(tmA, tmAe, h->tmB16, h->d_norm, h->gthr.as<int32_t>(), (int)nq, h->n, plan, ktop, 2,
+                            nullptr, nullptr, nullptr, h->part_key.as<float>(), h->part_id.as<int32_t>(), st));
     if (h->profile) {
         VSB_CUDA(cudaEventRecord(h->ev1, st));
         h->ev_valid = true;
@@ -374,7 +394,7 @@ int exact_search_core(vs_exact* h, const float* q_dev, int64_t nq, int k, int pr
         }
         VSB_TRY(exact_ensure_split(h, split3, st));
         h->last_precision = split3 ? VS_PREC_FP32_3XTF32 : VS_PREC_TF32_1X;
-        const TcPlan plan = tc_make_plan(h->n, nq, h->num_sms);
+        const TcPlan plan = tc_make_plan(h->n, nq, h->num_sms, split3 ? 1 : 0);
         const int n_lists = plan.n_splits * tc_lists_per_split(split3 ? 1 : 0);
         VSB_TRY(h->part_key.reserve(sizeof(float) * (size_t)n_lists * nq * ktop));
         VSB_TRY(h->part_id.reserve(sizeof(int32_t) * (size_t)n_lists * nq * ktop));
@@ -388,7 +408,7 @@ int exact_search_core(vs_exact* h, const float* q_dev, int64_t nq, int k, int pr
             // shared per-query thresholds start at a huge finite value (0x7f7f7f7f in the ordered-int encoding)
             VSB_CUDA(cudaMemsetAsync(h->gthr.p, 0x7f, sizeof(int32_t) * (size_t)nq, st));
             if (h->profile && pass == 0) VSB_CUDA(cudaEventRecord(h->ev0, st));
-            VSB_TRY(launch_exact_tc(tmA_hi, tmA_lo, h->tmB32, h->d_norm, h->gthr.as<int32_t>(), (int)nq, plan,
+            VSB_TRY(launch_exact_tc(tmA_hi, tmA_lo, h->tmB32, h->d_norm, h->gthr.as<int32_t>(), (int)nq, h->n, plan,
                                     ktop, split3 ? 1 : 0, nullptr, lb ? h->lbk.as<float>() : nullptr,
                                     lb ? h->lbi.as<int32_t>() : nullptr, h->part_key.as<float>(), h->part_id.as<int32_t>(), st));
             if (h->profile && pass == 0) {
@@ -478,9 +498,10 @@ int vs_exact_refresh(vs_exact_t* h) {
     if (h->d_hi && h->d_hi != h->d_base) cudaFree(h->d_hi);
     if (h->d_lo) cudaFree(h->d_lo);
     if (h->d_f16) cudaFree(h->d_f16);
+    if (h->d_fold) cudaFree(h->d_fold);
     if (h->d_norm) cudaFree(h->d_norm);
     h->d_hi = h->d_lo = h->d_norm = nullptr;
-    h->d_f16 = nullptr;
+    h->d_f16 = h->d_fold = nullptr;
     h->split_ready = false;
     const int rc = exact_build(h);
     h->broken = rc != VS_OK;  // a failed rebuild leaves no usable buffers: every later search is refused
@@ -564,6 +585,8 @@ int vs_exact_debug_f16_candidates(vs_exact_t* h, const float* queries, int64_t n
     VSB_CUDA(cudaMemcpyAsync(qn.data(), h->qnorm.p, sizeof(float) * (size_t)nq, cudaMemcpyDeviceToHost, st));
     VSB_CUDA(cudaMemcpyAsync(&qp, h->qparams.p, sizeof(qp), cudaMemcpyDeviceToHost, st));
     VSB_CUDA(cudaStreamSynchronize(st));
+    if (!qp.fold_ok) return fail(VS_ERR_UNSUPPORTED, "query / base magnitudes too far apart for the fp16 candidate pass");
+    for (int64_t i = 0; i < nq * ktop; ++i) out_keys[i] *= qp.key_unscale;  // accumulator units -> distance units (exact)
     for (int64_t i = 0; i < nq; ++i) out_bound[i] = qp.cert_a * sqrtf(qn[(size_t)i]) + qp.cert_b;
     return VS_OK;
 }

@@ -156,7 +156,7 @@ static int int8_search_core(vs_int8* h, const float* q_dev, int64_t nq, int k, i
     for (int c = 1; c < rep; ++c)
         VSB_CUDA(cudaMemcpyAsync(h->q_u8.as<uint8_t>() + (size_t)c * (128 / rep) * 128, h->q_u8.p, (size_t)nq * 128,
                                  cudaMemcpyDeviceToDevice, st));
-    const TcPlan plan = tc_make_plan(h->n, nq, h->num_sms);
+    const TcPlan plan = tc_make_plan(h->n, nq, h->num_sms, 2);  // independent CTAs (no pair mode in this kernel)
     const int n_lists = plan.n_splits * int8_lists_per_split() * rep;
     VSB_TRY(h->part_key.reserve(sizeof(float) * (size_t)n_lists * nq * ktop));
     VSB_TRY(h->part_id.reserve(sizeof(int32_t) * (size_t)n_lists * nq * ktop));

@@ -20,6 +20,7 @@ struct vs_exact {
     float* d_hi = nullptr;          // TF32 split, built on first use (dim == 128 only); d_hi aliases d_base when the
     float* d_lo = nullptr;          // base is TF32-exact
     bool split_ready = false;
+    void* d_fold = nullptr;         // [n_pad x 16] fp16: the norm term s_b^2 ||x||^2 / 2 as an extra K = 16 operand block
     void* d_f16 = nullptr;          // [n x 128] fp16 copy scaled by s_b (candidate pass)
     float s_b = 1.f;                // power-of-two scale of the fp16 copy
     float bn_max = 0.f;             // max ||x||^2
@@ -30,7 +31,7 @@ struct vs_exact {
     vsb::TcBaseMaps tmB16;          // scaled fp16 copy (hi == lo)
     cudaStream_t stream = nullptr;
     // workspace (grow-only)
-    DevBuf q, qhi, qlo, qf16, qnorm, part_key, part_id, lbk, lbi, out_ids, out_keys, flag, gthr, qparams, unc_list, fb_q,
+    DevBuf q, qhi, qlo, qf16, qnorm, part_key, part_id, lbk, lbi, out_ids, out_keys, flag, gthr, qparams, qfold, unc_list, fb_q,
         fb_ids, fb_keys;
     int* h_flag = nullptr;  // pinned: [0] exactness flag, [1] uncertified count
     int last_launches = 0;

@@ -12,7 +12,7 @@ namespace vsb {
 // Split the base into n_splits contiguous tile ranges so that n_mtiles * n_splits units fill the grid in an
 // (almost) integral number of rounds.  More splits = better balance but more partial lists and more list
 // warm-up; each split keeps at least 16 tiles unless the problem is tiny.
-TcPlan tc_make_plan(int64_t n, int64_t nq, int num_sms) {
+TcPlan tc_make_plan(int64_t n, int64_t nq, int num_sms, int mode) {
     TcPlan pl{};
     pl.n_tiles = (int)ceil_div64(n, TC_BN);
     pl.n_mtiles = (int)ceil_div64(nq, TC_BM);
@@ -21,7 +21,7 @@ TcPlan tc_make_plan(int64_t n, int64_t nq, int num_sms) {
     // bound by shared-memory bandwidth and the epilogue, not by L2 reads) and couple the two CTAs' stalls: independent CTAs
     // stay the default
     pl.cl = 1;
-    if (const char* e = getenv("VSB_TC_CL")) pl.cl = atoi(e) == 2 && num_sms >= 2 ? 2 : 1;
+    if (const char* e = getenv("VSB_TC_CL")) pl.cl = atoi(e) == 2 && num_sms >= 2 && mode != TC_F16 ? 2 : 1;
     const int cols = pl.cl == 2 ? (pl.n_mtiles + 1) / 2 : pl.n_mtiles;   // unit columns
     const int workers = pl.cl == 2 ? num_sms / 2 : num_sms;              // CTAs or CTA pairs
     // few query tiles (small batches): allow enough splits for two units per worker; many query tiles: cap the number of
@@ -52,8 +52,9 @@ template <int KTOP, int MODE, bool HAS_LB>
 static int set_attr_one() {
     VSB_CUDA(cudaFuncSetAttribute(exact_tc_kernel<KTOP, MODE, HAS_LB, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   TcSmem<MODE>::TOTAL));
-    VSB_CUDA(cudaFuncSetAttribute(exact_tc_kernel<KTOP, MODE, HAS_LB, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  TcSmem<MODE>::TOTAL));
+    if constexpr (MODE != TC_F16)
+        VSB_CUDA(cudaFuncSetAttribute(exact_tc_kernel<KTOP, MODE, HAS_LB, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      TcSmem<MODE>::TOTAL));
     return VS_OK;
 }
 
@@ -73,8 +74,14 @@ static int launch_one(const TcPlan& plan, const CUtensorMap& tmA_hi, const CUten
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (plan.cl == 2) VSB_CUDA(cudaLaunchKernelEx(&cfg, exact_tc_kernel<KTOP, MODE, HAS_LB, 2>, tmA_hi, tmA_lo, tmB_hi, tmB_lo, p));
-    else VSB_CUDA(cudaLaunchKernelEx(&cfg, exact_tc_kernel<KTOP, MODE, HAS_LB, 1>, tmA_hi, tmA_lo, tmB_hi, tmB_lo, p));
+    if constexpr (MODE != TC_F16) {
+        if (plan.cl == 2) {
+            VSB_CUDA(cudaLaunchKernelEx(&cfg, exact_tc_kernel<KTOP, MODE, HAS_LB, 2>, tmA_hi, tmA_lo, tmB_hi, tmB_lo, p));
+            return VS_OK;
+        }
+    }
+    if (plan.cl != 1) return fail(VS_ERR_INVALID, "tc: CTA pairs are not available for this mode");
+    VSB_CUDA(cudaLaunchKernelEx(&cfg, exact_tc_kernel<KTOP, MODE, HAS_LB, 1>, tmA_hi, tmA_lo, tmB_hi, tmB_lo, p));
     return VS_OK;
 }
 
@@ -100,7 +107,8 @@ int tc_set_attributes() {
 // mode: TC_TF32X1 / TC_TF32X3 (tmA_lo / tmB_lo used by X3 only) / TC_F16 (tmA_hi / tmB_hi are the fp16 maps,
 // *key_scale_dev = -2 / (s_q * s_b); list sizes 16 and 32 only).  tmB: full-tile boxes (128 rows) and half-tile boxes
 // (64 rows, used when plan.cl == 2)
-int launch_exact_tc(const CUtensorMap& tmA_hi, const CUtensorMap& tmA_lo, const TcBaseMaps& tmB, const float* bnorm, int32_t* gthr, int nq, const TcPlan& plan,
+int launch_exact_tc(const CUtensorMap& tmA_hi, const CUtensorMap& tmA_lo, const TcBaseMaps& tmB, const float* bnorm, int32_t* gthr, int nq,
+                    int64_t n_rows, const TcPlan& plan,
                     int ktop, int mode, const float* key_scale_dev, const float* lb_key, const int32_t* lb_id, float* part_key,
                     int32_t* part_id, cudaStream_t st) {
     TcParams p{};
@@ -115,8 +123,9 @@ int launch_exact_tc(const CUtensorMap& tmA_hi, const CUtensorMap& tmA_lo, const 
     p.n_mtiles = plan.n_mtiles;
     p.n_splits = plan.n_splits;
     p.tiles_per_split = plan.tiles_per_split;
+    p.n_rem = (int)(n_rows % TC_BN);
     p.key_scale_ptr = key_scale_dev;
-    if (mode == TC_F16 && !key_scale_dev) return fail(VS_ERR_INVALID, "tc: fp16 pass needs the device-side key scale");
+    if ((int64_t)plan.n_tiles != ceil_div64(n_rows, TC_BN)) return fail(VS_ERR_INVALID, "tc: plan does not match the row count");
     {
         const char* e = getenv("VSB_TC_DBG");
         p.dbg = e ? atoi(e) : 0;

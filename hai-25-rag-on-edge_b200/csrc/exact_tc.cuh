@@ -54,25 +54,33 @@ constexpr int TC_THR_REFRESH = 4; // tiles of one group between reads of the sha
 //              per query, that no true neighbour can have been missed.
 enum TcMode : int { TC_TF32X1 = 0, TC_TF32X3 = 1, TC_F16 = 2 };
 
+constexpr int TC_FOLD_BYTES = 128 * 32;  // the K = 16 norm block of a 128-row operand tile: 128 rows x 32 B (SWIZZLE_32B)
+
 template <int MODE>
 struct TcSmem {
     static constexpr bool SPLIT3 = MODE == TC_TF32X3;
     static constexpr int NKB = MODE == TC_F16 ? 2 : 4;  // 128-byte k-blocks per row (128 fp16 = 256 B, 128 fp32 = 512 B)
-    static constexpr int A_BYTES = (SPLIT3 ? 2 : 1) * NKB * TC_KB_BYTES;
+    // TC_F16 folds the norm term into the MMA: one extra K = 16 block on both operands (kernels.cuh, TC_FOLD_COLS)
+    static constexpr bool FOLD = MODE == TC_F16;
+    static constexpr int A_BYTES = (SPLIT3 ? 2 : 1) * NKB * TC_KB_BYTES + (FOLD ? TC_FOLD_BYTES : 0);
     // TC_F16 keeps ONE candidate list per query row in the registers of dedicated list-keeper warps that are fed
     // through per-quadrant shared-memory queues; the other modes keep three per-thread register lists per row in the
     // epilogue warps themselves (their query tile leaves no room for the queues: 64 / 128 KB)
     static constexpr bool SMEM_LIST = MODE == TC_F16;
     static constexpr int THREADS = SMEM_LIST ? TC_THREADS_Q : TC_THREADS;
-    static constexpr int NSTAGE = MODE == TC_F16 ? 7 : (SPLIT3 ? 5 : 8);
-    static constexpr int B_BYTES = NSTAGE * TC_KB_BYTES;
-    static constexpr int NORM_BYTES = TC_NACC * TC_BN * 4;
+    // ring of base operand stages: TC_F16 one whole tile per stage (two k-blocks + the norm block, 36 KB), the TF32 modes one
+    // k-block per stage
+    static constexpr int NSTAGE = MODE == TC_F16 ? 3 : (SPLIT3 ? 5 : 8);
+    static constexpr int BSTAGE = MODE == TC_F16 ? 2 * TC_KB_BYTES + TC_FOLD_BYTES : TC_KB_BYTES;
+    static constexpr int B_BYTES = NSTAGE * BSTAGE;
+    static constexpr int NORM_BYTES = FOLD ? 0 : TC_NACC * TC_BN * 4;
     static constexpr int PUB_BYTES = SMEM_LIST ? 0 : TC_EPI_GROUPS * TC_BM * 8;  // per (group, query row): {key, unit tag}
     static constexpr int STAGE_BYTES = SMEM_LIST ? 4 * TC_QN * TC_QENTRY : 0;       // candidate queues, one per quadrant
     static constexpr int AUX_BYTES = SMEM_LIST ? TC_BM * 8 + 4 * TC_QN * 4 + 64 : 0;  // worst kept key per row, entry mask per row, ready words, tail/head
     static constexpr int BAR_BYTES = 1024;
     static constexpr int TOTAL = A_BYTES + B_BYTES + NORM_BYTES + PUB_BYTES + STAGE_BYTES + AUX_BYTES + BAR_BYTES +
                                  1024;  // + slack for 1024-B alignment
+    static_assert(TOTAL <= 227 * 1024, "shared memory budget");
 };
 
 struct TcParams {
@@ -88,7 +96,9 @@ struct TcParams {
     int n_mtiles;        // ceil(nq / 128)
     int n_splits;
     int tiles_per_split;
-    const float* key_scale_ptr;  // TC_F16: key = bn + (*key_scale_ptr) * acc, -2 / (s_q * s_b), derived on the device
+    int n_rem;           // rows of the last base tile (n % 128, 0 = full): TC_F16 masks the columns beyond (the norm block cannot
+                         // carry +inf)
+    const float* key_scale_ptr;  // unused (TC_F16 keys stay in accumulator units: key = acc * 2 / (s_q * s_b), kernels.cuh)
     unsigned long long* stats;  // debug counters (VSB_TC_STATS) or nullptr: [0] warp slow-path entries, [1] lane entries,
                          // [2] qualifying elements, [3] insertions
     int qbatch;          // TC_F16: queued rows that make a batch worth folding (0 = default)
@@ -272,6 +282,46 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
                     tma_prefetch_desc(&tmB_lo);
                 }
             }
+            if constexpr (MODE == TC_F16) {
+              // one ring stage = one whole base tile: k-blocks 0 and 1 (64 fp16 each) + the norm block (16 fp16, SWIZZLE_32B);
+              // tmA_lo / tmB_lo are the norm-block maps
+              static_assert(CL == 1, "the fp16 pass runs with independent CTAs");
+              if (leader) {
+                  tma_prefetch_desc(&tmA_lo);
+                  tma_prefetch_desc(&tmB_lo);
+              }
+              int stage = 0;
+              uint32_t phase = 0;
+              int it = 0;
+              for (int unit = worker; unit < n_units; unit += n_workers, ++it) {
+                  const int m_tile = unit % n_mt;
+                  const int split = unit / n_mt;
+                  mbar_wait(a_empty, (uint32_t)((it & 1) ^ 1));
+                  if (leader) {
+                      mbar_expect_tx(a_full, (uint32_t)S::A_BYTES);
+                      tma_load_2d(sA, &tmA_hi, a_full, 0, m_tile * TC_BM);
+                      tma_load_2d(sA + TC_KB_BYTES, &tmA_hi, a_full, 64, m_tile * TC_BM);
+                      tma_load_2d(sA + 2 * TC_KB_BYTES, &tmA_lo, a_full, 0, 0);  // the same 128 x 16 constants for every tile
+                  }
+                  const int t0 = split * p.tiles_per_split;
+                  const int t1 = min(t0 + p.tiles_per_split, p.n_tiles);
+                  for (int t = t0; t < t1; ++t) {
+                      mbar_wait(&empty[stage], phase ^ 1);
+                      if (leader) {
+                          uint8_t* dst = sB + stage * S::BSTAGE;
+                          if (p.dbg & 8) {
+                              mbar_arrive(&full[stage]);
+                          } else {
+                              mbar_expect_tx(&full[stage], (uint32_t)S::BSTAGE);
+                              tma_load_2d(dst, &tmB_hi, &full[stage], 0, t * TC_BN);
+                              tma_load_2d(dst + TC_KB_BYTES, &tmB_hi, &full[stage], 64, t * TC_BN);
+                              tma_load_2d(dst + 2 * TC_KB_BYTES, &tmB_lo, &full[stage], 0, t * TC_BN);
+                          }
+                      }
+                      if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                  }
+              }
+            } else {
             int stage = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0;
             int it = 0;
@@ -332,6 +382,7 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
                     }
                 }
             }
+            }
         }
     } else if (warp == 1) {
         // ===================================== MMA issuer =======================================
@@ -343,6 +394,42 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
             int stage = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0;
             int it = 0;
+            if constexpr (MODE == TC_F16) {
+              // 9 instructions per tile: 2 k-blocks x 4 (K = 16 each) of  (-s_q q) . (s_b x)  and the norm block
+              // (2^rho constants) . (pieces of s_b^2 ||x||^2 / 2):  acc = (s_q s_b / 2) (||x||^2 - 2 q.x)
+              const uint64_t a_e = umma_desc_sw32(sA_u + 2 * TC_KB_BYTES);
+              for (int unit = worker; unit < n_units; unit += n_workers, ++it) {
+                  const int split = unit / n_mt;
+                  const int t0 = split * p.tiles_per_split;
+                  const int t1 = min(t0 + p.tiles_per_split, p.n_tiles);
+                  mbar_wait(a_full, (uint32_t)(it & 1));
+                  tc_fence_after();
+                  for (int t = t0; t < t1; ++t) {
+                      mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+                      mbar_wait(&full[stage], phase);
+                      tc_fence_after();
+                      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TC_BN);
+                      const uint32_t b_u = sB_u + stage * S::BSTAGE;
+                      if (!(p.dbg & 4) && leader) {
+#pragma unroll
+                          for (int kb = 0; kb < 2; ++kb) {
+                              const uint64_t a = umma_desc_sw128(sA_u + kb * TC_KB_BYTES);
+                              const uint64_t b = umma_desc_sw128(b_u + kb * TC_KB_BYTES);
+#pragma unroll
+                              for (int ks = 0; ks < 4; ++ks) tc_mma_f16(d_tmem, a + 2 * ks, b + 2 * ks, idesc, (kb | ks) ? 1u : 0u);
+                          }
+                          tc_mma_f16(d_tmem, a_e, umma_desc_sw32(b_u + 2 * TC_KB_BYTES), idesc, 1u);
+                      }
+                      if (leader) {
+                          tc_commit(&empty[stage]);
+                          tc_commit(&acc_full[acc]);
+                      }
+                      if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                      if (++acc == TC_NACC) { acc = 0; acc_phase ^= 1; }
+                  }
+                  if (leader) tc_commit(a_empty);
+              }
+            } else
             for (int unit = worker; unit < n_units; unit += n_workers, ++it) {
                 const int split = unit / n_mt;
                 const int t0 = split * p.tiles_per_split;
@@ -558,7 +645,6 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         const int grp = (warp - 4) >> 2;
         const int row = quad * 32 + lane;
         const float INF = __int_as_float(0x7f800000);
-        const float key_scale = __ldg(p.key_scale_ptr);
         constexpr int CH = TC_BN / 32;
         const uint32_t queue_u = smem_u32(sQueue + quad * TC_QN * TC_QENTRY);
         int tcount = 0;
@@ -598,13 +684,13 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
                     if ((j & (TC_QUANT_REFRESH - 1)) == 0) cap = fminf(cap, tc_quantile_cap(p.gthr, p.nq, p.n_splits, q));
                 }
                 const float capn = valid ? next_up(cap) : -INF;  // rows beyond the last query never qualify
-                mbar_wait(&n_full[acc], acc_phase);
                 mbar_wait(&acc_full[acc], acc_phase);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * TC_BN);
-                const uint32_t bn_s = smem_u32(sN + acc * TC_BN);
                 uint32_t r[2][32];
                 const bool skip = (p.dbg & 1) || !quad_live;
+                // the last base tile may be ragged: its missing rows arrive as zeros (TMA fill) and would rank as key 0
+                const int live_cols = (t == p.n_tiles - 1 && p.n_rem) ? p.n_rem : TC_BN;
                 if (!skip) tmem_ld32(taddr, r[0]);
 #pragma unroll
                 for (int c = 0; c < CH; ++c) {
@@ -613,15 +699,14 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
                     tc_wait_ld();
                     if (c + 1 < CH) tmem_ld32(taddr + (c + 1) * 32, r[(c + 1) & 1]);
                     if (p.dbg & 16) continue;                // timing experiment: TMEM loads without the arithmetic
+                    // the accumulator IS the ranking key (in units of s_q s_b / 2): norm and dot product were combined by
+                    // the tensor core, nothing to add here
                     float d[32];
 #pragma unroll
-                    for (int j4 = 0; j4 < 8; ++j4) {
-                        const float4 bn = lds128(bn_s + (uint32_t)(c * 32 + 4 * j4) * 4u);  // smem broadcast
-                        const uint32_t* rr = r[c & 1] + 4 * j4;
-                        d[4 * j4 + 0] = fmaf(key_scale, __uint_as_float(rr[0]), bn.x);
-                        d[4 * j4 + 1] = fmaf(key_scale, __uint_as_float(rr[1]), bn.y);
-                        d[4 * j4 + 2] = fmaf(key_scale, __uint_as_float(rr[2]), bn.z);
-                        d[4 * j4 + 3] = fmaf(key_scale, __uint_as_float(rr[3]), bn.w);
+                    for (int jj = 0; jj < 32; ++jj) d[jj] = __uint_as_float(r[c & 1][jj]);
+                    if (live_cols < TC_BN) {
+#pragma unroll
+                        for (int jj = 0; jj < 32; ++jj) d[jj] = (c * 32 + jj < live_cols) ? d[jj] : INF;
                     }
                     float m[16];  // min tree (the compiler folds it into 3-input FMNMX3)
 #pragma unroll

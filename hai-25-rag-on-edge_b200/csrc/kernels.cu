@@ -154,48 +154,96 @@ int launch_absmax_f32(const float* x, int64_t count, float* out_zeroed, cudaStre
     return VS_OK;
 }
 
-// power-of-two scale that brings absmax into [2^14, 2^15): fp16 keeps 11 significant bits for everything above
-// 2^-14 in scaled units (i.e. 2^-29 of the largest magnitude)
+// power-of-two scale that brings absmax into [2^10, 2^11): fp16 keeps 11 significant bits for everything above 2^-14 in
+// scaled units (2^-25 of the largest magnitude), integers up to 2048 stay exact, and the norm term s_b^2 * bn / 2 <= 2^28
+// fits three fp16 pieces (below)
 __host__ __device__ inline float f16_scale_for(float absmax) {
     if (!(absmax > 0.f) || !(absmax < 3.0e38f)) return 1.0f;
     int e;
     frexpf(absmax, &e);  // absmax = m * 2^e, m in [0.5, 1)
-    int se = 15 - e;
+    int se = 11 - e;
     se = se < -100 ? -100 : (se > 100 ? 100 : se);
     return ldexpf(1.0f, se);
 }
 float f16_scale_host(float absmax) { return f16_scale_for(absmax); }
 
-// TcQueryParams (kernels.cuh): scale of the query copy, key factor and the two certification constants.
-//   |key_f16 - key_exact| <= cert_a * sqrt(qn) + cert_b   with, per element, |x^ - x| <= eps|x| + u (eps = 2^-11,
-//   u = 2^-25 / scale: half the fp16 subnormal spacing), Cauchy-Schwarz for sum|q||x| <= sqrt(qn * bn_max) and
-//   sum|v| <= sqrt(128 * ||v||^2), plus 2^-15 * sum|q||x| for the tensor core's fp32 accumulation, times 1.02,
-//   plus the fp32 rounding of the refined distances themselves (4e-6 * (qn + bn_max), folded into cert_b per query
-//   by the merge kernel).
-__global__ void tc_query_params_kernel(const float* __restrict__ q_absmax, float s_b, float bn_max, TcQueryParams* out) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    const float s_q = f16_scale_for(*q_absmax);
-    const float eps = 1.0f / 2048.0f;
-    const float A = 2.0f * eps + eps * eps + 1.0f / 32768.0f;
-    const float u_q = ldexpf(1.0f, -25) / s_q, u_b = ldexpf(1.0f, -25) / s_b;
-    TcQueryParams r;
-    r.s_q = s_q;
-    r.key_scale = -2.0f / (s_q * s_b);
-    r.cert_a = 2.04f * (A * sqrtf(bn_max) + u_b * sqrtf(128.0f));
-    r.cert_b = 2.04f * (u_q * sqrtf(128.0f * bn_max) + 128.0f * u_q * u_b);
-    r.bn_max = bn_max;
-    *out = r;
+// Base side of the norm block: U = s_b^2 * bn / 2 (<= 2^28) as three fp16 pieces of 11 bits each,
+// U = 2^13 * p1 + 2^2 * p2 + 2^-8 * p3 (residual <= 2^-5: 33 bits cover the 24-bit fp32 norm exactly unless a piece lands in the
+// fp16 subnormals, whose spacing is 2^-32 in U units).  Row layout {p1 x8, p2 x4, p3, 0, 0, 0}; rows >= n are zero (their
+// columns are masked in the kernel's last tile).
+__global__ void norm_pieces_kernel(const float* __restrict__ bnorm, int64_t n, int64_t n_pad, float s_b, __half* __restrict__ e) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_pad) return;
+    __half p1 = __float2half_rn(0.f), p2 = p1, p3 = p1;
+    if (r < n) {
+        const double U = 0.5 * (double)bnorm[r] * (double)s_b * (double)s_b;
+        p1 = __double2half(U * (1.0 / 8192.0));
+        const double r1 = U - (double)__half2float(p1) * 8192.0;
+        p2 = __double2half(r1 * 0.25);
+        const double r2 = r1 - (double)__half2float(p2) * 4.0;
+        p3 = __double2half(r2 * 256.0);
+    }
+    const __half z = __float2half_rn(0.f);
+    __half row[TC_FOLD_COLS] = {p1, p1, p1, p1, p1, p1, p1, p1, p2, p2, p2, p2, p3, z, z, z};
+    uint4* dst = reinterpret_cast<uint4*>(e + r * TC_FOLD_COLS);
+    dst[0] = *reinterpret_cast<uint4*>(row);
+    dst[1] = *reinterpret_cast<uint4*>(row + 8);
 }
-int launch_tc_query_params(const float* q_absmax, float s_b, float bn_max, TcQueryParams* out, cudaStream_t st) {
-    tc_query_params_kernel<<<1, 32, 0, st>>>(q_absmax, s_b, bn_max, out);
+int launch_norm_pieces(const float* bnorm, int64_t n, int64_t n_pad, float s_b, void* e_half, cudaStream_t st) {
+    if (n_pad <= 0) return VS_OK;
+    norm_pieces_kernel<<<(unsigned)ceil_div64(n_pad, 256), 256, 0, st>>>(bnorm, n, n_pad, s_b, (__half*)e_half);
     VSB_CUDA(cudaGetLastError());
     return VS_OK;
 }
 
-// out[i] = fp16_rn(x[i] * scale); scale either given or read from *scale_dev (the query scale is derived on the device)
+// TcQueryParams (kernels.cuh): scale of the query copy, key factor, the two certification constants and the query side
+// of the norm block.
+//   |key_f16 - key_exact| <= cert_a * sqrt(qn) + cert_b   with, per element, |x^ - x| <= eps|x| + u (eps = 2^-11,
+//   u = 2^-25 / scale: half the fp16 subnormal spacing), Cauchy-Schwarz for sum|q||x| <= sqrt(qn * bn_max) and
+//   sum|v| <= sqrt(128 * ||v||^2), plus 2^-15 * (sum|q||x| + bn/2) for the tensor core's fp32 accumulation of the dot
+//   product AND the norm block (in key units: 2^-15 * (2 sqrt(qn bn_max) + bn_max)), plus 2^-23 * bn_max for the residual of
+//   the three-piece norm, times 1.02, plus the fp32 rounding of the refined distances themselves (4e-6 * (qn + bn_max), folded
+//   into cert_b per query by the merge kernel).  tests/test_exact_gpu.py measures the actual error against this bound.
+__global__ void tc_query_params_kernel(const float* __restrict__ q_absmax, float s_b, float bn_max, TcQueryParams* out,
+                                       __half* __restrict__ qe) {
+    __shared__ __half row[TC_FOLD_COLS];
+    const float s_q = f16_scale_for(*q_absmax);
+    if (threadIdx.x == 0) {
+        const float eps = 1.0f / 2048.0f;
+        const float A = 2.0f * eps + eps * eps + 1.0f / 32768.0f;
+        const float u_q = ldexpf(1.0f, -25) / s_q, u_b = ldexpf(1.0f, -25) / s_b;
+        int eq, eb;
+        frexpf(s_q, &eq);
+        frexpf(s_b, &eb);
+        const int rho = eq - eb;  // s_q / s_b = 2^rho (both are powers of two)
+        TcQueryParams r;
+        r.s_q = s_q;
+        r.key_unscale = 2.0f / (s_q * s_b);
+        r.cert_a = 2.04f * (A * sqrtf(bn_max) + u_b * sqrtf(128.0f));
+        r.cert_b = 2.04f * (u_q * sqrtf(128.0f * bn_max) + 128.0f * u_q * u_b) + 1.02f * bn_max * (1.0f / 32768.0f + 1.0f / 8388608.0f);
+        r.bn_max = bn_max;
+        r.fold_ok = (rho <= 5 && rho >= -16) ? 1 : 0;
+        *out = r;
+        const __half a1 = __float2half_rn(r.fold_ok ? ldexpf(1.0f, rho + 10) : 0.f);
+        const __half a2 = __float2half_rn(r.fold_ok ? ldexpf(1.0f, rho) : 0.f);
+        const __half a3 = __float2half_rn(r.fold_ok ? ldexpf(1.0f, rho - 8) : 0.f);  // down to 2^-24: exact as a subnormal
+        const __half z = __float2half_rn(0.f);
+        for (int i = 0; i < TC_FOLD_COLS; ++i) row[i] = i < 8 ? a1 : (i < 12 ? a2 : (i == 12 ? a3 : z));
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 128 * TC_FOLD_COLS; i += blockDim.x) qe[i] = row[i % TC_FOLD_COLS];
+}
+int launch_tc_query_params(const float* q_absmax, float s_b, float bn_max, TcQueryParams* out, void* qe_half, cudaStream_t st) {
+    tc_query_params_kernel<<<1, 128, 0, st>>>(q_absmax, s_b, bn_max, out, (__half*)qe_half);
+    VSB_CUDA(cudaGetLastError());
+    return VS_OK;
+}
+
+// out[i] = fp16_rn(x[i] * scale); scale either given or -s_q read from *scale_dev (the query scale is derived on the device;
+// the query copy is NEGATED so that the accumulator  -s_q s_b q.x + s_q s_b bn / 2  is the key times s_q s_b / 2)
 __global__ void to_half_scaled_kernel(const float* __restrict__ x, int64_t count, float scale, const TcQueryParams* scale_dev,
                                       __half* __restrict__ out) {
-    const float s = scale_dev ? scale_dev->s_q : scale;
+    const float s = scale_dev ? -scale_dev->s_q : scale;
     for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < count; i += (int64_t)gridDim.x * blockDim.x * 4) {
         if (i + 3 < count) {
             const float4 v = __ldg(reinterpret_cast<const float4*>(x + i));
@@ -415,10 +463,11 @@ __global__ void __launch_bounds__(128) merge_lists_kernel(const float* __restric
         // lastk = key of the last popped candidate = largest candidate key (lists pop in ascending key order)
         const unsigned holder = __ballot_sync(0xffffffffu, myid >= 0 && rank == k - 1);
         const float dk = __shfl_sync(0xffffffffu, myk, holder ? __ffs(holder) - 1 : 0);
-        if (lane == 0 && n_valid == nsel) {
+        if (lane == 0 && (n_valid == nsel || !rf.qp->fold_ok)) {
             const float qn = __ldg(rf.qnorm + q);
             const float e = rf.qp->cert_a * sqrtf(qn) + rf.qp->cert_b + 4e-6f * (qn + rf.qp->bn_max);
-            const bool ok = holder != 0 && (qn + lastk) - e > dk;
+            // candidate keys are in accumulator units (x s_q s_b / 2, an exact power-of-two factor)
+            const bool ok = rf.qp->fold_ok && holder != 0 && (qn + lastk * rf.qp->key_unscale) - e > dk;
             if (!ok) rf.uncert_list[atomicAdd(rf.uncert_count, 1)] = (int32_t)q;
         }
     }

@@ -8,17 +8,26 @@ namespace vsb {
 
 // per-call constants of the scaled-fp16 candidate pass, derived on the device from the queries (no host round trip)
 struct TcQueryParams {
-    float s_q;        // power-of-two scale of the fp16 query copy
-    float key_scale;  // key = bn + (*key_scale_dev) * acc,  -2 / (s_q * s_b)
-    float cert_a;     // |key_f16 - key_exact| <= cert_a * sqrt(qn) + cert_b
+    float s_q;          // power-of-two scale of the fp16 query copy (the copy holds -s_q * q)
+    float key_unscale;  // key = acc * key_unscale,  2 / (s_q * s_b): the accumulator already contains the norm term
+    float cert_a;       // |key_f16 - key_exact| <= cert_a * sqrt(qn) + cert_b
     float cert_b;
     float bn_max;
+    int fold_ok;        // 0: s_q / s_b is outside the range in which the norm block's query-side constants are fp16 numbers
+                        // -> the pass cannot run, every query is reported uncertified (and redone on the fp32 path)
 };
+// The norm term of the candidate pass travels through the tensor core as an extra K = 16 block (exact_tc.cuh):
+// base side  e[row][16] fp16 = { p1 x8, p2 x4, p3, 0, 0, 0 },  U = s_b^2 * ||x||^2 / 2 = 2^13 * p1 + 2^2 * p2 + 2^-8 * p3
+// query side a[16]      fp16 = { 2^(rho+10) x8, 2^rho x4, 2^(rho-8), 0, 0, 0 },  rho = log2(s_q / s_b)
+constexpr int TC_FOLD_COLS = 16;
+int launch_norm_pieces(const float* bnorm, int64_t n, int64_t n_pad, float s_b, void* e_half, cudaStream_t st);
 int launch_absmax_f32(const float* x, int64_t count, float* out_zeroed, cudaStream_t st);
 float f16_scale_host(float absmax);
 // dim == 128 only: norms (reference summation order) + abs-max of the whole batch in one pass
 int launch_query_prep(const float* x, int64_t rows, float* norms, float* absmax_zeroed, cudaStream_t st);
-int launch_tc_query_params(const float* q_absmax, float s_b, float bn_max, TcQueryParams* out, cudaStream_t st);
+// also writes the query-side norm block qe_half[128][16] (every row the same)
+int launch_tc_query_params(const float* q_absmax, float s_b, float bn_max, TcQueryParams* out, void* qe_half, cudaStream_t st);
+// out = fp16(x * scale), or fp16(x * -scale_dev->s_q) when scale_dev != nullptr (the NEGATED scaled query copy)
 int launch_to_half_scaled(const float* x, int64_t count, float scale, const TcQueryParams* scale_dev, void* out_half,
                           cudaStream_t st);
 int launch_gather_rows(const float* src, const int32_t* idx, int n_idx, float* dst, cudaStream_t st);
@@ -51,10 +60,11 @@ struct TcPlan {
 struct TcBaseMaps {
     CUtensorMap hi, lo, hi_half, lo_half;
 };
-TcPlan tc_make_plan(int64_t n, int64_t nq, int num_sms);
-// mode: 0 = 1xTF32, 1 = 3xTF32, 2 = scaled fp16 candidate pass (exact_tc.cuh TcMode); key = bn + (*key_scale_dev) * acc
+TcPlan tc_make_plan(int64_t n, int64_t nq, int num_sms, int mode = 0);  // mode: exact_tc.cuh TcMode
+// mode: 0 = 1xTF32, 1 = 3xTF32, 2 = scaled fp16 candidate pass (exact_tc.cuh TcMode; keys stay in accumulator units,
+// tmA_lo = the query-side norm block [128 x 16] fp16, tmB.lo = the base-side norm block [n_pad x 16] fp16, both SWIZZLE_32B)
 int launch_exact_tc(const CUtensorMap& tmA_hi, const CUtensorMap& tmA_lo, const TcBaseMaps& tmB, const float* bnorm,
-                    int32_t* gthr, int nq, const TcPlan& plan,
+                    int32_t* gthr, int nq, int64_t n_rows, const TcPlan& plan,
                     int ktop, int mode, const float* key_scale_dev, const float* lb_key, const int32_t* lb_id, float* part_key,
                     int32_t* part_id, cudaStream_t st);
 int tc_lists_per_split(int mode);  // partial lists written per (split, query): 1 (TC_F16, mode 2) or 3
@@ -116,6 +126,8 @@ int launch_int8_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, int32_t* gthr
 
 // api.cu helpers shared with api_ivf.cu / api_int8.cu
 int make_tmap_2d(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_t cols, int elem_bytes, uint32_t box_rows);
+// [rows x 16] fp16 (32-byte rows), box = 32 B x box_rows, SWIZZLE_32B: the K = 16 norm block of the fp16 candidate pass
+int make_tmap_fold(CUtensorMap* out, const void* gptr, uint64_t rows, uint32_t box_rows);
 
 int round_up_ktop(int k);  // smallest supported register-list size >= k (1,5,10,16,32), 0 if k > 32
 

@@ -220,6 +220,15 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     d |= (uint64_t)2 << 61;                       // SWIZZLE_128B         bits [61,64)
     return d;
 }
+// The same for 32-byte swizzle: rows of 32 B (16 fp16 along K = one K = 16 instruction), 8-row groups 256 B apart.
+__device__ __forceinline__ uint64_t umma_desc_sw32(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)(256 >> 4) << 32;              // stride byte offset
+    d |= (uint64_t)1 << 46;                       // descriptor version
+    d |= (uint64_t)6 << 61;                       // SWIZZLE_32B
+    return d;
+}
 // Instruction descriptor: D fp32 (or s32), A/B format, both K-major, M x N tile.
 __host__ __device__ constexpr uint32_t umma_idesc(uint32_t c_fmt, uint32_t ab_fmt, uint32_t M, uint32_t N) {
     return (c_fmt << 4) | (ab_fmt << 7) | (ab_fmt << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
