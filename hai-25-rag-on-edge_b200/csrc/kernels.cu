@@ -303,8 +303,8 @@ int launch_scatter_results(const float* key, const int32_t* id, const int32_t* i
 // Refine (rf.base != nullptr): the tensor-core accumulator does not round to nearest (measured on B200: a
 // systematic ~2e-6 relative truncation bias of the dot product on continuous data), so the fused kernel's keys
 // are treated as a candidate ranking; the nsel selected candidates get their distance recomputed in plain fp32
-// — 16 accumulators by (d mod 16) with FMA, pairwise lane tree, then (qn + bn) - 2*dot (cpu_baseline.cpp:241)
-// — and are re-sorted by (distance, id).  Reported distances are then fp32-faithful regardless of which
+// — rows read cooperatively, four FMAs per lane, a fixed pairwise lane tree (warp_refine_dots), then (qn + bn) - 2*dot
+// (cpu_baseline.cpp:241) — and are re-sorted by (distance, id).  Reported distances are then fp32-faithful regardless of which
 // kernel generated the candidates.
 // ------------------------------------------------------------------------------------------------
 // Lists that live in per-shard exchange blocks (block = ids [nq x k] | keys [nq x k] | 16-byte trailer, see
@@ -329,27 +329,85 @@ struct RefineArgs {
     int32_t* uncert_list;   // their indices
 };
 
-__device__ __forceinline__ float dot16_128(const float* __restrict__ a, const float* __restrict__ b) {
-    float lane[16];
+// Exact fp32 dot products q . x_id of a warp's (up to 32) candidates, lane r holding candidate r's local row id (or -1).
+// Every row is read COOPERATIVELY — lane i takes components 4i .. 4i+3 (one coalesced 512-byte request per row) — and the
+// 32 partial sums are added in a FIXED tree (lane i + lane i+16, then +8, +4, +2, +1), so the value of a (query, row) pair
+// does not depend on the lane the candidate sits in: every kernel path, shard count and list position gives the same bits.
+// Returns, in lane r, the dot product of candidate r.
+__device__ __forceinline__ float warp_refine_dots(const float* __restrict__ q_row, const float* __restrict__ base, int nsel,
+                                                  int32_t myid, int lane) {
+    const float4 qv = __ldg(reinterpret_cast<const float4*>(q_row) + lane);
+    float mydot = 0.f;
+    for (int r0 = 0; r0 < nsel; r0 += 4) {
+        float4 x[4];
 #pragma unroll
-    for (int l = 0; l < 16; ++l) lane[l] = 0.f;
+        for (int u = 0; u < 4; ++u) {  // four independent row loads in flight
+            const int32_t id = __shfl_sync(0xffffffffu, myid, (r0 + u) & 31);
+            x[u] = (r0 + u < nsel && id >= 0) ? __ldg(reinterpret_cast<const float4*>(base + (size_t)id * 128) + lane)
+                                              : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
 #pragma unroll
-    for (int i = 0; i < 128; i += 16) {
+        for (int u = 0; u < 4; ++u) {
+            float p = __fmul_rn(x[u].x, qv.x);
+            p = fmaf(x[u].y, qv.y, p);
+            p = fmaf(x[u].z, qv.z, p);
+            p = fmaf(x[u].w, qv.w, p);
 #pragma unroll
-        for (int v = 0; v < 4; ++v) {
-            const float4 x = __ldg(reinterpret_cast<const float4*>(a + i) + v);
-            const float4 y = __ldg(reinterpret_cast<const float4*>(b + i) + v);
-            lane[4 * v + 0] = fmaf(x.x, y.x, lane[4 * v + 0]);
-            lane[4 * v + 1] = fmaf(x.y, y.y, lane[4 * v + 1]);
-            lane[4 * v + 2] = fmaf(x.z, y.z, lane[4 * v + 2]);
-            lane[4 * v + 3] = fmaf(x.w, y.w, lane[4 * v + 3]);
+            for (int o = 16; o > 0; o >>= 1) p = __fadd_rn(p, __shfl_down_sync(0xffffffffu, p, o));
+            const float tot = __shfl_sync(0xffffffffu, p, 0);
+            if (lane == r0 + u) mydot = tot;
         }
     }
-#pragma unroll
-    for (int w = 8; w >= 1; w >>= 1)
-#pragma unroll
-        for (int l = 0; l < w; ++l) lane[l] = __fadd_rn(lane[l], lane[l + w]);
-    return lane[0];
+    return mydot;
+}
+
+// Common tail of the merge kernels.  In: lane r holds candidate r (myk, myid; -1 = none) of the nsel selected by the candidate
+// keys, lastk / lasti = the last (largest) selected candidate.  Does: lower bound for the next pass, exact fp32 refine,
+// (distance, id) ranking, certification, output rows.
+__device__ __forceinline__ void merge_tail(float myk, int32_t myid, float lastk, int32_t lasti, int64_t q, int lane, int nsel, int k,
+                                           int64_t id_base, int neg_out, float* __restrict__ out_key, int32_t* __restrict__ out_id,
+                                           int out_stride, int out_off, float* __restrict__ lb_key_out,
+                                           int32_t* __restrict__ lb_id_out, const RefineArgs& rf) {
+    const float INF = __int_as_float(0x7f800000);
+    if (lb_key_out && lane == 0) {  // exclusive lower bound for the next pass (local ids, candidate-ranking keys)
+        lb_key_out[q] = lasti >= 0 ? lastk : INF;
+        lb_id_out[q] = lasti >= 0 ? lasti : 0x7fffffff;
+    }
+    if (rf.base) {
+        const float dot = warp_refine_dots(rf.q + (size_t)q * 128, rf.base, nsel, myid, lane);
+        if (myid >= 0) myk = fmaf(-2.0f, dot, __fadd_rn(__ldg(rf.qnorm + q), __ldg(rf.bnorm + myid)));
+    }
+    // rank by counting (ids are unique; padding sorts last and is never written)
+    int rank = 0;
+#pragma unroll 1
+    for (int j = 0; j < nsel; ++j) {
+        const float ok = __shfl_sync(0xffffffffu, myk, j);
+        const int32_t oi = __shfl_sync(0xffffffffu, myid, j);
+        rank += (oi >= 0 && pair_less(ok, oi, myk, myid)) ? 1 : 0;
+    }
+    const int n_valid = __popc(__ballot_sync(0xffffffffu, myid >= 0));
+    if (rf.qp) {
+        // lastk = key of the last popped candidate = largest candidate key (lists pop in ascending key order)
+        const unsigned holder = __ballot_sync(0xffffffffu, myid >= 0 && rank == k - 1);
+        const float dk = __shfl_sync(0xffffffffu, myk, holder ? __ffs(holder) - 1 : 0);
+        if (lane == 0 && (n_valid == nsel || !rf.qp->fold_ok)) {
+            const float qn = __ldg(rf.qnorm + q);
+            const float e = rf.qp->cert_a * sqrtf(qn) + rf.qp->cert_b + 4e-6f * (qn + rf.qp->bn_max);
+            // candidate keys are in accumulator units (x s_q s_b / 2, an exact power-of-two factor)
+            const bool ok = rf.qp->fold_ok && holder != 0 && (qn + lastk * rf.qp->key_unscale) - e > dk;
+            if (!ok) rf.uncert_list[atomicAdd(rf.uncert_count, 1)] = (int32_t)q;
+        }
+    }
+    float* ok_row = out_key + q * out_stride + out_off;
+    int32_t* oi_row = out_id + q * out_stride + out_off;
+    if (myid >= 0 && rank < k) {
+        ok_row[rank] = neg_out ? -myk : myk;
+        oi_row[rank] = (int32_t)(myid + id_base);
+    }
+    for (int r = n_valid + lane; r < k; r += 32) {
+        ok_row[r] = neg_out ? -INF : INF;
+        oi_row[r] = -1;
+    }
 }
 
 template <int KTOP>
@@ -434,53 +492,90 @@ __global__ void __launch_bounds__(128) merge_lists_kernel(const float* __restric
             L.id[KTOP - 1] = -1;
         }
     }
-    if (lb_key_out && lane == 0) {  // exclusive lower bound for the next pass (local ids, candidate-ranking keys)
-        lb_key_out[q] = lasti >= 0 ? lastk : INF;
-        lb_id_out[q] = lasti >= 0 ? lasti : 0x7fffffff;
-    }
     __syncwarp();
-    // ---- this lane's candidate (nsel <= 32), refined when requested
+    // ---- this lane's candidate (nsel <= 32)
     float myk = INF;
     int32_t myid = -1;
     if (lane < nsel) {
         myk = s_key[wib][lane];
         myid = s_id[wib][lane];
-        if (rf.base && myid >= 0) {
-            const float dot = dot16_128(rf.q + (size_t)q * 128, rf.base + (size_t)myid * 128);
-            myk = fmaf(-2.0f, dot, __fadd_rn(__ldg(rf.qnorm + q), __ldg(rf.bnorm + myid)));
+    }
+    merge_tail(myk, myid, lastk, lasti, q, lane, nsel, k, id_base, neg_out, out_key, out_id, out_stride, out_off, lb_key_out,
+               lb_id_out, rf);
+}
+
+// The same for n_lists <= 32 (every tensor-core / IVF / exchange merge): the lists are staged in shared memory with coalesced
+// loads (a list = 128 contiguous bytes), lane j walks list j with a cursor, and every round the warp takes the smallest head
+// (shuffle arg-min) — no register-list shifting, ~1/4 of the instructions of the general kernel.
+__global__ void __launch_bounds__(128) merge_small_kernel(const float* __restrict__ part_key, const int32_t* __restrict__ part_id,
+                                                          int n_lists, int64_t nq, int list_len, int nsel, int k, int64_t id_base,
+                                                          int neg_in, int neg_out, float* __restrict__ out_key,
+                                                          int32_t* __restrict__ out_id, int out_stride, int out_off,
+                                                          float* __restrict__ lb_key_out, int32_t* __restrict__ lb_id_out,
+                                                          RefineArgs rf, BlockArgs ba) {
+    extern __shared__ float sm_lists[];  // per warp: keys [n_lists][32] then ids [n_lists][32]
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    const int64_t q = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
+    if (ba.trailer && blockIdx.x == 0 && threadIdx.x == 0) {
+        int32_t tot = 0;
+        for (int l = 0; l < n_lists; ++l) tot += ba.trailer[(size_t)l * ba.list_stride];
+        *ba.total_out = tot;
+    }
+    if (q >= nq) return;
+    const float INF = __int_as_float(0x7f800000);
+    const size_t lstride = ba.list_stride ? ba.list_stride : (size_t)nq * list_len;
+    float* sk = sm_lists + (size_t)wib * n_lists * 64;
+    int32_t* si = reinterpret_cast<int32_t*>(sk + n_lists * 32);
+    for (int l = 0; l < n_lists; ++l) {
+        float kk = INF;
+        int32_t ii = -1;
+        if (lane < list_len) {
+            kk = part_key[(size_t)l * lstride + (size_t)q * list_len + lane];
+            ii = part_id[(size_t)l * lstride + (size_t)q * list_len + lane];
+        }
+        sk[l * 32 + lane] = ii >= 0 ? (neg_in ? -kk : kk) : INF;
+        si[l * 32 + lane] = ii;
+    }
+    __syncwarp();
+    int cur = 0;
+    float hk = INF;
+    int32_t hid = -1;
+    if (lane < n_lists) {
+        hk = sk[lane * 32];
+        hid = si[lane * 32];
+    }
+    float myk = INF, lastk = INF;
+    int32_t myid = -1, lasti = -1;
+    for (int r = 0; r < nsel; ++r) {
+        float bk = hk;
+        int32_t bi = hid;
+        int src = lane;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ok = __shfl_xor_sync(0xffffffffu, bk, o);
+            const int32_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            const int os = __shfl_xor_sync(0xffffffffu, src, o);
+            if (pair_less(ok, oi, bk, bi)) {
+                bk = ok;
+                bi = oi;
+                src = os;
+            }
+        }
+        if (lane == r) {
+            myk = bi >= 0 ? bk : INF;
+            myid = bi;
+        }
+        lastk = bk;
+        lasti = bi;
+        if (src == lane && bi >= 0) {
+            ++cur;
+            hid = cur < list_len ? si[lane * 32 + cur] : -1;
+            hk = hid >= 0 ? sk[lane * 32 + cur] : INF;
         }
     }
-    // rank by counting (ids are unique; padding sorts last and is never written)
-    int rank = 0;
-#pragma unroll 1
-    for (int j = 0; j < nsel; ++j) {
-        const float ok = __shfl_sync(0xffffffffu, myk, j);
-        const int32_t oi = __shfl_sync(0xffffffffu, myid, j);
-        rank += (oi >= 0 && pair_less(ok, oi, myk, myid)) ? 1 : 0;
-    }
-    const int n_valid = __popc(__ballot_sync(0xffffffffu, myid >= 0));
-    if (rf.qp) {
-        // lastk = key of the last popped candidate = largest candidate key (lists pop in ascending key order)
-        const unsigned holder = __ballot_sync(0xffffffffu, myid >= 0 && rank == k - 1);
-        const float dk = __shfl_sync(0xffffffffu, myk, holder ? __ffs(holder) - 1 : 0);
-        if (lane == 0 && (n_valid == nsel || !rf.qp->fold_ok)) {
-            const float qn = __ldg(rf.qnorm + q);
-            const float e = rf.qp->cert_a * sqrtf(qn) + rf.qp->cert_b + 4e-6f * (qn + rf.qp->bn_max);
-            // candidate keys are in accumulator units (x s_q s_b / 2, an exact power-of-two factor)
-            const bool ok = rf.qp->fold_ok && holder != 0 && (qn + lastk * rf.qp->key_unscale) - e > dk;
-            if (!ok) rf.uncert_list[atomicAdd(rf.uncert_count, 1)] = (int32_t)q;
-        }
-    }
-    float* ok_row = out_key + q * out_stride + out_off;
-    int32_t* oi_row = out_id + q * out_stride + out_off;
-    if (myid >= 0 && rank < k) {
-        ok_row[rank] = neg_out ? -myk : myk;
-        oi_row[rank] = (int32_t)(myid + id_base);
-    }
-    for (int r = n_valid + lane; r < k; r += 32) {
-        ok_row[r] = neg_out ? -INF : INF;
-        oi_row[r] = -1;
-    }
+    merge_tail(myk, myid, lastk, lasti, q, lane, nsel, k, id_base, neg_out, out_key, out_id, out_stride, out_off, lb_key_out,
+               lb_id_out, rf);
 }
 
 int launch_merge_lists(const float* part_key, const int32_t* part_id, int n_lists, int64_t nq, int list_len, int nsel,
@@ -495,6 +590,13 @@ int launch_merge_lists(const float* part_key, const int32_t* part_id, int n_list
     const unsigned blocks = (unsigned)ceil_div64(nq, 4);
     RefineArgs rf{rf_base, rf_bnorm, rf_q, rf_qnorm, cert_qp, uncert_count, uncert_list};
     BlockArgs ba{list_stride, trailer, trailer_total_out};
+    if (n_lists <= 32 && round_up_ktop(list_len) != 0) {
+        const size_t smem = (size_t)4 * n_lists * 64 * sizeof(float);  // <= 32 KB
+        merge_small_kernel<<<blocks, 128, smem, st>>>(part_key, part_id, n_lists, nq, list_len, nsel, k, id_base, neg_in, neg_out,
+                                                     out_key, out_id, out_stride, out_off, lb_key_out, lb_id_out, rf, ba);
+        VSB_CUDA(cudaGetLastError());
+        return VS_OK;
+    }
 #define VSB_MERGE_CASE(KT)                                                                                            \
     case KT:                                                                                                          \
         merge_lists_kernel<KT><<<blocks, 128, 0, st>>>(part_key, part_id, n_lists, nq, list_len, nsel, k, id_base,    \
