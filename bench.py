@@ -64,7 +64,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "20", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -239,11 +239,14 @@ def main():
     assert sptr != 0
     searcher = vsb_sharded.ShardedExact(vsb, index, nq, k, dev)
 
-    def device_step(q_ptr):
-        # local fused search; for N > 1: ONE in-place NCCL all-gather of the exchange blocks + merge kernel; finish()
-        # waits for the 4-byte total of the uncertified counts (0 on this data: nothing to redo)
+    def device_step(q_ptr, after_enqueue=None):
+        # local fused search; for N > 1: ONE in-place NCCL all-gather of the exchange blocks + merge kernel.  Everything
+        # the step does on the GPU is enqueued by enqueue(); finish() is the host-side check of the 4-byte total of the
+        # uncertified counts (0 on this data: nothing is redone), it enqueues nothing in that case
         out = searcher.enqueue(q_ptr, nq, prec, sptr)
-        searcher.finish()
+        if after_enqueue is not None:
+            after_enqueue()
+        assert searcher.finish() == 0
         return out
 
     # N > 1: every rank uploads ITS 1/N of the queries (they cross PCIe once in total) and one all-gather replicates
@@ -281,10 +284,11 @@ def main():
             flush.fill_(1)
             barrier()
             if use_events:
+                # device time of the step: the closing event is recorded right after the step's last GPU operation was
+                # enqueued (before the host waits for anything)
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record(stream)
-                fn()
-                e1.record(stream)
+                fn(lambda: e1.record(stream))
                 e1.synchronize()
                 out.append(e0.elapsed_time(e1))
             else:
@@ -304,8 +308,8 @@ def main():
         sampler.start()
     kernel_ms = []
 
-    def dev_fn():
-        device_step(q_dev.data_ptr())
+    def dev_fn(after_enqueue=None):
+        device_step(q_dev.data_ptr(), after_enqueue)
 
     t_dev = []
     for _ in range(args.steps):
@@ -315,7 +319,6 @@ def main():
     fallbacks = index.last_fallbacks()
     t_e2e = timed(e2e_step, args.steps, use_events=False)  # wall clock: the host-buffer call blocks the host
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
 
     def max_over_ranks(x):
         t = torch.tensor([x], dtype=torch.float64, device=dev)
@@ -330,8 +333,10 @@ def main():
     # the pure fp32-faithful tensor-core path (3xTF32 split, no fp16 candidate pass) timed in the same run, for reference
     alt = None
     if prec == vsb.PREC_AUTO:
-        def alt_fn():
+        def alt_fn(after_enqueue=None):
             searcher.enqueue(q_dev.data_ptr(), nq, vsb.PREC_3XTF32, sptr)
+            if after_enqueue is not None:
+                after_enqueue()
             searcher.finish()
         for _ in range(3):
             alt_fn()
@@ -339,6 +344,8 @@ def main():
         ms_alt = max_over_ranks(float(np.sum(timed(alt_fn, args.steps)))) / args.steps
         alt = {"precision": vsb.PREC_NAMES[vsb.PREC_3XTF32], "value": nq / (ms_alt * 1e-3), "unit": "queries/s",
                "ms_per_step": ms_alt, "note": "same workload through VS_PREC_FP32_3XTF32 only (device-resident queries)"}
+
+    clocks = sampler.stop() if rank == 0 else None  # sampled over all three timed loops (device, e2e, 3xTF32)
 
     # sanity: the timed path produced a plausible answer (ascending distances, ids in range)
     oi, od = device_step(q_dev.data_ptr())

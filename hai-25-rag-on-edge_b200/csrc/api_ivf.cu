@@ -371,56 +371,41 @@ int vs_ivf_build(const float* base, int64_t n, int dim, int nlist, int max_iter,
     VSB_CUDA(cudaSetDevice(device));
 
     std::vector<float> cent((size_t)nlist * dim);
-    if (init_centroids) {
-        std::memcpy(cent.data(), init_centroids, cent.size() * 4);
-    } else {  // seeded sample of distinct rows
-        std::mt19937_64 rng(seed);
-        std::vector<int64_t> pick;
-        pick.reserve((size_t)nlist);
-        std::vector<bool> used;
-        if (n <= (int64_t)4 * nlist) {
-            std::vector<int64_t> all((size_t)n);
-            for (int64_t i = 0; i < n; ++i) all[(size_t)i] = i;
-            std::shuffle(all.begin(), all.end(), rng);
-            pick.assign(all.begin(), all.begin() + nlist);
-        } else {
-            used.assign((size_t)n, false);
-            while ((int)pick.size() < nlist) {
-                const int64_t r = (int64_t)(rng() % (uint64_t)n);
-                if (!used[(size_t)r]) {
-                    used[(size_t)r] = true;
-                    pick.push_back(r);
-                }
-            }
-        }
-        for (int c = 0; c < nlist; ++c) std::memcpy(&cent[(size_t)c * dim], base + (size_t)pick[(size_t)c] * dim, (size_t)dim * 4);
-    }
-
     float* d_base = nullptr;
     float* d_cent = nullptr;
-    int32_t *d_lab = nullptr, *d_off = nullptr, *d_mem = nullptr;
+    int32_t *d_lab = nullptr, *d_prev = nullptr, *d_off = nullptr, *d_mem = nullptr, *d_ws = nullptr, *d_changed = nullptr;
     float* d_dist = nullptr;
-    double* d_shift = nullptr;
+    double *d_shift = nullptr, *d_part = nullptr;
     vs_exact_t* cidx = nullptr;
-    std::vector<int32_t> labels((size_t)n), prev, offsets, members;
-    std::vector<float> dist((size_t)n);
+    std::vector<int32_t> labels((size_t)n), offsets((size_t)nlist + 1), members((size_t)n);
     int iters = 0;
     double inertia = 0.0;
     auto cleanup = [&]() {
         if (cidx) vs_exact_destroy(cidx);
-        for (void* p : {(void*)d_base, (void*)d_cent, (void*)d_lab, (void*)d_off, (void*)d_mem, (void*)d_dist, (void*)d_shift})
+        for (void* p : {(void*)d_base, (void*)d_cent, (void*)d_lab, (void*)d_prev, (void*)d_off, (void*)d_mem, (void*)d_ws,
+                        (void*)d_changed, (void*)d_dist, (void*)d_shift, (void*)d_part})
             if (p) cudaFree(p);
     };
     auto body = [&]() -> int {
         VSB_CUDA(cudaMalloc((void**)&d_base, sizeof(float) * (size_t)n * dim));
         VSB_CUDA(cudaMalloc((void**)&d_cent, sizeof(float) * (size_t)nlist * dim));
         VSB_CUDA(cudaMalloc((void**)&d_lab, sizeof(int32_t) * (size_t)n));
+        VSB_CUDA(cudaMalloc((void**)&d_prev, sizeof(int32_t) * (size_t)n));
         VSB_CUDA(cudaMalloc((void**)&d_dist, sizeof(float) * (size_t)n));
         VSB_CUDA(cudaMalloc((void**)&d_off, sizeof(int32_t) * ((size_t)nlist + 1)));
         VSB_CUDA(cudaMalloc((void**)&d_mem, sizeof(int32_t) * (size_t)n));
-        VSB_CUDA(cudaMalloc((void**)&d_shift, sizeof(double)));
+        VSB_CUDA(cudaMalloc((void**)&d_ws, sizeof(int32_t) * multisplit_workspace_ints(n, nlist)));
+        VSB_CUDA(cudaMalloc((void**)&d_changed, sizeof(int32_t)));
+        VSB_CUDA(cudaMalloc((void**)&d_shift, sizeof(double) * 2));
+        VSB_CUDA(cudaMalloc((void**)&d_part, sizeof(double) * (size_t)ceil_div64(n, 1024)));
         VSB_CUDA(cudaMemcpy(d_base, base, sizeof(float) * (size_t)n * dim, cudaMemcpyHostToDevice));
-        VSB_CUDA(cudaMemcpy(d_cent, cent.data(), sizeof(float) * (size_t)nlist * dim, cudaMemcpyHostToDevice));
+        if (init_centroids) {
+            VSB_CUDA(cudaMemcpy(d_cent, init_centroids, sizeof(float) * (size_t)nlist * dim, cudaMemcpyHostToDevice));
+        } else {
+            // sklearn's default init: greedy k-means++ (2 + ln k candidates per centre drawn ~ D^2), on the device
+            VSB_TRY(launch_kmeanspp(d_base, n, nlist, seed, d_cent, nullptr));
+        }
+        VSB_CUDA(cudaMemset(d_prev, 0xff, sizeof(int32_t) * (size_t)n));  // -1: "no label yet"
         // data variance for sklearn's relative tolerance (tol = 1e-4 * mean per-feature variance)
         double var = 0.0;
         {
@@ -440,31 +425,34 @@ int vs_ivf_build(const float* base, int64_t n, int dim, int nlist, int max_iter,
             if (!cidx)
                 VSB_TRY(vs_exact_create_dev(&cidx, d_cent, nlist, dim, device, 0));
             else
-                VSB_TRY(vs_exact_refresh(cidx));  // centroids moved: recompute norms and the TF32 split in place
+                VSB_TRY(vs_exact_refresh(cidx));  // centroids moved: norms / fp16 copy / TF32 split recomputed in place
             VSB_TRY(vs_exact_search_dev(cidx, d_base, n, 1, VS_PREC_FP32_3XTF32, d_lab, d_dist, nullptr));
-            VSB_CUDA(cudaDeviceSynchronize());
-            prev.swap(labels);
-            labels.resize((size_t)n);
-            VSB_CUDA(cudaMemcpy(labels.data(), d_lab, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost));
-            const bool same = (it > 0) && (prev == labels);
-            if (it >= max_iter || same) {
-                VSB_CUDA(cudaMemcpy(dist.data(), d_dist, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost));
-                inertia = 0.0;
-                for (int64_t i = 0; i < n; ++i) inertia += std::max(0.f, dist[(size_t)i]);
+            // labels changed? (counted on the device: 4 bytes come back, not the labels)
+            VSB_CUDA(cudaMemsetAsync(d_changed, 0, sizeof(int32_t), nullptr));
+            VSB_CUDA(cudaDeviceSynchronize());  // the search ran on the handle's stream
+            VSB_TRY(launch_labels_changed(d_lab, d_prev, n, d_changed, nullptr));
+            int32_t changed = 0;
+            VSB_CUDA(cudaMemcpy(&changed, d_changed, sizeof(int32_t), cudaMemcpyDeviceToHost));
+            if (it >= max_iter || changed == 0) {
                 iters = it;
                 break;
             }
-            // ---- update: inverted lists on the host (stable counting sort), per-list means on the device
-            labels_to_lists(labels, nlist, offsets, members);
-            VSB_CUDA(cudaMemcpy(d_off, offsets.data(), sizeof(int32_t) * ((size_t)nlist + 1), cudaMemcpyHostToDevice));
-            VSB_CUDA(cudaMemcpy(d_mem, members.data(), sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice));
-            VSB_CUDA(cudaMemset(d_shift, 0, sizeof(double)));
+            // ---- update: inverted lists (stable counting sort on the device), per-list means
+            VSB_TRY(launch_multisplit(d_lab, n, nlist, d_ws, d_off, d_mem, nullptr));
+            VSB_CUDA(cudaMemsetAsync(d_shift, 0, sizeof(double), nullptr));
             list_mean_kernel<<<nlist, 128>>>(d_base, d_off, d_mem, d_cent, d_shift);
             VSB_CUDA(cudaGetLastError());
             double shift2 = 0.0;
             VSB_CUDA(cudaMemcpy(&shift2, d_shift, sizeof(double), cudaMemcpyDeviceToHost));
             if (shift2 <= tol) max_iter = std::min(max_iter, it + 1);  // converged: one final assignment, then stop
         }
+        // final state: labels, lists, inertia (sum of the exact fp32 distances to the assigned centroid, fixed order)
+        VSB_TRY(launch_multisplit(d_lab, n, nlist, d_ws, d_off, d_mem, nullptr));
+        VSB_TRY(launch_inertia(d_dist, n, d_part, d_shift + 1, nullptr));
+        VSB_CUDA(cudaMemcpy(labels.data(), d_lab, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost));
+        VSB_CUDA(cudaMemcpy(offsets.data(), d_off, sizeof(int32_t) * ((size_t)nlist + 1), cudaMemcpyDeviceToHost));
+        VSB_CUDA(cudaMemcpy(members.data(), d_mem, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost));
+        VSB_CUDA(cudaMemcpy(&inertia, d_shift + 1, sizeof(double), cudaMemcpyDeviceToHost));
         VSB_CUDA(cudaMemcpy(cent.data(), d_cent, sizeof(float) * (size_t)nlist * dim, cudaMemcpyDeviceToHost));
         return VS_OK;
     };
@@ -473,8 +461,7 @@ int vs_ivf_build(const float* base, int64_t n, int dim, int nlist, int max_iter,
     cleanup();
     if (rc != VS_OK) return fail(rc, keep);
 
-    // ---- inverted lists + files (create_ivf_model.py:114-166, create_ivf_model_reordered.py:108-169)
-    labels_to_lists(labels, nlist, offsets, members);
+    // ---- files (create_ivf_model.py:114-166, create_ivf_model_reordered.py:108-169)
     int32_t mn = 0x7fffffff, mx = 0;
     std::vector<int32_t> sizes((size_t)nlist);
     for (int c = 0; c < nlist; ++c) {

@@ -96,6 +96,18 @@ int launch_merge_shards(const float* in_key, const int32_t* in_id, int n_shards,
 int launch_synth(float* out, int64_t row0, int64_t nrows, int dim, int law, uint64_t seed, uint64_t centre_seed,
                  cudaStream_t st);
 
+// kmeans.cu -------------------------------------------------------------------------------------
+// greedy k-means++ seeding (sklearn's rule: 2 + floor(ln k) candidates per centre drawn ~ D^2, keep the one that lowers the
+// potential most), deterministic for a given seed; base_dev [n x 128] -> cent_dev [k x 128]; synchronises `st`
+int launch_kmeanspp(const float* base_dev, int64_t n, int k, uint64_t seed, float* cent_dev, cudaStream_t st);
+// *changed_zeroed += number of rows with cur != prev; prev = cur
+int launch_labels_changed(const int32_t* cur, int32_t* prev, int64_t n, int32_t* changed_zeroed, cudaStream_t st);
+// stable counting sort by label: offsets [nlist+1] (CSR), members [n] (ascending row ids inside a list, np.where order)
+size_t multisplit_workspace_ints(int64_t n, int nlist);
+int launch_multisplit(const int32_t* lab, int64_t n, int nlist, int32_t* ws, int32_t* offsets, int32_t* members, cudaStream_t st);
+// *out = sum of max(dist, 0) in double, fixed order; part_ws: ceil(n/1024) doubles
+int launch_inertia(const float* dist, int64_t n, double* part_ws, double* out, cudaStream_t st);
+
 // ivf.cu ----------------------------------------------------------------------------------------
 int launch_ivf_coarse(const float* q, int64_t nq, const float* cent, int nlist, float* scores, cudaStream_t st);
 int launch_ivf_probes(const float* scores, int64_t nq, int nlist, int nprobe, int32_t* probes, cudaStream_t st);

@@ -214,3 +214,38 @@ def test_gpu_matches_reference_ivfsearcher_golden(path, scan, tmp_path, gpu_vsb,
                                           what=f"{path} {how} nprobe={nprobe} {scan}")
         finally:
             idx.close()
+
+
+@pytest.mark.parametrize("law,n,nlist", [("mix", 60_000, 128), ("cont", 40_000, 64)])
+def test_builder_matches_sklearn_kmeans(law, n, nlist, tmp_path, gpu_vsb, oracle):
+    """build_ivf_index (qidk_ivf/prepare/create_ivf_model.py:102-110) is KMeans(n_clusters, random_state=42, n_init=1,
+    max_iter=100): greedy k-means++ seeding + Lloyd with sklearn's tolerance.  The random streams differ, so the centroids
+    differ; what must agree is the QUALITY of the clustering — final inertia within 2 % of sklearn's on the same data —
+    and the build must be a pure function of (data, seed)."""
+    from sklearn.cluster import KMeans
+
+    vsb = gpu_vsb
+    base = vsb.synth.make(law, 21, n)
+    d1, d2 = str(tmp_path / "a"), str(tmp_path / "b")
+    info = vsb.ivf_build(base, nlist, d1, max_iter=100, seed=42)
+    km = KMeans(n_clusters=nlist, random_state=42, n_init=1, max_iter=100).fit(base)
+    ratio = info["inertia"] / float(km.inertia_)
+    print(f"\n[kmeans] {law} n={n} k={nlist}: inertia {info['inertia']:.6g} after {info['iters']} iterations, "
+          f"sklearn {km.inertia_:.6g} after {km.n_iter_}: ratio {ratio:.4f}")
+    assert 0.97 <= ratio <= 1.02
+    # the reported inertia is the true one of the written centroids / labels
+    cent = np.load(os.path.join(d1, "centroids.npy"))
+    lab = np.load(os.path.join(d1, "cluster_ids.npy"))
+    olab, od = oracle.kmeans_assign(base, cent)
+    assert np.array_equal(lab, olab)
+    assert abs(info["inertia"] - float(od.astype(np.float64).sum())) <= 1e-6 * info["inertia"]
+    # k-means++ beats a uniform row sample as a starting point (same Lloyd, same data)
+    rng = np.random.default_rng(0)
+    info_u = vsb.ivf_build(base, nlist, str(tmp_path / "u"), max_iter=0, init_centroids=base[rng.choice(n, nlist, replace=False)])
+    info_p = vsb.ivf_build(base, nlist, str(tmp_path / "p"), max_iter=0, seed=42)
+    assert info_p["inertia"] < info_u["inertia"]
+    # deterministic
+    info2 = vsb.ivf_build(base, nlist, d2, max_iter=100, seed=42)
+    assert info2 == info and np.array_equal(np.load(os.path.join(d2, "centroids.npy")), cent)
+    assert np.array_equal(np.load(os.path.join(d2, "cluster_indices.npy" if not os.path.exists(os.path.join(d2, "reorder_to_original.npy")) else "reorder_to_original.npy")),
+                          np.load(os.path.join(d1, "cluster_indices.npy" if not os.path.exists(os.path.join(d1, "reorder_to_original.npy")) else "reorder_to_original.npy")))
