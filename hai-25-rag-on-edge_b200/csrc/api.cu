@@ -90,6 +90,11 @@ int exact_free(vs_exact* h) {
     for (DevBuf* b : {&h->q, &h->qhi, &h->qlo, &h->qf16, &h->qnorm, &h->part_key, &h->part_id, &h->lbk, &h->lbi, &h->out_ids,
                       &h->out_keys, &h->flag, &h->gthr, &h->qparams, &h->qfold, &h->unc_list, &h->fb_q, &h->fb_ids, &h->fb_keys})
         b->release();
+    for (auto& g : h->graphs) cudaGraphExecDestroy(g.exec);
+    for (DevBuf* b : {&h->g_q, &h->g_qnorm, &h->g_part_key, &h->g_part_id, &h->g_ids, &h->g_keys}) b->release();
+    if (h->hp_q) cudaFreeHost(h->hp_q);
+    if (h->hp_ids) cudaFreeHost(h->hp_ids);
+    if (h->hp_keys) cudaFreeHost(h->hp_keys);
     if (h->h_flag) cudaFreeHost(h->h_flag);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -467,6 +472,72 @@ int exact_search_core(vs_exact* h, const float* q_dev, int64_t nq, int k, int pr
     return VS_OK;
 }
 
+// Batch <= 8, k <= 32 through the host-buffer entry point: latency is launch-bound (three kernels, two copies and a
+// synchronisation around a ~0.1 ms scan), so the whole sequence is captured once per (nq, k) and replayed as one graph.
+// The graph works on its own (fixed-size) workspaces and pinned staging buffers, so larger searches in between cannot move
+// the buffers it has baked in.
+static int exact_search_small_graph(vs_exact* h, const float* queries, int64_t nq, int k, int32_t* out_ids, float* out_dists) {
+    cudaStream_t st = h->stream;
+    if (!h->hp_q) {
+        VSB_CUDA(cudaMallocHost((void**)&h->hp_q, sizeof(float) * 8 * 128));
+        VSB_CUDA(cudaMallocHost((void**)&h->hp_ids, sizeof(int32_t) * 8 * kMaxRegK));
+        VSB_CUDA(cudaMallocHost((void**)&h->hp_keys, sizeof(float) * 8 * kMaxRegK));
+        const int max_ctas = stream_num_ctas(h->device, 1);
+        VSB_TRY(h->g_q.reserve(sizeof(float) * 8 * 128));
+        VSB_TRY(h->g_qnorm.reserve(sizeof(float) * 8));
+        VSB_TRY(h->g_part_key.reserve(sizeof(float) * (size_t)max_ctas * 8 * kMaxRegK));
+        VSB_TRY(h->g_part_id.reserve(sizeof(int32_t) * (size_t)max_ctas * 8 * kMaxRegK));
+        VSB_TRY(h->g_ids.reserve(sizeof(int32_t) * 8 * kMaxRegK));
+        VSB_TRY(h->g_keys.reserve(sizeof(float) * 8 * kMaxRegK));
+    }
+    cudaGraphExec_t exec = nullptr;
+    for (auto& g : h->graphs)
+        if (g.nq == nq && g.k == k) exec = g.exec;
+    if (!exec) {
+        // capture: the same calls as the ordinary path, on the graph's own workspaces
+        std::swap(h->qnorm, h->g_qnorm);
+        std::swap(h->part_key, h->g_part_key);
+        std::swap(h->part_id, h->g_part_id);
+        cudaGraph_t graph = nullptr;
+        int rc = VS_OK;
+        cudaError_t e = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
+        if (e != cudaSuccess) rc = fail(VS_ERR_CUDA, std::string("cudaStreamBeginCapture: ") + cudaGetErrorString(e));
+        if (rc == VS_OK) {
+            const size_t qb = sizeof(float) * (size_t)nq * 128, rb = (size_t)nq * k * 4;
+            e = cudaMemcpyAsync(h->g_q.p, h->hp_q, qb, cudaMemcpyHostToDevice, st);
+            if (e == cudaSuccess)
+                rc = exact_search_core(h, h->g_q.as<float>(), nq, k, VS_PREC_FP32_FFMA, h->g_ids.as<int32_t>(), h->g_keys.as<float>(), st);
+            if (e == cudaSuccess && rc == VS_OK) e = cudaMemcpyAsync(h->hp_ids, h->g_ids.p, rb, cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess && rc == VS_OK) e = cudaMemcpyAsync(h->hp_keys, h->g_keys.p, rb, cudaMemcpyDeviceToHost, st);
+            const cudaError_t e2 = cudaStreamEndCapture(st, &graph);  // always ends the capture
+            if (rc == VS_OK && e != cudaSuccess) rc = fail(VS_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(e));
+            if (rc == VS_OK && e2 != cudaSuccess) rc = fail(VS_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e2));
+        }
+        std::swap(h->qnorm, h->g_qnorm);
+        std::swap(h->part_key, h->g_part_key);
+        std::swap(h->part_id, h->g_part_id);
+        if (rc == VS_OK) {
+            e = cudaGraphInstantiate(&exec, graph, 0);
+            if (e != cudaSuccess) rc = fail(VS_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+        }
+        if (graph) cudaGraphDestroy(graph);
+        if (rc != VS_OK) {
+            cudaGetLastError();
+            return rc;
+        }
+        h->graphs.push_back({nq, k, exec});
+    }
+    memcpy(h->hp_q, queries, sizeof(float) * (size_t)nq * 128);
+    VSB_CUDA(cudaGraphLaunch(exec, st));
+    VSB_CUDA(cudaStreamSynchronize(st));
+    memcpy(out_ids, h->hp_ids, (size_t)nq * k * 4);
+    memcpy(out_dists, h->hp_keys, (size_t)nq * k * 4);
+    h->last_launches = 3;
+    h->last_precision = VS_PREC_FP32_FFMA;
+    h->last_fallback = 0;
+    return VS_OK;
+}
+
 extern "C" {
 
 const char* vs_last_error(void) { return g_err.c_str(); }
@@ -545,6 +616,9 @@ int vs_exact_search_f32(vs_exact_t* h, const float* queries, int64_t nq, int k, 
     if (!queries || !out_ids || !out_dists) return fail(VS_ERR_INVALID, "NULL buffer");
     VSB_CUDA(cudaSetDevice(h->device));
     cudaStream_t st = h->stream;
+    if (nq <= 8 && k <= kMaxRegK && h->dim == 128 && (precision == VS_PREC_AUTO || precision == VS_PREC_FP32_FFMA) && !h->profile &&
+        !h->cert_pending && !h->broken && !getenv("VSB_NO_GRAPH"))
+        return exact_search_small_graph(h, queries, nq, k, out_ids, out_dists);
     VSB_TRY(h->q.reserve(sizeof(float) * (size_t)nq * h->dim));
     VSB_TRY(h->out_ids.reserve(sizeof(int32_t) * (size_t)nq * k));
     VSB_TRY(h->out_keys.reserve(sizeof(float) * (size_t)nq * k));

@@ -4,6 +4,8 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <vector>
+
 #include "kernels.cuh"
 #include "vsb_common.cuh"
 
@@ -33,6 +35,18 @@ struct vs_exact {
     // workspace (grow-only)
     DevBuf q, qhi, qlo, qf16, qnorm, part_key, part_id, lbk, lbi, out_ids, out_keys, flag, gthr, qparams, qfold, unc_list, fb_q,
         fb_ids, fb_keys;
+    // batch <= 8 host calls (vs_exact_search_f32): the whole call — H2D, query norms, streaming kernel, merge, D2H — as ONE
+    // CUDA graph per (nq, k), over workspaces and pinned staging buffers that only the graphs touch
+    struct SmallGraph {
+        int64_t nq;
+        int k;
+        cudaGraphExec_t exec;
+    };
+    std::vector<SmallGraph> graphs;
+    DevBuf g_q, g_qnorm, g_part_key, g_part_id, g_ids, g_keys;
+    float* hp_q = nullptr;       // pinned [8 x 128]
+    int32_t* hp_ids = nullptr;   // pinned [8 x 32]
+    float* hp_keys = nullptr;    // pinned [8 x 32]
     int* h_flag = nullptr;  // pinned: [0] exactness flag, [1] uncertified count
     int last_launches = 0;
     int last_precision = 0;
