@@ -32,8 +32,15 @@ struct vs_ivf {
     int32_t* d_order = nullptr;    // [nlist] lists by descending length (work order of the list-major scan)
     float* d_centroids = nullptr;  // [nlist x 128]
     CUtensorMap tmV;
+    // tensor-core list-major scan: TF32 hi / lo split of the vectors (hi aliases d_vectors and lo is absent when every
+    // component is TF32-exact, e.g. integer SIFT data; lo is then a zero array created on first need)
+    float* d_vhi = nullptr;
+    float* d_vlo = nullptr;
+    bool v_exact = false;
+    CUtensorMap tmVhi, tmVlo;
+    int* h_flag = nullptr;  // pinned: "queries are not TF32-exact"
     cudaStream_t stream = nullptr;
-    DevBuf q, scores, probes, out_ids, out_scores, out_counts, total, lm_ws, part_key, part_id;
+    DevBuf q, scores, probes, out_ids, out_scores, out_counts, total, lm_ws, part_key, part_id, qhi, qlo, gthr;
     int num_sms = 148;
     unsigned long long* h_total = nullptr;  // pinned
     bool profile = false;
@@ -46,12 +53,15 @@ static int ivf_free(vs_ivf* h) {
     if (!h) return VS_OK;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->d_vhi && h->d_vhi != h->d_vectors) cudaFree(h->d_vhi);
+    if (h->d_vlo) cudaFree(h->d_vlo);
     for (void* p : {(void*)h->d_vectors, (void*)h->d_offsets, (void*)h->d_idmap, (void*)h->d_centroids, (void*)h->d_order})
         if (p) cudaFree(p);
     for (DevBuf* b : {&h->q, &h->scores, &h->probes, &h->out_ids, &h->out_scores, &h->out_counts, &h->total, &h->lm_ws,
-                      &h->part_key, &h->part_id})
+                      &h->part_key, &h->part_id, &h->qhi, &h->qlo, &h->gthr})
         b->release();
     if (h->h_total) cudaFreeHost(h->h_total);
+    if (h->h_flag) cudaFreeHost(h->h_flag);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -112,6 +122,28 @@ static int ivf_create_impl(vs_ivf_t** out, const float* vectors, int64_t n, int 
         cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device);
         VSB_TRY(h->total.reserve(sizeof(unsigned long long)));
         VSB_CUDA(cudaMallocHost((void**)&h->h_total, sizeof(unsigned long long)));
+        VSB_CUDA(cudaMallocHost((void**)&h->h_flag, sizeof(int)));
+        // TF32 split of the vectors for the tensor-core scan (rows incl. the zero padding behind the last list)
+        {
+            const int64_t rows = n + (int64_t)pad_rows;
+            VSB_TRY(h->gthr.reserve(sizeof(int)));
+            int* flag = h->gthr.as<int>();
+            VSB_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), h->stream));
+            VSB_TRY(launch_prep_rows(h->d_vectors, n, 128, nullptr, nullptr, nullptr, flag, h->stream));
+            VSB_CUDA(cudaMemcpyAsync(h->h_flag, flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+            VSB_CUDA(cudaStreamSynchronize(h->stream));
+            h->v_exact = *h->h_flag == 0;
+            if (h->v_exact) {
+                h->d_vhi = h->d_vectors;
+            } else {
+                VSB_CUDA(cudaMalloc((void**)&h->d_vhi, sizeof(float) * (size_t)rows * 128));
+                VSB_CUDA(cudaMalloc((void**)&h->d_vlo, sizeof(float) * (size_t)rows * 128));
+                VSB_TRY(launch_prep_rows(h->d_vectors, rows, 128, nullptr, h->d_vhi, h->d_vlo, nullptr, h->stream));
+                VSB_TRY(make_tmap_2d(&h->tmVlo, h->d_vlo, (uint64_t)rows, 128, 4, 128));
+            }
+            VSB_TRY(make_tmap_2d(&h->tmVhi, h->d_vhi, (uint64_t)rows, 128, 4, 128));
+            if (!h->d_vlo) h->tmVlo = h->tmVhi;
+        }
         VSB_CUDA(cudaStreamSynchronize(h->stream));
         return VS_OK;
     };
@@ -142,7 +174,59 @@ static int ivf_search_core(vs_ivf* h, const float* q_dev, int64_t nq, int k, int
     // (nprobe 8: from ~700 queries), and for nprobe >= 16 at any batch (K6 walks a query's lists one after the other)
     const bool lm_auto = (int64_t)nq * nprobe >= 6 * (int64_t)h->nlist || (nprobe >= 16 && nq >= 8);
     const bool list_major = lm_env ? atoi(lm_env) != 0 : (lm_auto && round_up_ktop(k) != 0);
+    // list-major on the tensor cores (default) or with FFMA (K8, VSB_IVF_TC=0: scores bit-identical by construction)
+    const char* tc_env = getenv("VSB_IVF_TC");
+    const bool use_tc = list_major && !(tc_env && atoi(tc_env) == 0) && k <= 30;
     if (h->profile) VSB_CUDA(cudaEventRecord(h->ev0, st));
+    if (use_tc) {
+        // candidates: fused TF32 tensor-core GEMM + top-k per (query, probe slot) over the list-major work items; the merge
+        // re-scores the best k + 2 per query in the reference's NEON order, so the returned scores are bit-identical to
+        // IVFIndex.cpp:278-357 and to the FFMA kernels
+        const int ktop = round_up_ktop(std::min(k + 2, kMaxRegK));
+        const int64_t n_pairs = nq * nprobe;
+        const int n_lists = nprobe * 3;
+        if (n_lists > 96) return fail(VS_ERR_UNSUPPORTED, "IVF tensor-core scan: nprobe > 32 (use VSB_IVF_TC=0)");
+        VSB_TRY(h->lm_ws.reserve(sizeof(int32_t) * ivf_tc_workspace_ints(nq, nprobe, h->nlist)));
+        VSB_TRY(h->qhi.reserve(sizeof(float) * (size_t)(n_pairs + 128) * 128));
+        VSB_TRY(h->qlo.reserve(sizeof(float) * (size_t)(n_pairs + 128) * 128));
+        VSB_TRY(h->part_key.reserve(sizeof(float) * (size_t)n_lists * nq * ktop));
+        VSB_TRY(h->part_id.reserve(sizeof(int32_t) * (size_t)n_lists * nq * ktop));
+        VSB_TRY(h->gthr.reserve(sizeof(int32_t) * (size_t)nq));
+        const int4* items;
+        const int32_t *n_items, *pairs;
+        int32_t* q_cand;
+        int* q_flag;
+        VSB_TRY(launch_ivf_tc_prep(q_dev, h->d_offsets, h->nlist, h->d_order, h->probes.as<int32_t>(), nq, nprobe, h->lm_ws.as<int32_t>(),
+                                   h->qhi.as<float>(), h->qlo.as<float>(), &items, &n_items, &pairs, &q_cand, &q_flag, st));
+        bool split3 = true;
+        if (h->v_exact) {  // 1xTF32 is bit-identical to 3xTF32 iff the query lo parts are all zero too (one 4-byte round trip)
+            VSB_CUDA(cudaMemcpyAsync(h->h_flag, q_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+            VSB_CUDA(cudaStreamSynchronize(st));
+            split3 = *h->h_flag != 0;
+            if (split3 && !h->d_vlo) {  // a real zero lo operand keeps the arithmetic honest
+                const int64_t rows = h->n + (int64_t)ivf_scan_rows_per_chunk();
+                VSB_CUDA(cudaMalloc((void**)&h->d_vlo, sizeof(float) * (size_t)rows * 128));
+                VSB_CUDA(cudaMemsetAsync(h->d_vlo, 0, sizeof(float) * (size_t)rows * 128, st));
+                VSB_TRY(make_tmap_2d(&h->tmVlo, h->d_vlo, (uint64_t)rows, 128, 4, 128));
+            }
+        }
+        VSB_CUDA(cudaMemsetAsync(h->gthr.p, 0x7f, sizeof(int32_t) * (size_t)nq, st));
+        CUtensorMap tmQhi, tmQlo;
+        VSB_TRY(make_tmap_2d(&tmQhi, h->qhi.p, (uint64_t)(n_pairs + 128), 128, 4, 128));
+        VSB_TRY(make_tmap_2d(&tmQlo, h->qlo.p, (uint64_t)(n_pairs + 128), 128, 4, 128));
+        VSB_TRY(launch_exact_tc_ivf(tmQhi, tmQlo, h->tmVhi, h->tmVlo, items, n_items, pairs, nprobe, h->gthr.as<int32_t>(), (int)nq, ktop,
+                                    split3, h->part_key.as<float>(), h->part_id.as<int32_t>(), h->num_sms, st));
+        VSB_TRY(launch_ivf_counts(q_cand, nq, k, out_counts, h->total.as<unsigned long long>(), st));
+        if (h->profile) {
+            VSB_CUDA(cudaEventRecord(h->ev1, st));
+            h->ev_valid = true;
+        }
+        VSB_TRY(launch_merge_lists(h->part_key.as<float>(), h->part_id.as<int32_t>(), n_lists, nq, ktop, ktop, k, 0, 0, 1, out_scores,
+                                   out_ids, k, 0, nullptr, nullptr, h->d_vectors, nullptr, q_dev, nullptr, st, nullptr, nullptr, nullptr, 0,
+                                   nullptr, nullptr, h->d_idmap));
+        h->last_launches = 10;
+        return VS_OK;
+    }
     if (list_major) {
         const int ktop = round_up_ktop(k);
         if (ktop == 0) return fail(VS_ERR_UNSUPPORTED, "IVF search: k > 32 is not implemented");

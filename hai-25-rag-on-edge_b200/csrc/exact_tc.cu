@@ -85,6 +85,48 @@ static int launch_one(const TcPlan& plan, const CUtensorMap& tmA_hi, const CUten
     return VS_OK;
 }
 
+// IVF list-major scan on the tensor cores (exact_tc.cuh, IVF = true): tmA_* = gathered / split queries in pair order,
+// tmB_* = list-contiguous vectors (hi / lo), work items and pair table produced by launch_ivf_tc_prep.  split3 = 3xTF32.
+template <int KTOP, int MODE>
+static int launch_ivf_one(int grid, const CUtensorMap& tmA_hi, const CUtensorMap& tmA_lo, const CUtensorMap& tmB_hi,
+                          const CUtensorMap& tmB_lo, const TcParams& p, cudaStream_t st) {
+    VSB_CUDA(cudaFuncSetAttribute(exact_tc_kernel<KTOP, MODE, false, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  TcSmem<MODE>::TOTAL));  // per device, hence not cached in a static
+    exact_tc_kernel<KTOP, MODE, false, 1, true><<<grid, TcSmem<MODE>::THREADS, TcSmem<MODE>::TOTAL, st>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, p);
+    VSB_CUDA(cudaGetLastError());
+    return VS_OK;
+}
+
+int launch_exact_tc_ivf(const CUtensorMap& tmA_hi, const CUtensorMap& tmA_lo, const CUtensorMap& tmB_hi, const CUtensorMap& tmB_lo,
+                        const int4* items, const int32_t* n_items, const int32_t* pairs, int nprobe, int32_t* gthr, int nq, int ktop,
+                        bool split3, float* part_key, int32_t* part_id, int num_sms, cudaStream_t st) {
+    TcParams p{};
+    p.gthr = gthr;
+    p.part_key = part_key;
+    p.part_id = part_id;
+    p.nq = nq;
+    p.items = items;
+    p.n_items = n_items;
+    p.pairs = pairs;
+    p.nprobe = nprobe;
+    p.n_mtiles = 1;
+    p.n_splits = 1;
+    p.tiles_per_split = 1;
+#define VSB_IVF_CASE(KT)                                                                              \
+    case KT:                                                                                          \
+        return split3 ? launch_ivf_one<KT, TC_TF32X3>(num_sms, tmA_hi, tmA_lo, tmB_hi, tmB_lo, p, st) \
+                      : launch_ivf_one<KT, TC_TF32X1>(num_sms, tmA_hi, tmA_lo, tmB_hi, tmB_lo, p, st);
+    switch (ktop) {
+        VSB_IVF_CASE(5)
+        VSB_IVF_CASE(10)
+        VSB_IVF_CASE(16)
+        VSB_IVF_CASE(32)
+        default:
+            return fail(VS_ERR_INVALID, "ivf tc: unsupported list size");
+    }
+#undef VSB_IVF_CASE
+}
+
 int tc_lists_per_split(int mode) { return mode == TC_F16 ? 1 : TC_EPI_GROUPS; }
 
 int tc_set_attributes() {

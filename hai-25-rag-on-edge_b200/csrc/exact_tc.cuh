@@ -102,6 +102,11 @@ struct TcParams {
     unsigned long long* stats;  // debug counters (VSB_TC_STATS) or nullptr: [0] warp slow-path entries, [1] lane entries,
                          // [2] qualifying elements, [3] insertions
     int qbatch;          // TC_F16: queued rows that make a batch worth folding (0 = default)
+    // IVF = true: work items {first pair, pairs, first row, rows}, their number, pair -> query * nprobe + probe slot
+    const int4* items;
+    const int32_t* n_items;
+    const int32_t* pairs;
+    int nprobe;
     int dbg;             // timing experiments only (VSB_TC_DBG): 1 no epilogue work, 2 no inserts, 4 no MMA, 8 no B loads,
                          // 16 epilogue = TMEM loads only, 32 epilogue = math only (no TMEM loads)
 };
@@ -184,7 +189,15 @@ __device__ __forceinline__ float tc_quantile_cap(const int32_t* gthr, int nq, in
 // chip-wide L2 read rate, not by the tensor pipe).  A ring stage is refilled only when BOTH CTAs' MMAs have read it:
 // the `empty` barriers take two arrivals, the second one being the peer's multicast tcgen05.commit.  tmB_* are then the
 // 64-row-box tensor maps.
-template <int KTOP, int MODE, bool HAS_LB, int CL>
+//
+// IVF = true (TF32 modes only): the same machine as the list-major fine scan of the IVF search (IVFIndex::searchBatch's
+// per-query list scan, qidk_ivf/android/app/main/jni/IVFIndex.cpp:715-779, regrouped by list).  A unit is a work item
+// {first pair, pairs (<= 128), first row, rows}: the A tile holds the (hi/lo split) queries of up to 128 (query, probe slot)
+// pairs that probe ONE inverted list, gathered contiguously in pair order; the base tiles are that list's rows (a TMA box
+// may start at any row).  Key = -2 q.x (inner product, largest first; no norm term); thresholds are shared per QUERY
+// across all its lists; one sorted list per (probe slot, epilogue group, query) goes to the merge kernel, ids = row
+// positions in the list-contiguous array.
+template <int KTOP, int MODE, bool HAS_LB, int CL, bool IVF = false>
 __global__ void __launch_bounds__(TcSmem<MODE>::THREADS, 1)
 exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                 const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
@@ -261,7 +274,8 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
 
     // unit = (query tile [pair], base split), split-major; the odd tile out of an odd tile count is paired with a ghost
     // (all rows beyond nq: the TMA fills zeros, nothing is written)
-    const int n_units = n_mt * p.n_splits;
+    const int n_units = IVF ? __ldg(p.n_items) : n_mt * p.n_splits;
+    static_assert(!IVF || (MODE != TC_F16 && !HAS_LB && CL == 1), "IVF units run on the TF32 path with independent CTAs");
 
     if (warp < 4) {
       if constexpr (S::SMEM_LIST)
@@ -326,27 +340,40 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
             uint32_t phase = 0, acc_phase = 0;
             int it = 0;
             for (int unit = worker; unit < n_units; unit += n_workers, ++it) {
-                const int m_tile = (unit % n_mt) * CL + cta_rank;
-                const int split = unit / n_mt;
+                int a_row0, b_row0, n_t;  // first query row of the A tile, first base row, base tiles of the unit
+                if constexpr (IVF) {
+                    const int4 rec = __ldg(p.items + unit);
+                    a_row0 = rec.x;
+                    b_row0 = rec.z;
+                    n_t = (rec.w + TC_BN - 1) / TC_BN;
+                } else {
+                    const int m_tile = (unit % n_mt) * CL + cta_rank;
+                    const int split = unit / n_mt;
+                    const int t0 = split * p.tiles_per_split;
+                    a_row0 = m_tile * TC_BM;
+                    b_row0 = t0 * TC_BN;
+                    n_t = min(t0 + p.tiles_per_split, p.n_tiles) - t0;
+                }
                 mbar_wait(a_empty, (uint32_t)((it & 1) ^ 1));
                 if (leader) {
                     mbar_expect_tx(a_full, (uint32_t)S::A_BYTES);
 #pragma unroll
                     for (int kb = 0; kb < TC_NKB; ++kb) {
-                        tma_load_2d(sA + kb * TC_KB_BYTES, &tmA_hi, a_full, kb * KB_ELEMS, m_tile * TC_BM);
-                        if (SPLIT3) tma_load_2d(sA + (TC_NKB + kb) * TC_KB_BYTES, &tmA_lo, a_full, kb * 32, m_tile * TC_BM);
+                        tma_load_2d(sA + kb * TC_KB_BYTES, &tmA_hi, a_full, kb * KB_ELEMS, a_row0);
+                        if (SPLIT3) tma_load_2d(sA + (TC_NKB + kb) * TC_KB_BYTES, &tmA_lo, a_full, kb * 32, a_row0);
                     }
                 }
-                const int t0 = split * p.tiles_per_split;
-                const int t1 = min(t0 + p.tiles_per_split, p.n_tiles);
-                for (int t = t0; t < t1; ++t) {
-                    // norms of this tile go to the slot of the accumulator the tile will use
-                    mbar_wait(&acc_empty[acc], acc_phase ^ 1);
-                    if (leader) {
-                        mbar_expect_tx(&n_full[acc], (uint32_t)(TC_BN * 4));
-                        bulk_load_1d(sN + acc * TC_BN, p.bnorm + (size_t)t * TC_BN, TC_BN * 4, &n_full[acc]);
+                for (int ti = 0; ti < n_t; ++ti) {
+                    const int t_row = b_row0 + ti * TC_BN;  // first base row of the tile
+                    if constexpr (!IVF) {
+                        // norms of this tile go to the slot of the accumulator the tile will use
+                        mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+                        if (leader) {
+                            mbar_expect_tx(&n_full[acc], (uint32_t)(TC_BN * 4));
+                            bulk_load_1d(sN + acc * TC_BN, p.bnorm + (size_t)t_row, TC_BN * 4, &n_full[acc]);
+                        }
+                        if (++acc == TC_NACC) { acc = 0; acc_phase ^= 1; }
                     }
-                    if (++acc == TC_NACC) { acc = 0; acc_phase ^= 1; }
 #pragma unroll
                     for (int kb = 0; kb < TC_NKB; ++kb) {
                         mbar_wait(&empty[stage], phase ^ 1);
@@ -357,9 +384,9 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
                                 mbar_expect_tx(&full[stage], (uint32_t)TC_KB_BYTES);
                                 if (CL == 2)
                                     tma_load_2d_mcast(sB + stage * TC_KB_BYTES + cta_rank * (TC_KB_BYTES / 2), &tmB_hi, &full[stage],
-                                                      kb * KB_ELEMS, t * TC_BN + cta_rank * (TC_BN / 2), (uint16_t)3);
+                                                      kb * KB_ELEMS, t_row + cta_rank * (TC_BN / 2), (uint16_t)3);
                                 else
-                                    tma_load_2d(sB + stage * TC_KB_BYTES, &tmB_hi, &full[stage], kb * KB_ELEMS, t * TC_BN);
+                                    tma_load_2d(sB + stage * TC_KB_BYTES, &tmB_hi, &full[stage], kb * KB_ELEMS, t_row);
                             }
                         }
                         if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
@@ -372,9 +399,9 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
                                     mbar_expect_tx(&full[stage], (uint32_t)TC_KB_BYTES);
                                     if (CL == 2)
                                         tma_load_2d_mcast(sB + stage * TC_KB_BYTES + cta_rank * (TC_KB_BYTES / 2), &tmB_lo, &full[stage],
-                                                          kb * 32, t * TC_BN + cta_rank * (TC_BN / 2), (uint16_t)3);
+                                                          kb * 32, t_row + cta_rank * (TC_BN / 2), (uint16_t)3);
                                     else
-                                        tma_load_2d(sB + stage * TC_KB_BYTES, &tmB_lo, &full[stage], kb * 32, t * TC_BN);
+                                        tma_load_2d(sB + stage * TC_KB_BYTES, &tmB_lo, &full[stage], kb * 32, t_row);
                                 }
                             }
                             if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
@@ -431,12 +458,16 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
               }
             } else
             for (int unit = worker; unit < n_units; unit += n_workers, ++it) {
-                const int split = unit / n_mt;
-                const int t0 = split * p.tiles_per_split;
-                const int t1 = min(t0 + p.tiles_per_split, p.n_tiles);
+                int n_t;
+                if constexpr (IVF) {
+                    n_t = (__ldg(p.items + unit).w + TC_BN - 1) / TC_BN;
+                } else {
+                    const int t0 = (unit / n_mt) * p.tiles_per_split;
+                    n_t = min(t0 + p.tiles_per_split, p.n_tiles) - t0;
+                }
                 mbar_wait(a_full, (uint32_t)(it & 1));
                 tc_fence_after();
-                for (int t = t0; t < t1; ++t) {
+                for (int ti = 0; ti < n_t; ++ti) {
                     mbar_wait(&acc_empty[acc], acc_phase ^ 1);
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TC_BN);
@@ -769,14 +800,29 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         constexpr bool DB = KTOP <= 16;       // double-buffered TMEM loads while the register budget allows
         int tcount = 0;                       // tiles this CTA has gone through before the current unit
         for (int unit = worker; unit < n_units; unit += n_workers) {
-            const int m_tile = (unit % n_mt) * CL + cta_rank;
-            const int split = unit / n_mt;
-            const int t0 = split * p.tiles_per_split;
-            const int t1 = min(t0 + p.tiles_per_split, p.n_tiles);
-            const int q = m_tile * TC_BM + row;
-            const bool valid = q < p.nq;
-            // whole 32-lane quadrant beyond the last query (small batches): barriers only, no TMEM traffic
-            const bool quad_live = m_tile * TC_BM + quad * 32 < p.nq;
+            int q, n_t, b_row0, b_rows = 0x7fffffff, split = 0, slot = 0;
+            bool valid, quad_live;
+            if constexpr (IVF) {
+                const int4 rec = __ldg(p.items + unit);  // {first pair, pairs, first row, rows}
+                valid = row < rec.y;
+                quad_live = quad * 32 < rec.y;
+                const int pair = valid ? __ldg(p.pairs + rec.x + row) : 0;
+                q = pair / p.nprobe;
+                slot = pair - q * p.nprobe;
+                b_row0 = rec.z;
+                b_rows = rec.w;
+                n_t = (rec.w + TC_BN - 1) / TC_BN;
+            } else {
+                const int m_tile = (unit % n_mt) * CL + cta_rank;
+                split = unit / n_mt;
+                const int t0 = split * p.tiles_per_split;
+                q = m_tile * TC_BM + row;
+                valid = q < p.nq;
+                // whole 32-lane quadrant beyond the last query (small batches): barriers only, no TMEM traffic
+                quad_live = m_tile * TC_BM + quad * 32 < p.nq;
+                b_row0 = t0 * TC_BN;
+                n_t = min(t0 + p.tiles_per_split, p.n_tiles) - t0;
+            }
             float lbk = -INF;
             int32_t lbi = -1;
             if (HAS_LB && valid) {
@@ -801,8 +847,7 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
             int32_t pending = valid ? __ldcg(p.gthr + q) : 0x7f7f7f7f;
             int first = (grp - tcount % TC_EPI_GROUPS + TC_EPI_GROUPS) % TC_EPI_GROUPS;
             int j = 0;  // tiles of this unit seen by this group
-            for (int i = first; i < t1 - t0; i += TC_EPI_GROUPS, ++j) {
-                const int t = t0 + i;
+            for (int i = first; i < n_t; i += TC_EPI_GROUPS, ++j) {
                 const int tc = tcount + i;
                 const int acc = tc & (TC_NACC - 1);
                 const uint32_t acc_phase = (uint32_t)(tc / TC_NACC) & 1u;
@@ -825,11 +870,12 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
                     }
                     thr = fminf(top.threshold(), next_up(cap));
                 }
-                mbar_wait(&n_full[acc], acc_phase);
+                if constexpr (!IVF) mbar_wait(&n_full[acc], acc_phase);
                 mbar_wait(&acc_full[acc], acc_phase);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * TC_BN);
                 const uint32_t bn_s = smem_u32(sN + acc * TC_BN);
+                const int live_cols = b_rows - i * TC_BN;  // IVF: rows of the list left in this tile (the next list follows)
                 uint32_t r[DB ? 2 : 1][32];
                 const bool skip = (p.dbg & 1) || !quad_live;
                 if (!skip) tmem_ld32(taddr, r[0]);
@@ -838,12 +884,19 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
                     if (skip) break;
                     tc_wait_ld();
                     if (DB && c + 1 < CH) tmem_ld32(taddr + (c + 1) * 32, r[(c + 1) & 1]);
-                    const int col0 = t * TC_BN + c * 32;
+                    const int col0 = b_row0 + i * TC_BN + c * 32;
                     float d[32];
 #pragma unroll
                     for (int j4 = 0; j4 < 8; ++j4) {
-                        const float4 bn = lds128(bn_s + (uint32_t)(c * 32 + 4 * j4) * 4u);  // smem broadcast
                         const uint32_t* rr = r[DB ? (c & 1) : 0] + 4 * j4;
+                        if constexpr (IVF) {  // inner product, largest first: key = -2 q.x; columns past the list's end never rank
+                            d[4 * j4 + 0] = c * 32 + 4 * j4 + 0 < live_cols ? -2.0f * __uint_as_float(rr[0]) : INF;
+                            d[4 * j4 + 1] = c * 32 + 4 * j4 + 1 < live_cols ? -2.0f * __uint_as_float(rr[1]) : INF;
+                            d[4 * j4 + 2] = c * 32 + 4 * j4 + 2 < live_cols ? -2.0f * __uint_as_float(rr[2]) : INF;
+                            d[4 * j4 + 3] = c * 32 + 4 * j4 + 3 < live_cols ? -2.0f * __uint_as_float(rr[3]) : INF;
+                            continue;
+                        }
+                        const float4 bn = lds128(bn_s + (uint32_t)(c * 32 + 4 * j4) * 4u);  // smem broadcast
                         if (MODE == TC_F16) {
                             d[4 * j4 + 0] = fmaf(key_scale, __uint_as_float(rr[0]), bn.x);
                             d[4 * j4 + 1] = fmaf(key_scale, __uint_as_float(rr[1]), bn.y);
@@ -900,10 +953,10 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&acc_empty[acc]);
             }
-            tcount += t1 - t0;
+            tcount += n_t;
             if (valid) {
                 if (cap < INF) atomicMin(p.gthr + q, float_to_ordered(cap));
-                const size_t list = (size_t)split * TC_EPI_GROUPS + grp;
+                const size_t list = (size_t)(IVF ? slot : split) * TC_EPI_GROUPS + grp;
                 float* pk = p.part_key + (list * p.nq + q) * KTOP;
                 int32_t* pi = p.part_id + (list * p.nq + q) * KTOP;
 #pragma unroll

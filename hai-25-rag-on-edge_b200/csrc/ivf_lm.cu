@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(1024) lm_scan_kernel(const int32_t* __restrict
                                                        const int32_t* __restrict__ order,
                                                        const int32_t* __restrict__ offsets, int32_t* __restrict__ pair_start,
                                                        int32_t* __restrict__ cursor, int4* __restrict__ items,
-                                                       int32_t* __restrict__ n_items) {
+                                                       int32_t* __restrict__ n_items, int qt /* queries per work item */) {
     __shared__ int s_pairs[1024], s_items[1024];
     const int t = threadIdx.x;
     const int per = (nlist + 1023) / 1024;
@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(1024) lm_scan_kernel(const int32_t* __restrict
     for (int i = c0; i < c1; ++i) {
         const int c = order[i];
         np += list_cnt[c];
-        ni += (list_cnt[c] + LM_QT - 1) / LM_QT;
+        ni += (list_cnt[c] + qt - 1) / qt;
     }
     s_pairs[t] = np;
     s_items[t] = ni;
@@ -74,8 +74,8 @@ __global__ void __launch_bounds__(1024) lm_scan_kernel(const int32_t* __restrict
         cursor[c] = pp;
         const int cnt = list_cnt[c];
         const int r0 = offsets[c], rl = offsets[c + 1] - r0;
-        for (int q0 = 0; q0 < cnt; q0 += LM_QT)  // {first pair, queries, first row, rows}: one 16-byte load per item
-            items[ii++] = make_int4(pp + q0, min(LM_QT, cnt - q0), r0, rl);
+        for (int q0 = 0; q0 < cnt; q0 += qt)  // {first pair, queries, first row, rows}: one 16-byte load per item
+            items[ii++] = make_int4(pp + q0, min(qt, cnt - q0), r0, rl);
         pp += cnt;
     }
     if (t == 1023) *n_items = s_items[1023];
@@ -363,7 +363,7 @@ int launch_ivf_listmajor(const float* q, const float* vectors, const int32_t* of
     VSB_CUDA(cudaMemsetAsync(ws, 0, sizeof(int32_t) * ((size_t)nlist + 2 * (size_t)nq + 2), st));
     const unsigned gb = (unsigned)std::min<int64_t>(ceil_div64(n_pairs, 256), 148 * 8);
     lm_count_kernel<<<gb, 256, 0, st>>>(probes, n_pairs, nprobe, offsets, list_cnt, q_cand);
-    lm_scan_kernel<<<1, 1024, 0, st>>>(list_cnt, nlist, list_order, offsets, pair_start, cursor, items, n_items);
+    lm_scan_kernel<<<1, 1024, 0, st>>>(list_cnt, nlist, list_order, offsets, pair_start, cursor, items, n_items, LM_QT);
     lm_fill_kernel<<<gb, 256, 0, st>>>(probes, n_pairs, cursor, pairs);
     LmParams p{q, vectors, offsets, id_map, pairs, items, n_items, next_item, gthr, part_key, part_id, nq, nprobe};
     const int grid = 2 * num_sms;  // two resident CTAs per SM
@@ -374,6 +374,77 @@ int launch_ivf_listmajor(const float* q, const float* vectors, const int32_t* of
         case 16: ivf_lm_kernel<16><<<grid, LM_THREADS, LM_SMEM + 128, st>>>(p); break;
         default: ivf_lm_kernel<32><<<grid, LM_THREADS, LM_SMEM + 128, st>>>(p); break;
     }
+    lm_counts_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(nq, 256), 148), 256, 0, st>>>(q_cand, nq, k, out_counts, total);
+    VSB_CUDA(cudaGetLastError());
+    return VS_OK;
+}
+
+// ---- tensor-core list-major scan (exact_tc.cuh, IVF = true) ------------------------------------------------------
+// queries of the pairs, in pair order, split for the TF32 tensor core (hi = rna_tf32(q), lo = rna_tf32(q - hi));
+// *not_exact |= 1 when some lo != 0.  One warp per pair.
+__global__ void __launch_bounds__(256) lm_gather_split_kernel(const float* __restrict__ q, const int32_t* __restrict__ pairs,
+                                                              int64_t n_pairs, int nprobe, float* __restrict__ qhi,
+                                                              float* __restrict__ qlo, int* __restrict__ not_exact) {
+    const int lane = threadIdx.x & 31;
+    int inexact = 0;
+    for (int64_t pi = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); pi < n_pairs; pi += (int64_t)gridDim.x * 8) {
+        const int query = pairs[pi] / nprobe;
+        const float4 v = __ldg(reinterpret_cast<const float4*>(q + (size_t)query * 128) + lane);
+        float4 h, l;
+        uint32_t t;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.x)); h.x = __uint_as_float(t);
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.y)); h.y = __uint_as_float(t);
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.z)); h.z = __uint_as_float(t);
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.w)); h.w = __uint_as_float(t);
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.x - h.x)); l.x = __uint_as_float(t);
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.y - h.y)); l.y = __uint_as_float(t);
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.z - h.z)); l.z = __uint_as_float(t);
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.w - h.w)); l.w = __uint_as_float(t);
+        reinterpret_cast<float4*>(qhi + (size_t)pi * 128)[lane] = h;
+        reinterpret_cast<float4*>(qlo + (size_t)pi * 128)[lane] = l;
+        inexact |= (l.x != 0.f) | (l.y != 0.f) | (l.z != 0.f) | (l.w != 0.f);
+    }
+    if (__any_sync(0xffffffffu, inexact) && lane == 0) atomicOr(not_exact, 1);
+}
+
+size_t ivf_tc_workspace_ints(int64_t nq, int nprobe, int nlist) {
+    const size_t n_pairs = (size_t)nq * nprobe;
+    // list_cnt[nlist] q_cand[nq] n_items[1] flag[1] pair_start[nlist+1] cursor[nlist] pairs[n_pairs] (+ alignment) items[4 x (n_pairs/128 + nlist + 1)]
+    return (size_t)nlist * 3 + (size_t)nq + 8 + n_pairs + 4 + 4 * (n_pairs / 128 + (size_t)nlist + 1);
+}
+
+// Pair grouping for the tensor-core scan: work items of <= 128 pairs, long lists first; gathers and splits the queries.
+// Outputs (inside ws): *items, *n_items (device), *pairs; qhi/qlo [(n_pairs + 128) x 128]; q_not_exact (device flag).
+int launch_ivf_tc_prep(const float* q, const int32_t* offsets, int nlist, const int32_t* list_order, const int32_t* probes, int64_t nq,
+                       int nprobe, int32_t* ws, float* qhi, float* qlo, const int4** items_out, const int32_t** n_items_out,
+                       const int32_t** pairs_out, int32_t** q_cand_out, int** q_not_exact_out, cudaStream_t st) {
+    const int64_t n_pairs = nq * nprobe;
+    if (n_pairs > 0x7fffffff - 256) return fail(VS_ERR_UNSUPPORTED, "IVF list-major scan: too many (query, probe) pairs");
+    int32_t* list_cnt = ws;
+    int32_t* q_cand = list_cnt + nlist;
+    int32_t* n_items = q_cand + nq;
+    int32_t* flag = n_items + 1;
+    int32_t* pair_start = flag + 1;
+    int32_t* cursor = pair_start + nlist + 1;
+    int32_t* pairs = cursor + nlist;
+    int4* items = reinterpret_cast<int4*>(ws + ((pairs + n_pairs - ws + 3) & ~(ptrdiff_t)3));
+    VSB_CUDA(cudaMemsetAsync(ws, 0, sizeof(int32_t) * ((size_t)nlist + (size_t)nq + 2), st));
+    const unsigned gb = (unsigned)std::min<int64_t>(ceil_div64(n_pairs, 256), 148 * 8);
+    lm_count_kernel<<<gb, 256, 0, st>>>(probes, n_pairs, nprobe, offsets, list_cnt, q_cand);
+    lm_scan_kernel<<<1, 1024, 0, st>>>(list_cnt, nlist, list_order, offsets, pair_start, cursor, items, n_items, 128);
+    lm_fill_kernel<<<gb, 256, 0, st>>>(probes, n_pairs, cursor, pairs);
+    lm_gather_split_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(n_pairs, 8), 148 * 16), 256, 0, st>>>(q, pairs, n_pairs, nprobe, qhi,
+                                                                                                           qlo, flag);
+    VSB_CUDA(cudaGetLastError());
+    *items_out = items;
+    *n_items_out = n_items;
+    *pairs_out = pairs;
+    *q_cand_out = q_cand;
+    *q_not_exact_out = flag;
+    return VS_OK;
+}
+
+int launch_ivf_counts(const int32_t* q_cand, int64_t nq, int k, int32_t* out_counts, unsigned long long* total, cudaStream_t st) {
     lm_counts_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(nq, 256), 148), 256, 0, st>>>(q_cand, nq, k, out_counts, total);
     VSB_CUDA(cudaGetLastError());
     return VS_OK;

@@ -327,7 +327,24 @@ struct RefineArgs {
     const TcQueryParams* qp;
     int32_t* uncert_count;  // number of uncertified queries
     int32_t* uncert_list;   // their indices
+    const int32_t* ivf_idmap;  // IVF re-score mode (see launch_merge_lists)
 };
+
+// q . x in the reference's NEON order (IVFIndex.cpp:278-357 computeDotProductsContiguous): four accumulators by d mod 4,
+// FMA over d = 0, 4, 8, ..., then (l0 + l1) + (l2 + l3) — bit-identical to the scan kernels and the CPU restatement
+__device__ __forceinline__ float dot_neon4_128(const float* __restrict__ q, const float* __restrict__ x) {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 8
+    for (int c4 = 0; c4 < 32; ++c4) {
+        const float4 qv = __ldg(reinterpret_cast<const float4*>(q) + c4);
+        const float4 xv = __ldg(reinterpret_cast<const float4*>(x) + c4);
+        a0 = fmaf(qv.x, xv.x, a0);
+        a1 = fmaf(qv.y, xv.y, a1);
+        a2 = fmaf(qv.z, xv.z, a2);
+        a3 = fmaf(qv.w, xv.w, a3);
+    }
+    return __fadd_rn(__fadd_rn(a0, a1), __fadd_rn(a2, a3));
+}
 
 // Exact fp32 dot products q . x_id of a warp's (up to 32) candidates, lane r holding candidate r's local row id (or -1).
 // Every row is read COOPERATIVELY — lane i takes components 4i .. 4i+3 (one coalesced 512-byte request per row) — and the
@@ -373,7 +390,12 @@ __device__ __forceinline__ void merge_tail(float myk, int32_t myid, float lastk,
         lb_key_out[q] = lasti >= 0 ? lastk : INF;
         lb_id_out[q] = lasti >= 0 ? lasti : 0x7fffffff;
     }
-    if (rf.base) {
+    if (rf.ivf_idmap) {
+        if (myid >= 0) {
+            myk = -dot_neon4_128(rf.q + (size_t)q * 128, rf.base + (size_t)myid * 128);
+            myid = __ldg(rf.ivf_idmap + myid);
+        }
+    } else if (rf.base) {
         const float dot = warp_refine_dots(rf.q + (size_t)q * 128, rf.base, nsel, myid, lane);
         if (myid >= 0) myk = fmaf(-2.0f, dot, __fadd_rn(__ldg(rf.qnorm + q), __ldg(rf.bnorm + myid)));
     }
@@ -504,7 +526,7 @@ __global__ void __launch_bounds__(128) merge_lists_kernel(const float* __restric
                lb_id_out, rf);
 }
 
-// The same for n_lists <= 32 (every tensor-core / IVF / exchange merge): the lists are staged in shared memory with coalesced
+// The same for n_lists <= 96 (every tensor-core / IVF / exchange merge): the lists are staged in shared memory with coalesced
 // loads (a list = 128 contiguous bytes), lane j walks list j with a cursor, and every round the warp takes the smallest head
 // (shuffle arg-min) — no register-list shifting, ~1/4 of the instructions of the general kernel.
 __global__ void __launch_bounds__(128) merge_small_kernel(const float* __restrict__ part_key, const int32_t* __restrict__ part_id,
@@ -538,18 +560,25 @@ __global__ void __launch_bounds__(128) merge_small_kernel(const float* __restric
         si[l * 32 + lane] = ii;
     }
     __syncwarp();
-    int cur = 0;
-    float hk = INF;
-    int32_t hid = -1;
-    if (lane < n_lists) {
-        hk = sk[lane * 32];
-        hid = si[lane * 32];
+    // lane j walks lists j, j + 32, j + 64 (n_lists <= 96) with one cursor each
+    int cur[3] = {0, 0, 0};
+    float hk[3];
+    int32_t hid[3];
+#pragma unroll
+    for (int u = 0; u < 3; ++u) {
+        const int l = lane + 32 * u;
+        hid[u] = l < n_lists ? si[l * 32] : -1;
+        hk[u] = hid[u] >= 0 ? sk[l * 32] : INF;
     }
     float myk = INF, lastk = INF;
     int32_t myid = -1, lasti = -1;
     for (int r = 0; r < nsel; ++r) {
-        float bk = hk;
-        int32_t bi = hid;
+        // this lane's best head, then the warp's
+        int bu = 0;
+        if (pair_less(hk[1], hid[1], hk[bu], hid[bu])) bu = 1;
+        if (pair_less(hk[2], hid[2], hk[bu], hid[bu])) bu = 2;
+        float bk = bu == 0 ? hk[0] : (bu == 1 ? hk[1] : hk[2]);
+        int32_t bi = bu == 0 ? hid[0] : (bu == 1 ? hid[1] : hid[2]);
         int src = lane;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -569,9 +598,14 @@ __global__ void __launch_bounds__(128) merge_small_kernel(const float* __restric
         lastk = bk;
         lasti = bi;
         if (src == lane && bi >= 0) {
-            ++cur;
-            hid = cur < list_len ? si[lane * 32 + cur] : -1;
-            hk = hid >= 0 ? sk[lane * 32 + cur] : INF;
+#pragma unroll
+            for (int u = 0; u < 3; ++u)
+                if (u == bu) {
+                    const int l = lane + 32 * u;
+                    ++cur[u];
+                    hid[u] = cur[u] < list_len ? si[l * 32 + cur[u]] : -1;
+                    hk[u] = hid[u] >= 0 ? sk[l * 32 + cur[u]] : INF;
+                }
         }
     }
     merge_tail(myk, myid, lastk, lasti, q, lane, nsel, k, id_base, neg_out, out_key, out_id, out_stride, out_off, lb_key_out,
@@ -583,15 +617,18 @@ int launch_merge_lists(const float* part_key, const int32_t* part_id, int n_list
                        int out_off, float* lb_key_out, int32_t* lb_id_out, const float* rf_base, const float* rf_bnorm,
                        const float* rf_q, const float* rf_qnorm, cudaStream_t st, const TcQueryParams* cert_qp,
                        int32_t* uncert_count, int32_t* uncert_list, size_t list_stride, const int32_t* trailer,
-                       int32_t* trailer_total_out) {
+                       int32_t* trailer_total_out, const int32_t* ivf_idmap) {
     if (nq <= 0) return VS_OK;
     if (nsel > list_len || k > nsel || nsel > 32) return fail(VS_ERR_INVALID, "merge: need k <= nsel <= list length <= 32");
     if (cert_qp && (!rf_base || !uncert_count || !uncert_list)) return fail(VS_ERR_INVALID, "merge: certification needs the refine");
     const unsigned blocks = (unsigned)ceil_div64(nq, 4);
-    RefineArgs rf{rf_base, rf_bnorm, rf_q, rf_qnorm, cert_qp, uncert_count, uncert_list};
+    RefineArgs rf{rf_base, rf_bnorm, rf_q, rf_qnorm, cert_qp, uncert_count, uncert_list, ivf_idmap};
     BlockArgs ba{list_stride, trailer, trailer_total_out};
-    if (n_lists <= 32 && round_up_ktop(list_len) != 0) {
-        const size_t smem = (size_t)4 * n_lists * 64 * sizeof(float);  // <= 32 KB
+    if (ivf_idmap && (!rf_base || !rf_q || n_lists > 96)) return fail(VS_ERR_INVALID, "merge: IVF re-score needs vectors, queries and <= 96 lists");
+    if (n_lists <= 96 && round_up_ktop(list_len) != 0) {
+        const size_t smem = (size_t)4 * n_lists * 64 * sizeof(float);  // <= 96 KB
+        if (smem > 48 * 1024)  // per device, hence not cached in a static
+            VSB_CUDA(cudaFuncSetAttribute(merge_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 96 * 64 * (int)sizeof(float)));
         merge_small_kernel<<<blocks, 128, smem, st>>>(part_key, part_id, n_lists, nq, list_len, nsel, k, id_base, neg_in, neg_out,
                                                      out_key, out_id, out_stride, out_off, lb_key_out, lb_id_out, rf, ba);
         VSB_CUDA(cudaGetLastError());

@@ -67,6 +67,9 @@ int launch_exact_tc(const CUtensorMap& tmA_hi, const CUtensorMap& tmA_lo, const 
                     int32_t* gthr, int nq, int64_t n_rows, const TcPlan& plan,
                     int ktop, int mode, const float* key_scale_dev, const float* lb_key, const int32_t* lb_id, float* part_key,
                     int32_t* part_id, cudaStream_t st);
+int launch_exact_tc_ivf(const CUtensorMap& tmA_hi, const CUtensorMap& tmA_lo, const CUtensorMap& tmB_hi, const CUtensorMap& tmB_lo,
+                        const int4* items, const int32_t* n_items, const int32_t* pairs, int nprobe, int32_t* gthr, int nq, int ktop,
+                        bool split3, float* part_key, int32_t* part_id, int num_sms, cudaStream_t st);
 int tc_lists_per_split(int mode);  // partial lists written per (split, query): 1 (TC_F16, mode 2) or 3
 int tc_set_attributes();  // opt-in to > 48 KB dynamic shared memory for every instantiation
 
@@ -85,7 +88,11 @@ int launch_merge_lists(const float* part_key, const int32_t* part_id, int n_list
                        int32_t* uncert_count = nullptr, int32_t* uncert_list = nullptr,
                        // lists inside per-shard exchange blocks: list l starts list_stride 4-byte words after list l-1
                        // (0 = dense [list][nq][len]); trailer: word 0 of each block's trailer, summed into *trailer_total_out
-                       size_t list_stride = 0, const int32_t* trailer = nullptr, int32_t* trailer_total_out = nullptr);
+                       size_t list_stride = 0, const int32_t* trailer = nullptr, int32_t* trailer_total_out = nullptr,
+                       // IVF re-score (rf_base = list-contiguous vectors, rf_q = queries, ids = row positions): the selected
+                       // candidates get their inner product in the reference's NEON order (IVFIndex.cpp:278-357), key = -score,
+                       // and are ranked / returned with their ORIGINAL ids ivf_idmap[position]
+                       const int32_t* ivf_idmap = nullptr);
 int launch_sort_rows(float* key, int32_t* id, int64_t nq, int k, cudaStream_t st);
 // G <= 32 sorted per-shard lists [G][nq][k] of any k -> the k best per query, canonical order (neg: largest key first)
 int launch_merge_shards(const float* in_key, const int32_t* in_id, int n_shards, int64_t nq, int k, int neg, float* out_key,
@@ -121,6 +128,12 @@ size_t ivf_lm_workspace_ints(int64_t nq, int nprobe, int nlist);
 int launch_ivf_listmajor(const float* q, const float* vectors, const int32_t* offsets, const int32_t* id_map, int nlist,
                          const int32_t* list_order /* lists by descending length */, const int32_t* probes, int64_t nq, int nprobe, int k, int32_t* ws, float* part_key, int32_t* part_id,
                          int32_t* out_counts, unsigned long long* total, int num_sms, cudaStream_t st);
+// tensor-core list-major scan: pair grouping into work items of <= 128 pairs (long lists first) + gathered TF32-split queries
+size_t ivf_tc_workspace_ints(int64_t nq, int nprobe, int nlist);
+int launch_ivf_tc_prep(const float* q, const int32_t* offsets, int nlist, const int32_t* list_order, const int32_t* probes, int64_t nq,
+                       int nprobe, int32_t* ws, float* qhi, float* qlo, const int4** items_out, const int32_t** n_items_out,
+                       const int32_t** pairs_out, int32_t** q_cand_out, int** q_not_exact_out, cudaStream_t st);
+int launch_ivf_counts(const int32_t* q_cand, int64_t nq, int k, int32_t* out_counts, unsigned long long* total, cudaStream_t st);
 int ivf_set_attributes();
 int ivf_scan_rows_per_chunk();
 

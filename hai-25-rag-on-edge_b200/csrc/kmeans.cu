@@ -330,11 +330,9 @@ int launch_multisplit(const int32_t* lab, int64_t n, int nlist, int32_t* ws, int
     const int n_blocks = (int)ceil_div64(n, 1024);
     const size_t smem = sizeof(int32_t) * (size_t)nlist;
     if (smem > 200 * 1024) return fail(VS_ERR_UNSUPPORTED, "multisplit: too many lists");
-    static bool attr = false;
-    if (!attr) {
+    if (smem > 48 * 1024) {  // per device, hence not cached in a static
         VSB_CUDA(cudaFuncSetAttribute(ms_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         VSB_CUDA(cudaFuncSetAttribute(ms_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr = true;
     }
     ms_count_kernel<<<n_blocks, 1024, smem, st>>>(lab, n, nlist, n_blocks, ws);
     ms_scan_kernel<<<1, 1024, 0, st>>>(ws, (int64_t)nlist * n_blocks, nlist, n_blocks, offsets);

@@ -19,7 +19,14 @@ def make_index(vsb, oracle, n, nlist, seed=3, law="mix"):
     return base, cent, order, offsets
 
 
-@pytest.mark.parametrize("scan", ["query_major", "list_major"])
+def _set_scan(monkeypatch, scan):
+    """query_major = K6; list_major = K8 (FFMA, scores bit-identical by construction); list_major_tc = the tensor-core
+    list-major scan (TF32 candidates + re-score in the reference's summation order)."""
+    monkeypatch.setenv("VSB_IVF_LM", "0" if scan == "query_major" else "1")
+    monkeypatch.setenv("VSB_IVF_TC", "1" if scan == "list_major_tc" else "0")
+
+
+@pytest.mark.parametrize("scan", ["query_major", "list_major", "list_major_tc"])
 @pytest.mark.parametrize("law", ["mix", "cont"])
 @pytest.mark.parametrize("n,nlist,nq,k,nprobe", [(20000, 64, 50, 10, 8), (5000, 16, 33, 5, 16), (3000, 300, 7, 10, 3),
                                                  (100000, 256, 200, 10, 32), (2000, 8, 5, 32, 100), (30000, 40, 700, 16, 5),
@@ -27,7 +34,7 @@ def make_index(vsb, oracle, n, nlist, seed=3, law="mix"):
 def test_search_matches_restatement(scan, law, n, nlist, nq, k, nprobe, gpu_vsb, oracle, monkeypatch):
     """Both fine-scan kernels (K6 query-major, K8 list-major) against the CPU restatement: same probe sets, bit-identical
     scores, canonical ids, counts and total candidates."""
-    monkeypatch.setenv("VSB_IVF_LM", "1" if scan == "list_major" else "0")
+    _set_scan(monkeypatch, scan)
     vsb = gpu_vsb
     base, cent, order, offsets = make_index(vsb, oracle, n, nlist, law=law)
     qry = vsb.synth.make(law, 99, nq)
@@ -164,13 +171,14 @@ def test_full_size_list_major_equals_query_major(tmp_path, gpu_vsb, monkeypatch)
     idx = vsb.IvfIndex(d_)
     try:
         for nprobe in (8, 32):
-            monkeypatch.setenv("VSB_IVF_LM", "0")
+            _set_scan(monkeypatch, "query_major")
             want = idx.search_batch(qry, k, nprobe)
-            monkeypatch.setenv("VSB_IVF_LM", "1")
-            for _ in range(3):
-                got = idx.search_batch(qry, k, nprobe)
-                assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
-                assert np.array_equal(got[2], want[2]) and got[3] == want[3]
+            for scan in ("list_major", "list_major_tc"):
+                _set_scan(monkeypatch, scan)
+                for _ in range(3):
+                    got = idx.search_batch(qry, k, nprobe)
+                    assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]), (scan, nprobe)
+                    assert np.array_equal(got[2], want[2]) and got[3] == want[3]
     finally:
         idx.close()
 
@@ -181,7 +189,7 @@ def _hp2_cases():
     return golden_cases("hp2_")
 
 
-@pytest.mark.parametrize("scan", ["query_major", "list_major"])
+@pytest.mark.parametrize("scan", ["query_major", "list_major", "list_major_tc"])
 @pytest.mark.parametrize("path", _hp2_cases(), ids=lambda p: p.split("/")[-1][:-4])
 def test_gpu_matches_reference_ivfsearcher_golden(path, scan, tmp_path, gpu_vsb, oracle, monkeypatch):
     """HP2 pin on the GPU: tests/golden/hp2_*.npz hold what the reference's OWN searcher (IVFSearcher.search,
@@ -191,7 +199,7 @@ def test_gpu_matches_reference_ivfsearcher_golden(path, scan, tmp_path, gpu_vsb,
     ties and its recall@k."""
     from util import assert_ivf_matches_golden, load_golden_ivf
 
-    monkeypatch.setenv("VSB_IVF_LM", "1" if scan == "list_major" else "0")
+    _set_scan(monkeypatch, scan)
     vsb = gpu_vsb
     g, base, qry, cent, labels, offsets, indices = load_golden_ivf(path, vsb.synth)
     k, nlist = int(g["k"]), int(g["nlist"])
