@@ -88,7 +88,8 @@ int exact_free(vs_exact* h) {
     if (h->d_fold) cudaFree(h->d_fold);
     if (h->d_norm) cudaFree(h->d_norm);
     for (DevBuf* b : {&h->q, &h->qhi, &h->qlo, &h->qf16, &h->qnorm, &h->part_key, &h->part_id, &h->lbk, &h->lbi, &h->out_ids,
-                      &h->out_keys, &h->flag, &h->gthr, &h->qparams, &h->qfold, &h->unc_list, &h->fb_q, &h->fb_ids, &h->fb_keys})
+                      &h->out_keys, &h->flag, &h->gthr, &h->qparams, &h->qfold, &h->unc_list, &h->fb_q, &h->fb_ids, &h->fb_keys,
+                      &h->f_smin, &h->f_thr, &h->f_cnt, &h->f_cand})
         b->release();
     for (auto& g : h->graphs) cudaGraphExecDestroy(g.exec);
     for (DevBuf* b : {&h->g_q, &h->g_qnorm, &h->g_part_key, &h->g_part_id, &h->g_ids, &h->g_keys}) b->release();
@@ -235,63 +236,95 @@ int exact_create_common(vs_exact_t** out, const float* base, bool on_device, int
     return VS_OK;
 }
 
-// The candidate pass of the certified search: query prep (norms, abs-max -> power-of-two scale, fp16 copy, bound
-// constants) and the fused fp16 tensor-core kernel.  Leaves n_lists sorted partial lists of 32 (key, local id) per query
-// in h->part_key / h->part_id.
-static int exact_f16_candidate_pass(vs_exact* h, const float* q_dev, int64_t nq, cudaStream_t st, int* n_lists_out) {
-    const int ktop = kMaxRegK;
+// The fp16 candidate pass is a THRESHOLD FILTER: every row whose fp16 key lies below a per-query threshold thr[q] becomes a
+// candidate (unordered (key, id) pairs appended to the query's array); nothing is kept sorted inside the tensor-core kernel.
+// Any threshold is legal, because the merge certifies each query against the bound it actually used ("no row outside the
+// kept candidates has a key below B"); a threshold that turns out too tight only sends the query to the fp32 fallback.  thr[q]
+// comes from a SAMPLE pass over every stride-th base tile: the m-th smallest of the query's group minima has at least m
+// sampled rows at or below it, i.e. about m * stride (~ 128) rows of the whole base — enough margin for k <= 16, few enough
+// to keep the candidate traffic negligible.
+constexpr int kF16CandCap = 512;      // candidates kept per query (more: the query is redone on the fp32 path)
+constexpr int kF16SampleOff = 3;      // first sampled tile
+constexpr int kF16MinSampleTiles = 24;
+
+// Sample geometry: one base tile in 16 and the 8th smallest group minimum (~ 8 x 16 rows below the threshold) for bases of
+// >= 400 tiles (~ 51 K rows); one tile in 4 and the 16th smallest group minimum below that (few groups: several of the
+// smallest sampled keys share a group, which only loosens the threshold).
+struct F16Sample {
+    int stride, m, tiles;
+};
+static F16Sample f16_sample_plan(int64_t n) {
+    const int64_t n_tiles = ceil_div64(n, 128);
+    F16Sample s;
+    s.stride = n_tiles >= 400 ? 16 : 4;
+    s.m = n_tiles >= 400 ? 8 : 16;
+    if (const char* e = getenv("VSB_F16_STRIDE")) s.stride = std::max(1, atoi(e));
+    if (const char* e = getenv("VSB_F16_M")) s.m = std::max(1, atoi(e));
+    s.tiles = n_tiles > kF16SampleOff ? (int)((n_tiles - kF16SampleOff + s.stride - 1) / s.stride) : 0;
+    return s;
+}
+// bases of <= kF16CandCap rows need no threshold at all; otherwise the sample must be large enough to mean something
+static bool f16_pass_supported(int64_t n) { return n <= kF16CandCap || f16_sample_plan(n).tiles >= kF16MinSampleTiles; }
+
+// Query prep (norms, abs-max -> power-of-two scale, fp16 copy, bound constants), sample pass, thresholds, filter pass.
+// Leaves the candidates in h->f_cand / h->f_cnt and the thresholds in h->f_thr.
+static int exact_f16_candidate_pass(vs_exact* h, const float* q_dev, int64_t nq, cudaStream_t st) {
     int* flag = h->flag.as<int>();
     VSB_TRY(h->qnorm.reserve(sizeof(float) * (size_t)nq));
     VSB_TRY(h->qf16.reserve(2 * (size_t)nq * 128));
     VSB_TRY(h->qparams.reserve(sizeof(TcQueryParams)));
     VSB_TRY(h->qfold.reserve((size_t)128 * TC_FOLD_COLS * 2));
+    VSB_TRY(h->f_thr.reserve(sizeof(float) * (size_t)nq));
+    VSB_TRY(h->f_cnt.reserve(sizeof(int32_t) * (size_t)nq));
+    VSB_TRY(h->f_cand.reserve(sizeof(uint2) * (size_t)nq * kF16CandCap));
     VSB_CUDA(cudaMemsetAsync(flag + 1, 0, 2 * sizeof(int), st));
     VSB_TRY(launch_query_prep(q_dev, nq, h->qnorm.as<float>(), reinterpret_cast<float*>(flag + 2), st));
     TcQueryParams* qp = h->qparams.as<TcQueryParams>();
     VSB_TRY(launch_tc_query_params(reinterpret_cast<const float*>(flag + 2), h->s_b, h->bn_max, qp, h->qfold.p, st));
     VSB_TRY(launch_to_half_scaled(q_dev, nq * 128, 1.f, qp, h->qf16.p, st));  // the NEGATED scaled copy
-    const TcPlan plan = tc_make_plan(h->n, nq, h->num_sms, 2);
-    const int n_lists = plan.n_splits * tc_lists_per_split(2);
-    VSB_TRY(h->part_key.reserve(sizeof(float) * (size_t)n_lists * nq * ktop));
-    VSB_TRY(h->part_id.reserve(sizeof(int32_t) * (size_t)n_lists * nq * ktop));
-    // shared bounds: [nq] live 32nd-best keys (ordered ints), then per finished unit the 8th / 16th best key of every query
-    // ([2][n_splits][nq] floats); 0x7f7f7f7f = "nothing known yet" in both encodings
-    const size_t gthr_words = (size_t)nq * (1 + 2 * (size_t)plan.n_splits);
-    VSB_TRY(h->gthr.reserve(sizeof(int32_t) * gthr_words));
-    VSB_CUDA(cudaMemsetAsync(h->gthr.p, 0x7f, sizeof(int32_t) * gthr_words, st));
     CUtensorMap tmA, tmAe;
     VSB_TRY(make_tmap_2d(&tmA, h->qf16.p, (uint64_t)nq, 128, 2, 128));
     VSB_TRY(make_tmap_fold(&tmAe, h->qfold.p, 128, 128));
     if (h->profile) VSB_CUDA(cudaEventRecord(h->ev0, st));
-    VSB_TRY(launch_exact_tc(tmA, tmAe, h->tmB16, h->d_norm, h->gthr.as<int32_t>(), (int)nq, h->n, plan, ktop, 2,
-                            nullptr, nullptr, nullptr, h->part_key.as<float>(), h->part_id.as<int32_t>(), st));
+    if (h->n <= kF16CandCap) {
+        VSB_TRY(launch_tc_fill_thr((int)nq, h->f_thr.as<float>(), h->f_cnt.as<int32_t>(), st));
+    } else {
+        const F16Sample sp = f16_sample_plan(h->n);
+        const int stride = sp.stride, m = sp.m, g_tiles = sp.tiles;
+        if (g_tiles < 1) return fail(VS_ERR_UNSUPPORTED, "fp16 candidate pass: base too small for the sample pass");
+        const TcPlan splan = tc_make_plan((int64_t)g_tiles * 128, nq, h->num_sms, 2);
+        const int n_groups = splan.n_splits * tc_sample_groups_per_split();
+        VSB_TRY(h->f_smin.reserve(sizeof(float) * (size_t)n_groups * nq));
+        VSB_TRY(launch_exact_tc_f16(tmA, tmAe, h->tmB16, (int)nq, h->n, splan, true, stride, kF16SampleOff, h->f_smin.as<float>(), nullptr,
+                                    nullptr, nullptr, 0, st));
+        VSB_TRY(launch_tc_select_thr(h->f_smin.as<float>(), n_groups, (int)nq, m, h->f_thr.as<float>(), h->f_cnt.as<int32_t>(), st));
+    }
+    const TcPlan plan = tc_make_plan(h->n, nq, h->num_sms, 2);
+    VSB_TRY(launch_exact_tc_f16(tmA, tmAe, h->tmB16, (int)nq, h->n, plan, false, 1, 0, nullptr, h->f_thr.as<float>(),
+                                h->f_cnt.as<int32_t>(), h->f_cand.p, kF16CandCap, st));
     if (h->profile) {
         VSB_CUDA(cudaEventRecord(h->ev1, st));
         h->ev_valid = true;
     }
-    *n_lists_out = n_lists;
     return VS_OK;
 }
 
-// Certified candidate pass: scaled fp16 tensor-core kernel keeps the 32 best keys per query (error bounded by
-// cert_a*sqrt(qn)+cert_b), the merge kernel recomputes those 32 distances in exact fp32, ranks them and certifies
-// the top k; the (rare) uncertified queries are redone on the 3xTF32 / FFMA path.  Synchronises `st` once (4-byte
-// count of uncertified queries).
+// Certified candidate pass: the scaled fp16 tensor-core kernel collects every row below the query's threshold (key error
+// bounded by cert_a*sqrt(qn)+cert_b), the merge kernel keeps the <= 32 best of them, recomputes their distances in exact
+// fp32, ranks them and certifies the top k; the (rare) uncertified queries are redone on the 3xTF32 / FFMA path.  The
+// 4-byte count of uncertified queries is waited for in exact_certified_finish.
 static int exact_search_certified(vs_exact* h, const float* q_dev, int64_t nq, int k, int32_t* out_ids, float* out_dists,
                                   cudaStream_t st, int32_t* unc_dev) {
-    const int ktop = kMaxRegK;
     int* flag = h->flag.as<int>();
     VSB_TRY(h->unc_list.reserve(sizeof(int32_t) * (size_t)nq));
-    int n_lists = 0;
-    VSB_TRY(exact_f16_candidate_pass(h, q_dev, nq, st, &n_lists));
+    VSB_TRY(exact_f16_candidate_pass(h, q_dev, nq, st));
     TcQueryParams* qp = h->qparams.as<TcQueryParams>();
     // count of uncertified queries: the handle's own word (zeroed by the candidate pass), or the caller's (trailer of an
     // exchange block, already zeroed)
     int32_t* unc = unc_dev ? unc_dev : flag + 1;
-    VSB_TRY(launch_merge_lists(h->part_key.as<float>(), h->part_id.as<int32_t>(), n_lists, nq, ktop, ktop, k, h->id_base, 0, 0,
-                               out_dists, out_ids, k, 0, nullptr, nullptr, h->d_base, h->d_norm, q_dev, h->qnorm.as<float>(), st,
-                               qp, unc, h->unc_list.as<int32_t>()));
-    h->last_launches = 5;
+    VSB_TRY(launch_filter_merge(h->f_cand.p, h->f_cnt.as<int32_t>(), kF16CandCap, h->f_thr.as<float>(), nq, k, h->id_base, out_dists,
+                                out_ids, k, h->d_base, h->d_norm, q_dev, h->qnorm.as<float>(), qp, unc, h->unc_list.as<int32_t>(), st));
+    h->last_launches = h->n <= kF16CandCap ? 6 : 7;
     h->last_precision = VS_PREC_F16_CERTIFIED;
     h->last_fallback = 0;
     VSB_CUDA(cudaMemcpyAsync(h->h_flag + 1, unc, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -362,7 +395,9 @@ int exact_search_core(vs_exact* h, const float* q_dev, int64_t nq, int k, int pr
     // 9..448 queries: TF32 tensor-core kernel (0.27-0.45 ms: fewer launches and no host round trip); beyond that the
     // certified fp16 candidate pass wins (0.49 vs 0.52 ms at 512 queries, 1.7 vs 3.4 ms at 4096)
     constexpr int64_t kAutoFfmaMax = 8, kAutoF16Min = 449;
-    if (prec == VS_PREC_AUTO && nq >= kAutoF16Min && k <= 16 && dim == 128) prec = VS_PREC_F16_CERTIFIED;
+    if (prec == VS_PREC_AUTO && nq >= kAutoF16Min && k <= 16 && dim == 128 && f16_pass_supported(h->n)) prec = VS_PREC_F16_CERTIFIED;
+    // bases too small for a meaningful sample pass (513 .. ~13 K rows) take the 3xTF32 path: same answer, and just as fast there
+    if (prec == VS_PREC_F16_CERTIFIED && dim == 128 && !f16_pass_supported(h->n)) prec = VS_PREC_FP32_3XTF32;
     const bool want_tc = (prec == VS_PREC_FP32_3XTF32 || prec == VS_PREC_TF32_1X || prec == VS_PREC_F16_CERTIFIED ||
                           (prec == VS_PREC_AUTO && nq > kAutoFfmaMax));
     if (want_tc && dim != 128) return fail(VS_ERR_UNSUPPORTED, "tensor-core path needs dim == 128");
@@ -643,12 +678,12 @@ int vs_exact_debug_f16_candidates(vs_exact_t* h, const float* queries, int64_t n
     VSB_TRY(h->out_ids.reserve(sizeof(int32_t) * (size_t)nq * ktop));
     VSB_TRY(h->out_keys.reserve(sizeof(float) * (size_t)nq * ktop));
     VSB_CUDA(cudaMemcpyAsync(h->q.p, queries, sizeof(float) * (size_t)nq * 128, cudaMemcpyHostToDevice, st));
-    int n_lists = 0;
-    VSB_TRY(exact_f16_candidate_pass(h, h->q.as<float>(), nq, st, &n_lists));
-    // the 32 best candidate keys per query exactly as the tensor-core pass ranked them: no refine, no certification
-    VSB_TRY(launch_merge_lists(h->part_key.as<float>(), h->part_id.as<int32_t>(), n_lists, nq, ktop, ktop, ktop, 0, 0, 0,
-                               h->out_keys.as<float>(), h->out_ids.as<int32_t>(), ktop, 0, nullptr, nullptr, nullptr, nullptr,
-                               nullptr, nullptr, st));
+    if (!f16_pass_supported(h->n)) return fail(VS_ERR_UNSUPPORTED, "the fp16 candidate pass needs <= 512 or >= ~13 K base rows");
+    VSB_TRY(exact_f16_candidate_pass(h, h->q.as<float>(), nq, st));
+    // the (up to) 32 best candidate keys per query exactly as the tensor-core pass ranked them: no refine, no certification
+    VSB_TRY(launch_filter_merge(h->f_cand.p, h->f_cnt.as<int32_t>(), kF16CandCap, h->f_thr.as<float>(), nq, ktop, 0,
+                                h->out_keys.as<float>(), h->out_ids.as<int32_t>(), ktop, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                nullptr, nullptr, st));
     std::vector<float> qn((size_t)nq);
     TcQueryParams qp;
     VSB_CUDA(cudaMemcpyAsync(out_ids, h->out_ids.p, sizeof(int32_t) * (size_t)nq * ktop, cudaMemcpyDeviceToHost, st));

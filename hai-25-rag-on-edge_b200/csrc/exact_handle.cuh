@@ -35,6 +35,8 @@ struct vs_exact {
     // workspace (grow-only)
     DevBuf q, qhi, qlo, qf16, qnorm, part_key, part_id, lbk, lbi, out_ids, out_keys, flag, gthr, qparams, qfold, unc_list, fb_q,
         fb_ids, fb_keys;
+    // fp16 threshold-filter candidate pass: group minima of the sample pass, per-query thresholds, candidate counters / arrays
+    DevBuf f_smin, f_thr, f_cnt, f_cand;
     // batch <= 8 host calls (vs_exact_search_f32): the whole call — H2D, query norms, streaming kernel, merge, D2H — as ONE
     // CUDA graph per (nq, k), over workspaces and pinned staging buffers that only the graphs touch
     struct SmallGraph {

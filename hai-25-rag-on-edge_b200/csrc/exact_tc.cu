@@ -127,6 +127,7 @@ int launch_exact_tc_ivf(const CUtensorMap& tmA_hi, const CUtensorMap& tmA_lo, co
 #undef VSB_IVF_CASE
 }
 
+int tc_sample_groups_per_split() { return TC_SAMPLE_GROUPS; }
 int tc_lists_per_split(int mode) { return mode == TC_F16 ? 1 : TC_EPI_GROUPS; }
 
 int tc_set_attributes() {
@@ -143,6 +144,7 @@ int tc_set_attributes() {
     VSB_TRY((set_attr_one<32, TC_TF32X1, true>()));
     VSB_TRY((set_attr_one<32, TC_TF32X3, true>()));
     VSB_TRY((set_attr_one<32, TC_F16, false>()));
+    VSB_TRY((set_attr_one<1, TC_F16, false>()));
     return VS_OK;
 }
 
@@ -182,7 +184,7 @@ int launch_exact_tc(const CUtensorMap& tmA_hi, const CUtensorMap& tmA_lo, const 
         p.stats = d_stats;
     }
     if (lb_key && ktop != 32) return fail(VS_ERR_INVALID, "tc: lower bound needs the 32-entry list");
-    if (lb_key && mode == TC_F16) return fail(VS_ERR_INVALID, "tc: the fp16 candidate pass has no multi-pass mode");
+    if (mode == TC_F16) return fail(VS_ERR_INVALID, "tc: the fp16 candidate pass is launched by launch_exact_tc_f16");
     const CUtensorMap& tmB_hi = plan.cl == 2 ? tmB.hi_half : tmB.hi;
     const CUtensorMap& tmB_lo = plan.cl == 2 ? tmB.lo_half : tmB.lo;
 #define VSB_TC_LAUNCH(KT, MD, LB) VSB_TRY((launch_one<KT, MD, LB>(plan, tmA_hi, tmA_lo, tmB_hi, tmB_lo, p, st)))
@@ -193,12 +195,7 @@ int launch_exact_tc(const CUtensorMap& tmA_hi, const CUtensorMap& tmA_lo, const 
         else                                         \
             VSB_TC_LAUNCH(KT, TC_TF32X1, false);     \
         break;
-    if (mode == TC_F16) {
-        if (ktop == 32)
-            VSB_TC_LAUNCH(32, TC_F16, false);
-        else
-            return fail(VS_ERR_INVALID, "tc: the fp16 candidate pass keeps 32 candidates per query");
-    } else {
+    {
         switch (ktop) {
             VSB_TC_CASE(1)
             VSB_TC_CASE(5)
@@ -232,14 +229,60 @@ int launch_exact_tc(const CUtensorMap& tmA_hi, const CUtensorMap& tmA_lo, const 
         fprintf(stderr, "[tc stats] mode=%d ktop=%d splits=%d: warp slow-path entries %llu (%.2f%% of warp-chunks), lane entries %llu, "
                 "qualifying %llu, inserts %llu (%.1f per query)\n", mode, ktop, plan.n_splits, hs[0], 100.0 * hs[0] / chunks, hs[1],
                 hs[2], hs[3], (double)hs[3] / nq);
-        if (hs[5])
-            fprintf(stderr, "[tc stats] keeper: %llu batches, %.1f entries/batch, %.0f busy cycles/batch (%.2f Mcycles per keeper warp); "
-                    "producer hand-off: %.0f cycles per warp entry (%.2f Mcycles per epilogue warp)\n", hs[5], (double)hs[4] / hs[5],
-                    (double)hs[6] / hs[5], (double)hs[6] / (4.0 * plan.grid) / 1e6, hs[0] ? (double)hs[7] / hs[0] : 0.0,
-                    (double)hs[7] / (12.0 * plan.grid) / 1e6);
-        if (hs[5])
-            fprintf(stderr, "[tc stats] keeper: scan+hand-over %.0f cycles/batch, %.2f insert rounds/batch, %.0f cycles/round\n",
-                    (double)hs[8] / hs[5], (double)hs[9] / hs[5], hs[9] ? (double)(hs[6] - hs[8]) / hs[9] : 0.0);
+    }
+    return VS_OK;
+}
+
+// The fp16 candidate pass (exact_tc.cuh, TC_F16).  sample = true: walks the tiles tile_off + t * tile_stride, t < plan.n_tiles,
+// and writes the group minima smin[plan.n_splits * TC_SAMPLE_GROUPS][nq]; sample = false: walks every tile (plan made for
+// n_rows) and appends every (query, row) pair with key < thr[query] to the query's candidate array.
+int launch_exact_tc_f16(const CUtensorMap& tmA, const CUtensorMap& tmA_fold, const TcBaseMaps& tmB, int nq, int64_t n_rows,
+                        const TcPlan& plan, bool sample, int tile_stride, int tile_off, float* smin, const float* thr,
+                        int32_t* cand_cnt, void* cand, int cand_cap, cudaStream_t st) {
+    TcParams p{};
+    p.nq = nq;
+    p.n_tiles = plan.n_tiles;
+    p.n_mtiles = plan.n_mtiles;
+    p.n_splits = plan.n_splits;
+    p.tiles_per_split = plan.tiles_per_split;
+    p.n_rem = (int)(n_rows % TC_BN);
+    p.n_tiles_real = (int)ceil_div64(n_rows, TC_BN);
+    p.tile_stride = sample ? tile_stride : 1;
+    p.tile_off = sample ? tile_off : 0;
+    p.smin = smin;
+    p.thr = thr;
+    p.cand_cnt = cand_cnt;
+    p.cand = reinterpret_cast<uint2*>(cand);
+    p.cand_cap = cand_cap;
+    if (plan.cl != 1) return fail(VS_ERR_INVALID, "tc: the fp16 pass runs with independent CTAs");
+    if (!sample && p.n_tiles != p.n_tiles_real) return fail(VS_ERR_INVALID, "tc: plan does not match the row count");
+    if (sample && (int64_t)(p.n_tiles - 1) * tile_stride + tile_off >= p.n_tiles_real) return fail(VS_ERR_INVALID, "tc: sample tiles out of range");
+    {
+        const char* e = getenv("VSB_TC_DBG");
+        p.dbg = e ? atoi(e) : 0;
+        const char* qb = getenv("VSB_TC_QBATCH");
+        p.qbatch = qb ? atoi(qb) : 0;
+    }
+    static unsigned long long* d_stats = nullptr;
+    const bool want_stats = !sample && getenv("VSB_TC_STATS") != nullptr;
+    if (want_stats) {
+        if (!d_stats) VSB_CUDA(cudaMalloc((void**)&d_stats, 16 * sizeof(unsigned long long)));
+        VSB_CUDA(cudaMemsetAsync(d_stats, 0, 16 * sizeof(unsigned long long), st));
+        p.stats = d_stats;
+    }
+    if (sample)
+        VSB_TRY((launch_one<1, TC_F16, false>(plan, tmA, tmA_fold, tmB.hi, tmB.lo, p, st)));
+    else
+        VSB_TRY((launch_one<32, TC_F16, false>(plan, tmA, tmA_fold, tmB.hi, tmB.lo, p, st)));
+    VSB_CUDA(cudaGetLastError());
+    if (want_stats) {
+        unsigned long long hs[16];
+        VSB_CUDA(cudaMemcpyAsync(hs, d_stats, sizeof(hs), cudaMemcpyDeviceToHost, st));
+        VSB_CUDA(cudaStreamSynchronize(st));
+        const double chunks = (double)plan.n_mtiles * 4.0 * plan.n_tiles * 4.0;  // warp-chunks of the whole sweep
+        fprintf(stderr, "[tc stats] f16 filter pass, splits=%d: warp hand-offs %llu (%.2f%% of warp-chunks), queue entries %llu (%.1f per "
+                "query), keeper batches %llu (%.1f entries each)\n", plan.n_splits, hs[0], 100.0 * hs[0] / chunks, hs[1], (double)hs[1] / nq,
+                hs[5], hs[5] ? (double)hs[4] / hs[5] : 0.0);
     }
     return VS_OK;
 }

@@ -39,7 +39,9 @@ constexpr int TC_REGS_CTRL = 80, TC_REGS_EPI = 144;   // setmaxnreg budgets: 128
 // epilogue warpgroups to 112 (128*40 + 128*104 + 384*112 = 61440: setmaxnreg.inc can only take what the CTA itself
 // released)
 constexpr int TC_THREADS_Q = TC_THREADS + 128;
-constexpr int TC_REGS_CTRL_Q = 40, TC_REGS_KEEP_Q = 104, TC_REGS_EPI_Q = 112;
+constexpr int TC_REGS_CTRL_Q = 40, TC_REGS_KEEP_Q = 64, TC_REGS_EPI_Q = 120;
+constexpr int TC_SAMPLE_SUB = 8;                                  // sample pass: running minima per thread and unit
+constexpr int TC_SAMPLE_GROUPS = TC_EPI_GROUPS * TC_SAMPLE_SUB;  // groups of sampled rows per unit
 constexpr int TC_QN = 128;            // candidate-queue entries per quadrant
 constexpr int TC_QBATCH = 24;         // queued rows that make a batch worth folding
 constexpr int TC_QUANT_REFRESH = 16;  // tiles of one group between reads of the finished units' quantile posts (power of two)
@@ -102,6 +104,14 @@ struct TcParams {
     unsigned long long* stats;  // debug counters (VSB_TC_STATS) or nullptr: [0] warp slow-path entries, [1] lane entries,
                          // [2] qualifying elements, [3] insertions
     int qbatch;          // TC_F16: queued rows that make a batch worth folding (0 = default)
+    // TC_F16 (threshold-filter candidate pass, see the kernel comment).  The base tiles walked are tile_off + t * tile_stride
+    // for t < n_tiles (the sample pass walks every tile_stride-th tile; n_tiles_real = ceil(n / 128) locates the ragged tile)
+    int tile_stride, tile_off, n_tiles_real;
+    float* smin;         // sample pass (KTOP == 1): [n_splits * TC_SAMPLE_GROUPS][nq] smallest key of each group of sampled rows
+    const float* thr;    // filter pass (KTOP == 32): [nq] per-query key thresholds; every row with key < thr is a candidate
+    int32_t* cand_cnt;   // [nq] candidates found (may exceed cand_cap: overflow, the query is then not certified)
+    uint2* cand;         // [nq][cand_cap] {key bits, local row id}, unordered
+    int cand_cap;
     // IVF = true: work items {first pair, pairs, first row, rows}, their number, pair -> query * nprobe + probe slot
     const int4* items;
     const int32_t* n_items;
@@ -207,6 +217,8 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
     constexpr bool SPLIT3 = S::SPLIT3;
     constexpr int TC_NKB = S::NKB;
     constexpr int KB_ELEMS = MODE == TC_F16 ? 64 : 32;  // elements per 128-byte k-block
+    constexpr bool SAMPLE = MODE == TC_F16 && KTOP == 1;  // TC_F16: KTOP == 1 is the sample pass, KTOP == 32 the filter pass
+    static_assert(MODE != TC_F16 || KTOP == 1 || KTOP == 32, "TC_F16: sample (1) or filter (32) pass");
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* sA = smem;
@@ -327,9 +339,10 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
                               mbar_arrive(&full[stage]);
                           } else {
                               mbar_expect_tx(&full[stage], (uint32_t)S::BSTAGE);
-                              tma_load_2d(dst, &tmB_hi, &full[stage], 0, t * TC_BN);
-                              tma_load_2d(dst + TC_KB_BYTES, &tmB_hi, &full[stage], 64, t * TC_BN);
-                              tma_load_2d(dst + 2 * TC_KB_BYTES, &tmB_lo, &full[stage], 0, t * TC_BN);
+                              const int row0 = (t * p.tile_stride + p.tile_off) * TC_BN;
+                              tma_load_2d(dst, &tmB_hi, &full[stage], 0, row0);
+                              tma_load_2d(dst + TC_KB_BYTES, &tmB_hi, &full[stage], 64, row0);
+                              tma_load_2d(dst + 2 * TC_KB_BYTES, &tmB_lo, &full[stage], 0, row0);
                           }
                       }
                       if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
@@ -521,157 +534,82 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
     } else {
       if constexpr (S::SMEM_LIST) {
        if (warp >= 4 + 4 * TC_EPI_GROUPS) {
-        // ===================================== list keepers (TC_F16) ==============================
-        // Keeper warp `quad` owns the 32 candidate lists of TMEM lane quadrant `quad`: LANE l KEEPS THE LIST OF ROW l
-        // IN ITS REGISTERS (sorted, 32 entries).  The epilogue's qualifying rows are sparse (1-4 lanes of a warp per
-        // chunk); they arrive through the quadrant's queue (entry = one row + the 32 keys of one 32-column chunk).
-        // Per batch of queued entries:
-        //   1. lane i scans entry i for the keys that still qualify (lane-rotated order, conflict-free banks);
-        //   2. the entries are handed to the lanes that own their rows (an atomicOr of the entry bit into a per-row
-        //      word of shared memory);
-        //   3. every lane folds the keys of its entries into its register list — the same instruction stream for all
-        //      lanes, so an insertion (~160 ALU instructions, no shared-memory dependency chain) serves up to 32 rows
-        //      at once instead of one.
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(TC_REGS_KEEP_Q));
-        static_assert(KTOP == 32, "the keeper lists hold 32 candidates per query");
+        // ===================================== candidate writers (TC_F16 filter pass) =============
+        // Keeper warp `quad` drains the queue of TMEM lane quadrant `quad`.  An entry = the 32 keys of one 32-column chunk
+        // of one query row whose minimum lies below the query's threshold.  Lane i of a batch takes entry i: it scans the
+        // 32 keys (lane-rotated order, conflict-free banks), reserves room in the query's candidate array with ONE
+        // atomicAdd and appends the (key, row id) pairs that pass.  No lists, no ordering: the merge kernel selects.
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TC_REGS_KEEP_Q));
+        if constexpr (!SAMPLE) {
         const int quad = warp & 3;
-        const float INF = __int_as_float(0x7f800000);
         const int* ready = sReady + quad * TC_QN;
         const uint32_t queue_u = smem_u32(sQueue + quad * TC_QN * TC_QENTRY);
-        float* my_worst = sWorst + quad * 32 + lane;
-        int* my_mask = sWpos + quad * 32 + lane;
         const int qbatch = p.qbatch > 0 ? p.qbatch : TC_QBATCH;
-        int next = 0;  // entries consumed so far (monotonic over the whole kernel)
-        int it = 0;
-        for (int unit = worker; unit < n_units; unit += n_workers, ++it) {
-            const int m_tile = (unit % n_mt) * CL + cta_rank;
-            const int split = unit / n_mt;
-            RegTopK<32> top;
-            top.init();
-            stsv_u32(my_worst, __float_as_uint(INF));
-            __syncwarp();
-            if (it > 0 && lane == 0) mbar_arrive(u_flushed);  // lists of the previous unit written out and reset
-            int final_tail = -1;
-            while (true) {
-                const int my = next + lane;
-                const unsigned rm = __ballot_sync(0xffffffffu, (int)ldsv_u32(ready + (my & (TC_QN - 1))) == my + 1);
-                const int n = rm == 0xffffffffu ? 32 : __ffs(~rm) - 1;  // consecutive ready entries
-                if (n == 0) {
-                    if (final_tail < 0) {
-                        if (mbar_try_wait(u_done, (uint32_t)(it & 1))) final_tail = (int)ldsv_u32(sTail + quad);
-                        else __nanosleep(64);
-                    } else if (next == final_tail) {
-                        break;
-                    }
-                    continue;
+        int next = 0;         // entries consumed so far
+        int final_tail = -1;  // total number of entries, known once every epilogue warp has finished its last unit
+        while (true) {
+            const int my = next + lane;
+            const unsigned rm = __ballot_sync(0xffffffffu, (int)ldsv_u32(ready + (my & (TC_QN - 1))) == my + 1);
+            const int n = rm == 0xffffffffu ? 32 : __ffs(~rm) - 1;  // consecutive ready entries
+            if (n == 0) {
+                if (final_tail < 0) {
+                    if (mbar_try_wait(u_done, 0u)) final_tail = (int)ldsv_u32(sTail + quad);
+                    else __nanosleep(64);
+                } else if (next == final_tail) {
+                    break;
                 }
-                // a batch has a (mostly) fixed cost: wait for a worthwhile one unless the queue fills up or the unit ends
-                if (n < qbatch && final_tail < 0 && (int)ldsv_u32(sTail + quad) - next < TC_QN / 2) {
-                    if (mbar_try_wait(u_done, (uint32_t)(it & 1))) final_tail = (int)ldsv_u32(sTail + quad);
-                    else __nanosleep(100);
-                    continue;
-                }
-                asm volatile("fence.acq_rel.cta;" ::: "memory");
-                const long long kc0 = p.stats ? clock64() : 0;
-                const bool act = lane < n;
-                const uint32_t e = queue_u + (uint32_t)(my & (TC_QN - 1)) * TC_QENTRY;
-                int rr = 0, col0 = 0, pad_;
-                float thr_e = -INF;
-                if (act) asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(rr), "=r"(col0), "=f"(thr_e), "=r"(pad_) : "r"(e + 128u) : "memory");
-                // ---- 1. which of the entry's 32 keys still qualify (the epilogue warps are the critical resource: the
-                // keeper does this scan, with the row's freshest bound)
-                unsigned qm = 0;
-                if (!(p.dbg & 64)) {
-                    const float bound = act ? fminf(thr_e, ldsv_f32(sWorst + quad * 32 + rr)) : -INF;
-#pragma unroll
-                    for (int j0 = 0; j0 < 32; j0 += 8) {  // eight loads in flight, then their tests
-                        float v[8];
-#pragma unroll
-                        for (int u = 0; u < 8; ++u) v[u] = lds_f32(e + (uint32_t)((j0 + u + lane) & 31) * 4u);
-#pragma unroll
-                        for (int u = 0; u < 8; ++u) qm |= (v[u] < bound) ? (1u << ((j0 + u + lane) & 31)) : 0u;
-                    }
-                }
-                // ---- 2. entry i -> the lane that owns its row
-                if (qm != 0) atomicOr(sWpos + quad * 32 + rr, 1 << lane);
-                __syncwarp();
-                unsigned mine = (unsigned)ldsv_u32(my_mask);
-                if (mine != 0) stsv_u32(my_mask, 0u);
-                const long long kc1 = p.stats ? clock64() : 0;
-                // ---- 3. fold: one entry per lane and outer iteration, one key per lane and inner iteration
-                int nins = 0, nrounds = 0;
-                while (__any_sync(0xffffffffu, mine != 0)) {
-                    const bool has = mine != 0;
-                    const int i = has ? __ffs(mine) - 1 : 0;
-                    mine &= mine - 1;
-                    unsigned qmi = __shfl_sync(0xffffffffu, qm, i);
-                    const int c0 = __shfl_sync(0xffffffffu, col0, i);
-                    const float the = __shfl_sync(0xffffffffu, thr_e, i);
-                    if (!has) qmi = 0;
-                    const uint32_t ei = queue_u + (uint32_t)((next + i) & (TC_QN - 1)) * TC_QENTRY;
-                    // the next key is loaded while the current one is inserted
-                    int jr = qmi ? __ffs(qmi) - 1 : 0;
-                    float x = qmi ? lds_f32(ei + (uint32_t)jr * 4u) : INF;
-                    while (__any_sync(0xffffffffu, qmi != 0)) {
-                        ++nrounds;
-                        const float cx = x;
-                        const int cj = jr;
-                        const bool cur = qmi != 0;
-                        qmi &= qmi - 1;
-                        if (qmi != 0) {
-                            jr = __ffs(qmi) - 1;
-                            x = lds_f32(ei + (uint32_t)jr * 4u);
-                        }
-                        if (cur && cx < fminf(the, top.threshold())) {
-                            top.insert(cx, c0 + cj);
-                            ++nins;
-                        }
-                    }
-                }
-                if (nins) stsv_u32(my_worst, __float_as_uint(top.threshold()));
-                __syncwarp();
-                next += n;
-                if (lane == 0) stsv_u32(sHead + quad, (uint32_t)next);  // the slots may be reused
-                if (p.stats) {
-                    atomicAdd(p.stats + 3, (unsigned long long)nins);
-                    if (lane == 0) {
-                        atomicAdd(p.stats + 4, (unsigned long long)n);
-                        atomicAdd(p.stats + 5, 1ull);
-                        atomicAdd(p.stats + 6, (unsigned long long)(clock64() - kc0));
-                        atomicAdd(p.stats + 8, (unsigned long long)(kc1 - kc0));
-                        atomicAdd(p.stats + 9, (unsigned long long)nrounds);
-                    }
-                }
+                continue;
             }
-            // ---- unit done: publish the bound and write this lane's (sorted) list
-            {
-                const int qv = m_tile * TC_BM + quad * 32 + lane;
-                if (qv < p.nq) {
-                    if (top.threshold() < INF) atomicMin(p.gthr + qv, float_to_ordered(top.threshold()));
-                    // 8 (16) rows of this unit lie at or below its 8th (16th) best key: four (two) such posts from
-                    // different units bound the query's 32nd best key (tc_quantile_cap)
-                    float* gq = reinterpret_cast<float*>(p.gthr + p.nq);
-                    if (top.key[7] < INF) __stcg(gq + (size_t)split * p.nq + qv, top.key[7]);
-                    if (top.key[15] < INF) __stcg(gq + ((size_t)p.n_splits + split) * p.nq + qv, top.key[15]);
-                    float4* pk = reinterpret_cast<float4*>(p.part_key + ((size_t)split * p.nq + qv) * 32);
-                    int4* pi = reinterpret_cast<int4*>(p.part_id + ((size_t)split * p.nq + qv) * 32);
+            // a batch has a (mostly) fixed cost: wait for a worthwhile one unless the queue fills up or the kernel ends
+            if (n < qbatch && final_tail < 0 && (int)ldsv_u32(sTail + quad) - next < TC_QN / 2) {
+                if (mbar_try_wait(u_done, 0u)) final_tail = (int)ldsv_u32(sTail + quad);
+                else __nanosleep(100);
+                continue;
+            }
+            asm volatile("fence.acq_rel.cta;" ::: "memory");
+            const bool act = lane < n;
+            const uint32_t e = queue_u + (uint32_t)(my & (TC_QN - 1)) * TC_QENTRY;
+            int qg = 0, col0 = 0, pad_;
+            float thr_e = -__int_as_float(0x7f800000);
+            if (act) asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(qg), "=r"(col0), "=f"(thr_e), "=r"(pad_) : "r"(e + 128u) : "memory");
+            unsigned qm = 0;
 #pragma unroll
-                    for (int g = 0; g < 8; ++g) {
-                        pk[g] = make_float4(top.key[4 * g], top.key[4 * g + 1], top.key[4 * g + 2], top.key[4 * g + 3]);
-                        pi[g] = make_int4(top.id[4 * g], top.id[4 * g + 1], top.id[4 * g + 2], top.id[4 * g + 3]);
-                    }
-                }
+            for (int j0 = 0; j0 < 32; j0 += 8) {  // eight loads in flight, then their tests
+                float v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = lds_f32(e + (uint32_t)((j0 + u + lane) & 31) * 4u);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) qm |= (v[u] < thr_e) ? (1u << ((j0 + u + lane) & 31)) : 0u;
+            }
+            int pos = 0;
+            if (qm != 0) pos = atomicAdd(p.cand_cnt + qg, __popc(qm));
+            uint2* dst = p.cand + (size_t)qg * p.cand_cap;
+            while (qm != 0) {
+                const int j = __ffs(qm) - 1;
+                qm &= qm - 1;
+                const float x = lds_f32(e + (uint32_t)j * 4u);
+                if (pos < p.cand_cap) __stcg(dst + pos, make_uint2(__float_as_uint(x), (uint32_t)(col0 + j)));
+                ++pos;
             }
             __syncwarp();
+            next += n;
+            if (lane == 0) stsv_u32(sHead + quad, (uint32_t)next);  // the slots may be reused
+            if (p.stats && lane == 0) {
+                atomicAdd(p.stats + 4, (unsigned long long)n);
+                atomicAdd(p.stats + 5, 1ull);
+            }
+        }
         }
        } else {
-        // ===================================== epilogue, queued candidates (TC_F16) ===============
-        // Fast path per 32-column chunk: keys, min tree, one test of the row minimum against the row's threshold.
-        // A row that qualifies is handed to the quadrant's list keeper as a whole: the thread copies its 32 keys into
-        // a queue entry (eight 16-byte stores; all qualifying lanes of the warp execute them together), so the
-        // epilogue warps never run an insertion themselves.
+        // ===================================== epilogue (TC_F16) ==================================
+        // Filter pass: per 32-column chunk the keys (the accumulator IS the key: norm and dot product were combined by the
+        // tensor core), a min tree and ONE test of the row minimum against the query's threshold thr[q], which is fixed for
+        // the whole launch — no lists, no bounds to refresh.  A chunk that passes is handed to the quadrant's keeper as a whole
+        // (eight 16-byte stores by all passing lanes together).
+        // Sample pass (KTOP == 1): no threshold yet; every thread keeps TC_SAMPLE_SUB running minima over the tiles it sees
+        // (tile sequence number mod TC_SAMPLE_SUB) and writes them out per unit: the group minima from which
+        // tc_select_thr_kernel derives thr[q].
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(TC_REGS_EPI_Q));
-        static_assert(KTOP == 32, "shared-memory lists hold exactly one entry per lane");
         const int quad = warp & 3;
         const int grp = (warp - 4) >> 2;
         const int row = quad * 32 + lane;
@@ -679,8 +617,7 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         constexpr int CH = TC_BN / 32;
         const uint32_t queue_u = smem_u32(sQueue + quad * TC_QN * TC_QENTRY);
         int tcount = 0;
-        int it = 0;
-        for (int unit = worker; unit < n_units; unit += n_workers, ++it) {
+        for (int unit = worker; unit < n_units; unit += n_workers) {
             const int m_tile = (unit % n_mt) * CL + cta_rank;
             const int split = unit / n_mt;
             const int t0 = split * p.tiles_per_split;
@@ -688,50 +625,33 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
             const int q = m_tile * TC_BM + row;
             const bool valid = q < p.nq;
             const bool quad_live = m_tile * TC_BM + quad * 32 < p.nq;
-            if (it > 0) mbar_wait(u_flushed, (uint32_t)((it - 1) & 1));  // lists and bounds belong to this unit now
-            float cap = INF;                     // bound of the query's 32nd best key learnt from other CTAs
-            float posted = INF;                  // last value this thread pushed to the global array
-            int32_t pending = valid ? __ldcg(p.gthr + q) : 0x7f7f7f7f;
+            float thr = -INF;  // rows beyond the last query never pass
+            if (!SAMPLE && valid) thr = __ldg(p.thr + q);
+            float gmin[TC_SAMPLE_SUB];
+#pragma unroll
+            for (int u = 0; u < TC_SAMPLE_SUB; ++u) gmin[u] = INF;
             int first = (grp - tcount % TC_EPI_GROUPS + TC_EPI_GROUPS) % TC_EPI_GROUPS;
             int j = 0;
             for (int i = first; i < t1 - t0; i += TC_EPI_GROUPS, ++j) {
-                const int t = t0 + i;
+                const int t = (t0 + i) * p.tile_stride + p.tile_off;  // the base tile
                 const int tc = tcount + i;
                 const int acc = tc & (TC_NACC - 1);
                 const uint32_t acc_phase = (uint32_t)(tc / TC_NACC) & 1u;
-                const int rel = j & (TC_THR_REFRESH - 1);
-                if (valid) {
-                    if (rel == TC_THR_REFRESH - 1) {
-                        const float w = ldsv_f32(sWorst + row);
-                        if (w < posted) {
-                            atomicMin(p.gthr + q, float_to_ordered(w));
-                            posted = w;
-                        }
-                    }
-                    if (rel == 0) {
-                        cap = fminf(cap, ordered_to_float(pending));
-                        pending = __ldcg(p.gthr + q);
-                    }
-                    if ((j & (TC_QUANT_REFRESH - 1)) == 0) cap = fminf(cap, tc_quantile_cap(p.gthr, p.nq, p.n_splits, q));
-                }
-                const float capn = valid ? next_up(cap) : -INF;  // rows beyond the last query never qualify
                 mbar_wait(&acc_full[acc], acc_phase);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * TC_BN);
                 uint32_t r[2][32];
                 const bool skip = (p.dbg & 1) || !quad_live;
                 // the last base tile may be ragged: its missing rows arrive as zeros (TMA fill) and would rank as key 0
-                const int live_cols = (t == p.n_tiles - 1 && p.n_rem) ? p.n_rem : TC_BN;
+                const int live_cols = (t == p.n_tiles_real - 1 && p.n_rem) ? p.n_rem : TC_BN;
+                float tmin = INF;
                 if (!skip) tmem_ld32(taddr, r[0]);
 #pragma unroll
                 for (int c = 0; c < CH; ++c) {
                     if (skip) break;
-                    const float thr = fminf(ldsv_f32(sWorst + row), capn);  // kept fresh by the keeper
                     tc_wait_ld();
                     if (c + 1 < CH) tmem_ld32(taddr + (c + 1) * 32, r[(c + 1) & 1]);
                     if (p.dbg & 16) continue;                // timing experiment: TMEM loads without the arithmetic
-                    // the accumulator IS the ranking key (in units of s_q s_b / 2): norm and dot product were combined by
-                    // the tensor core, nothing to add here
                     float d[32];
 #pragma unroll
                     for (int jj = 0; jj < 32; ++jj) d[jj] = __uint_as_float(r[c & 1][jj]);
@@ -746,10 +666,13 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
                     for (int w = 8; w >= 1; w >>= 1)
 #pragma unroll
                         for (int jj = 0; jj < w; ++jj) m[jj] = fminf(m[jj], m[jj + w]);
+                    if constexpr (SAMPLE) {
+                        tmin = fminf(tmin, m[0]);
+                        continue;
+                    }
                     const bool hit = m[0] < thr;
                     const unsigned todo = __ballot_sync(0xffffffffu, hit);
                     if (todo != 0 && !(p.dbg & 2)) {
-                        const long long pc0 = p.stats ? clock64() : 0;
                         int base = 0;
                         if (lane == 0) {
                             base = atomicAdd(sTail + quad, __popc(todo));
@@ -767,23 +690,33 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
                             for (int j4 = 0; j4 < 8; ++j4)
                                 asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(e + (uint32_t)(j4 << 4)),
                                              "f"(d[4 * j4 + 0]), "f"(d[4 * j4 + 1]), "f"(d[4 * j4 + 2]), "f"(d[4 * j4 + 3]) : "memory");
-                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(e + 128u), "r"(lane), "r"(t * TC_BN + c * 32),
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(e + 128u), "r"(q), "r"(t * TC_BN + c * 32),
                                          "f"(thr), "r"(0) : "memory");
                             asm volatile("fence.acq_rel.cta;" ::: "memory");
                             stsv_u32(sReady + quad * TC_QN + (idx & (TC_QN - 1)), (uint32_t)(idx + 1));
                         }
                         __syncwarp();
-                        if (p.stats && lane == 0) atomicAdd(p.stats + 7, (unsigned long long)(clock64() - pc0));
                     }
+                }
+                if constexpr (SAMPLE) {
+#pragma unroll
+                    for (int u = 0; u < TC_SAMPLE_SUB; ++u) gmin[u] = (j & (TC_SAMPLE_SUB - 1)) == u ? fminf(gmin[u], tmin) : gmin[u];
                 }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&acc_empty[acc]);
             }
             tcount += t1 - t0;
-            __syncwarp();
-            if (lane == 0) mbar_arrive(u_done);  // every candidate of this warp is in the queue (release)
+            if constexpr (SAMPLE) {
+                if (valid) {
+#pragma unroll
+                    for (int u = 0; u < TC_SAMPLE_SUB; ++u)
+                        p.smin[((size_t)(split * TC_EPI_GROUPS + grp) * TC_SAMPLE_SUB + u) * p.nq + q] = gmin[u];
+                }
+            }
         }
+        __syncwarp();
+        if (!SAMPLE && lane == 0) mbar_arrive(u_done);  // every candidate of this warp is in the queue (release)
        }
       } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(TC_REGS_EPI));

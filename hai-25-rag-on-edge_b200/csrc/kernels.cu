@@ -2,6 +2,8 @@
 #include <cuda_fp16.h>
 
 #include "kernels.cuh"
+
+#include <type_traits>
 #include "vsb_common.cuh"
 
 namespace vsb {
@@ -328,6 +330,11 @@ struct RefineArgs {
     int32_t* uncert_count;  // number of uncertified queries
     int32_t* uncert_list;   // their indices
     const int32_t* ivf_idmap;  // IVF re-score mode (see launch_merge_lists)
+    // threshold-filter candidates (filter_merge_kernel): `lastk` passed to merge_tail is a key bound B such that every row
+    // that is NOT among the selected candidates has key >= B; the query is always checked (there is no "fewer than nsel rows
+    // exist" shortcut) and fails outright when its candidate array overflowed
+    bool filter = false;
+    bool overflow = false;
 };
 
 // q . x in the reference's NEON order (IVFIndex.cpp:278-357 computeDotProductsContiguous): four accumulators by d mod 4,
@@ -412,11 +419,11 @@ __device__ __forceinline__ void merge_tail(float myk, int32_t myid, float lastk,
         // lastk = key of the last popped candidate = largest candidate key (lists pop in ascending key order)
         const unsigned holder = __ballot_sync(0xffffffffu, myid >= 0 && rank == k - 1);
         const float dk = __shfl_sync(0xffffffffu, myk, holder ? __ffs(holder) - 1 : 0);
-        if (lane == 0 && (n_valid == nsel || !rf.qp->fold_ok)) {
+        if (lane == 0 && (rf.filter || n_valid == nsel || !rf.qp->fold_ok)) {
             const float qn = __ldg(rf.qnorm + q);
             const float e = rf.qp->cert_a * sqrtf(qn) + rf.qp->cert_b + 4e-6f * (qn + rf.qp->bn_max);
             // candidate keys are in accumulator units (x s_q s_b / 2, an exact power-of-two factor)
-            const bool ok = rf.qp->fold_ok && holder != 0 && (qn + lastk * rf.qp->key_unscale) - e > dk;
+            const bool ok = rf.qp->fold_ok && !rf.overflow && holder != 0 && (qn + lastk * rf.qp->key_unscale) - e > dk;
             if (!ok) rf.uncert_list[atomicAdd(rf.uncert_count, 1)] = (int32_t)q;
         }
     }
@@ -610,6 +617,233 @@ __global__ void __launch_bounds__(128) merge_small_kernel(const float* __restric
     }
     merge_tail(myk, myid, lastk, lasti, q, lane, nsel, k, id_base, neg_out, out_key, out_id, out_stride, out_off, lb_key_out,
                lb_id_out, rf);
+}
+
+// ---- threshold-filter candidate pass (exact_tc.cuh, TC_F16) ----------------------------------------------------------
+// thr[q] = the m-th smallest of the query's group minima (sample pass): at least m sampled rows have a key <= thr[q], so about
+// m * (rows / sampled rows) rows of the whole base lie below it.  Fewer than m finite minima: +inf (everything is a
+// candidate; the candidate array then overflows unless the base is tiny).  Also zeroes the candidate counters.
+// One warp per query, eight consecutive queries per block (they share the 32-byte sectors of smin[g][.]).
+__global__ void __launch_bounds__(256) tc_select_thr_kernel(const float* __restrict__ smin, int n_groups, int nq, int m,
+                                                            float* __restrict__ thr, int32_t* __restrict__ cand_cnt) {
+    const int lane = threadIdx.x & 31;
+    const int q = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (q >= nq) return;
+    const float INF = __int_as_float(0x7f800000);
+    float pk = -INF;  // the previous pick (value, group); picks ascend lexicographically
+    int pg = -1;
+    for (int r = 0; r < m; ++r) {
+        float bk = INF;
+        int bg = 0x7fffffff;
+        for (int g = lane; g < n_groups; g += 32) {
+            const float v = smin[(size_t)g * nq + q];
+            const bool after = v > pk || (v == pk && g > pg);
+            if (after && (v < bk || (v == bk && g < bg))) {
+                bk = v;
+                bg = g;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ok = __shfl_xor_sync(0xffffffffu, bk, o);
+            const int og = __shfl_xor_sync(0xffffffffu, bg, o);
+            if (ok < bk || (ok == bk && og < bg)) {
+                bk = ok;
+                bg = og;
+            }
+        }
+        pk = bk;
+        pg = bg;
+        if (bg == 0x7fffffff) {  // fewer than m groups
+            pk = INF;
+            break;
+        }
+    }
+    if (lane == 0) {
+        thr[q] = pk;
+        cand_cnt[q] = 0;
+    }
+}
+int launch_tc_select_thr(const float* smin, int n_groups, int nq, int m, float* thr, int32_t* cand_cnt, cudaStream_t st) {
+    if (nq <= 0) return VS_OK;
+    tc_select_thr_kernel<<<(unsigned)ceil_div64(nq, 8), 256, 0, st>>>(smin, n_groups, nq, m, thr, cand_cnt);
+    VSB_CUDA(cudaGetLastError());
+    return VS_OK;
+}
+// thr[q] = +inf, counters zeroed: bases of at most cand_cap rows need no sample pass
+__global__ void tc_fill_thr_kernel(int nq, float* __restrict__ thr, int32_t* __restrict__ cand_cnt) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < nq) {
+        thr[q] = __int_as_float(0x7f800000);
+        cand_cnt[q] = 0;
+    }
+}
+int launch_tc_fill_thr(int nq, float* thr, int32_t* cand_cnt, cudaStream_t st) {
+    if (nq <= 0) return VS_OK;
+    tc_fill_thr_kernel<<<(unsigned)ceil_div64(nq, 256), 256, 0, st>>>(nq, thr, cand_cnt);
+    VSB_CUDA(cudaGetLastError());
+    return VS_OK;
+}
+
+__device__ __forceinline__ uint32_t key_to_u32(float f) {  // monotone: a < b  <=>  key_to_u32(a) < key_to_u32(b)
+    const uint32_t b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float u32_to_key(uint32_t u) { return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u); }
+
+// A pivot P over the warp's NPER x 32 keys u[] (0xffffffff = empty slot) with at most 32 keys below it, found by a radix
+// descent from the highest bit in which the keys differ.  *n_below = keys < P.  The descent stops early once >= 24 keys lie
+// below the current bucket (any P with <= 32 keys below it is a valid bound; a few candidates fewer cost nothing); a descent
+// that runs through bit 0 returns the exact 32nd smallest key and *n_ties = how many keys == P complete the 32.
+template <int NPER>
+__device__ __forceinline__ uint32_t warp_pivot32(const uint32_t (&u)[NPER], int* n_below, int* n_ties) {
+    uint32_t lo = 0xffffffffu, hi = 0u;
+#pragma unroll
+    for (int j = 0; j < NPER; ++j) {
+        if (u[j] != 0xffffffffu) {
+            lo = min(lo, u[j]);
+            hi = max(hi, u[j]);
+        }
+    }
+    lo = __reduce_min_sync(0xffffffffu, lo);
+    hi = __reduce_max_sync(0xffffffffu, hi);
+    const uint32_t diff = lo ^ hi;
+    int need = 32;
+    uint32_t prefix = lo;
+    if (diff == 0) {  // all keys equal
+        *n_below = 0;
+        *n_ties = 32;
+        return lo;
+    }
+    const int top = 31 - __clz(diff);
+    prefix = top == 31 ? 0u : (lo & ~((2u << top) - 1u));  // the common high bits
+    for (int bit = top; bit >= 0; --bit) {
+        const uint32_t hmask = bit == 31 ? 0u : ~((2u << bit) - 1u);
+        int c0 = 0;
+#pragma unroll
+        for (int j = 0; j < NPER; ++j) c0 += (((u[j] ^ prefix) & hmask) == 0u && !((u[j] >> bit) & 1u)) ? 1 : 0;
+        c0 = __reduce_add_sync(0xffffffffu, c0);
+        if (need > c0) {  // the whole 0-branch lies below the pivot
+            need -= c0;
+            prefix |= 1u << bit;
+            if (32 - need >= 24) {
+                *n_below = 32 - need;
+                *n_ties = 0;
+                return prefix;
+            }
+        }
+    }
+    *n_below = 32 - need;
+    *n_ties = need;
+    return prefix;
+}
+
+// Merge step of the threshold-filter candidate pass: one warp per query.  The query's candidates (every row with
+// key < thr[q], unordered, cnt of them) are cut down to <= 32 by key, then merge_tail refines them in exact fp32, ranks,
+// certifies against the bound B (= thr[q] when all candidates were kept, else the pivot key: no row outside the kept
+// ones has a key below it) and writes the k results.
+__global__ void __launch_bounds__(128) filter_merge_kernel(const uint2* __restrict__ cand, const int32_t* __restrict__ cand_cnt,
+                                                           int cap, const float* __restrict__ thr, int64_t nq, int k, int64_t id_base,
+                                                           float* __restrict__ out_key, int32_t* __restrict__ out_id, int out_stride,
+                                                           RefineArgs rf) {
+    __shared__ uint32_t s_key[4][32];
+    __shared__ int32_t s_id[4][32];
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    const int64_t q = (int64_t)blockIdx.x * 4 + wib;
+    if (q >= nq) return;
+    const float INF = __int_as_float(0x7f800000);
+    const int c_raw = __ldg(cand_cnt + q);
+    const int c = min(c_raw, cap);
+    const uint2* src = cand + (size_t)q * cap;
+    float myk = INF, bound = __ldg(thr + q);
+    int32_t myid = -1;
+    if (c <= 32) {
+        if (lane < c) {
+            const uint2 e = __ldcg(src + lane);
+            myk = __uint_as_float(e.x);
+            myid = (int32_t)e.y;
+        }
+    } else {
+        uint32_t pivot;
+        int n_below, n_ties;
+        auto run = [&](auto tag) {
+            constexpr int NPER = decltype(tag)::value;
+            uint32_t u[NPER];
+            int32_t id[NPER];
+#pragma unroll
+            for (int j = 0; j < NPER; ++j) {
+                const int i = lane + 32 * j;
+                u[j] = 0xffffffffu;
+                id[j] = -1;
+                if (i < c) {
+                    const uint2 e = __ldcg(src + i);
+                    u[j] = key_to_u32(__uint_as_float(e.x));
+                    id[j] = (int32_t)e.y;
+                }
+            }
+            pivot = warp_pivot32<NPER>(u, &n_below, &n_ties);
+            int base = 0;
+            const unsigned lt_mask = (1u << lane) - 1u;
+#pragma unroll
+            for (int j = 0; j < NPER; ++j) {
+                const bool lt = u[j] < pivot;
+                const unsigned b = __ballot_sync(0xffffffffu, lt);
+                if (lt) {
+                    const int pos = base + __popc(b & lt_mask);
+                    s_key[wib][pos] = u[j];
+                    s_id[wib][pos] = id[j];
+                }
+                base += __popc(b);
+            }
+            if (n_ties > 0) {
+#pragma unroll
+                for (int j = 0; j < NPER; ++j) {
+                    const bool eq = u[j] == pivot;
+                    const unsigned b = __ballot_sync(0xffffffffu, eq);
+                    if (eq) {
+                        const int pos = base + __popc(b & lt_mask);
+                        if (pos < 32) {
+                            s_key[wib][pos] = u[j];
+                            s_id[wib][pos] = id[j];
+                        }
+                    }
+                    base = min(32, base + __popc(b));
+                }
+            }
+            __syncwarp();
+            if (lane < base) {
+                myk = u32_to_key(s_key[wib][lane]);
+                myid = s_id[wib][lane];
+            }
+        };
+        if (c <= 128)
+            run(std::integral_constant<int, 4>{});
+        else if (c <= 256)
+            run(std::integral_constant<int, 8>{});
+        else
+            run(std::integral_constant<int, 16>{});
+        bound = fminf(bound, u32_to_key(pivot));
+    }
+    rf.filter = true;
+    rf.overflow = c_raw > cap;
+    merge_tail(myk, myid, bound, 0, q, lane, 32, k, id_base, 0, out_key, out_id, out_stride, 0, nullptr, nullptr, rf);
+}
+
+// cand [nq][cap] {key bits, local id}, cand_cnt [nq], thr [nq] -> out [nq][out_stride] (k written per query).  rf_base == nullptr:
+// no refine and no certification (debug: the candidates as the tensor-core pass ranked them)
+int launch_filter_merge(const void* cand, const int32_t* cand_cnt, int cap, const float* thr, int64_t nq, int k, int64_t id_base,
+                        float* out_key, int32_t* out_id, int out_stride, const float* rf_base, const float* rf_bnorm, const float* rf_q,
+                        const float* rf_qnorm, const TcQueryParams* cert_qp, int32_t* uncert_count, int32_t* uncert_list,
+                        cudaStream_t st) {
+    if (nq <= 0) return VS_OK;
+    if (k > 32 || cap > 512 || cap < 32) return fail(VS_ERR_INVALID, "filter merge: need k <= 32 and 32 <= cap <= 512");
+    if (cert_qp && (!rf_base || !uncert_count || !uncert_list)) return fail(VS_ERR_INVALID, "merge: certification needs the refine");
+    RefineArgs rf{rf_base, rf_bnorm, rf_q, rf_qnorm, cert_qp, uncert_count, uncert_list, nullptr};
+    filter_merge_kernel<<<(unsigned)ceil_div64(nq, 4), 128, 0, st>>>(reinterpret_cast<const uint2*>(cand), cand_cnt, cap, thr, nq, k, id_base,
+                                                                    out_key, out_id, out_stride, rf);
+    VSB_CUDA(cudaGetLastError());
+    return VS_OK;
 }
 
 int launch_merge_lists(const float* part_key, const int32_t* part_id, int n_lists, int64_t nq, int list_len, int nsel,

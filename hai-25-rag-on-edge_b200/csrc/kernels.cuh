@@ -70,6 +70,17 @@ int launch_exact_tc(const CUtensorMap& tmA_hi, const CUtensorMap& tmA_lo, const 
 int launch_exact_tc_ivf(const CUtensorMap& tmA_hi, const CUtensorMap& tmA_lo, const CUtensorMap& tmB_hi, const CUtensorMap& tmB_lo,
                         const int4* items, const int32_t* n_items, const int32_t* pairs, int nprobe, int32_t* gthr, int nq, int ktop,
                         bool split3, float* part_key, int32_t* part_id, int num_sms, cudaStream_t st);
+// the fp16 threshold-filter candidate pass: sample pass -> thresholds -> filter pass -> filter merge
+int launch_exact_tc_f16(const CUtensorMap& tmA, const CUtensorMap& tmA_fold, const TcBaseMaps& tmB, int nq, int64_t n_rows,
+                        const TcPlan& plan, bool sample, int tile_stride, int tile_off, float* smin, const float* thr,
+                        int32_t* cand_cnt, void* cand, int cand_cap, cudaStream_t st);
+int tc_sample_groups_per_split();
+int launch_tc_select_thr(const float* smin, int n_groups, int nq, int m, float* thr, int32_t* cand_cnt, cudaStream_t st);
+int launch_tc_fill_thr(int nq, float* thr, int32_t* cand_cnt, cudaStream_t st);
+int launch_filter_merge(const void* cand, const int32_t* cand_cnt, int cap, const float* thr, int64_t nq, int k, int64_t id_base,
+                        float* out_key, int32_t* out_id, int out_stride, const float* rf_base, const float* rf_bnorm, const float* rf_q,
+                        const float* rf_qnorm, const TcQueryParams* cert_qp, int32_t* uncert_count, int32_t* uncert_list,
+                        cudaStream_t st);
 int tc_lists_per_split(int mode);  // partial lists written per (split, query): 1 (TC_F16, mode 2) or 3
 int tc_set_attributes();  // opt-in to > 48 KB dynamic shared memory for every instantiation
 

@@ -273,7 +273,7 @@ def test_search_dev_begin_finish(gpu_vsb, oracle):
 
     vsb = gpu_vsb
     rng = np.random.default_rng(3)
-    base = vsb.synth.make("cont", 91, 30_000)
+    base = vsb.synth.make("cont", 91, 60_000)
     centre = base[7].copy()
     base[2000:2200] = centre[None, :] + rng.uniform(-0.02, 0.02, (200, 128)).astype(np.float32)   # uncertifiable cluster
     qry = vsb.synth.make("cont", 92, 500)
@@ -375,12 +375,12 @@ def test_f16_certification_bound_is_measured_not_assumed(family, gpu_vsb, oracle
     (kernels.cu, tc_query_params_kernel) — including a term for the tensor core's fp32 accumulation that cannot be
     derived from documentation.  Measure it: take the kernel's OWN candidate keys (vs_exact_debug_f16_candidates) and
     compare them with float64 keys of the same (query, row) pairs.  Two samples per data family: a 32-row base (every
-    row is a candidate of every query: arbitrary pairs, not only near neighbours) and a 30 000-row base (the 32 nearest
-    rows per query: the pairs the certificate is about).  The worst ratio error / E_q must stay below 1; it is printed
+    row is a candidate of every query: arbitrary pairs, not only near neighbours) and a 60 000-row base (the up to 32
+    nearest rows per query that passed the threshold filter: the pairs the certificate is about).  The worst ratio error / E_q must stay below 1; it is printed
     (and recorded in profiles/) together with the margin."""
     vsb = gpu_vsb
     worst = 0.0
-    for n, nq in ((32, 2000), (30_000, 1500)):
+    for n, nq in ((32, 2000), (60_000, 1500)):
         base = _bound_family(vsb, family, 600, n)
         qry = _bound_family(vsb, family, 601, nq)
         idx = vsb.ExactIndex(base)
@@ -388,12 +388,15 @@ def test_f16_certification_bound_is_measured_not_assumed(family, gpu_vsb, oracle
             ids, keys, bound = idx.debug_f16_candidates(qry)
         finally:
             idx.close()
-        assert (ids >= 0).all() and (np.diff(keys, axis=1) >= 0).all()
-        assert all(len(set(r.tolist())) == 32 for r in ids[:50])
+        have = ids >= 0                                                   # the filter merge keeps 24..32 candidates (fewer when fewer rows lie below the threshold)
+        assert (have[:, :10]).all() and have.mean() > 0.7
+        assert (np.diff(np.where(have, keys, np.float32(3e38)), axis=1) >= 0).all()   # sorted, padding last
+        assert all(len(set(r[r >= 0].tolist())) == int((r >= 0).sum()) for r in ids[:50])
         bn = oracle.norms(base).astype(np.float64)                       # the fp32 norms the kernel adds
-        dots = np.einsum("qd,qkd->qk", qry.astype(np.float64), base[ids].astype(np.float64))
-        exact = bn[ids] - 2.0 * dots
-        err = np.abs(keys.astype(np.float64) - exact)
+        safe = np.where(have, ids, 0)
+        dots = np.einsum("qd,qkd->qk", qry.astype(np.float64), base[safe].astype(np.float64))
+        exact = bn[safe] - 2.0 * dots
+        err = np.where(have, np.abs(keys.astype(np.float64) - exact), 0.0)
         ratio = float((err / bound[:, None].astype(np.float64)).max())
         worst = max(worst, ratio)
         with capsys.disabled():

@@ -226,7 +226,7 @@ def test_group_sequence_all_shards_on_one_gpu(G, law, k, prec_name, gpu_vsb, ora
     from vsb200 import sharded
 
     prec = {"auto": vsb.PREC_AUTO, "3xtf32": vsb.PREC_3XTF32, "f16cert": vsb.PREC_F16_CERT, "ffma": vsb.PREC_FFMA}[prec_name]
-    n, nq = 80_003, 16 if prec_name == "ffma" else 500
+    n, nq = 120_003, 16 if prec_name == "ffma" else 500   # shards of >= 15 K rows: the certified fp16 pass runs in every shard
     base, qry, n_adv = _base_with_uncertifiable_cluster(vsb, law, n, nq)
     dev = torch.device("cuda:0")
     base_d = torch.from_numpy(base).to(dev)
@@ -270,7 +270,7 @@ def test_mgpu_c_abi_on_one_gpu(spg, gpu_vsb, oracle):
     """vs_exact_mgpu_* (the C-ABI multi-GPU entry point: SURVEY §8b `n_gpus`) with n_gpus = 1 and shards_per_gpu
     shards: the same code path as on 8 GPUs minus the NCCL all-gather."""
     vsb = gpu_vsb
-    n, nq, k = 60_001, 700, 10
+    n, nq, k = 120_001, 700, 10
     base, qry, n_adv = _base_with_uncertifiable_cluster(vsb, "cont", n, nq, seed=33)
     want_ids, want_d = oracle.exact_search(base, qry, k, mode=1)
     m = vsb.ExactMultiGpu(base, n_gpus=1, shards_per_gpu=spg)
