@@ -16,7 +16,7 @@ import numpy as np
 from . import synth  # noqa: F401  (re-exported: seeded synthetic SIFT-shaped data)
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libvsb200.so")
+LIB_PATH = os.environ.get("VSB200_LIB") or os.path.join(HERE, "libvsb200.so")  # VSB200_LIB: build variants (tools/)
 
 PREC_AUTO, PREC_3XTF32, PREC_FFMA, PREC_TF32_1X, PREC_F16_CERT = 0, 1, 2, 3, 4
 PREC_NAMES = {0: "auto", 1: "fp32_3xtf32", 2: "fp32_ffma", 3: "tf32_1x", 4: "f16_certified+fp32_refine"}

@@ -189,9 +189,12 @@ static int ivf_search_core(vs_ivf* h, const float* q_dev, int64_t nq, int k, int
         VSB_TRY(h->lm_ws.reserve(sizeof(int32_t) * ivf_tc_workspace_ints(nq, nprobe, h->nlist)));
         VSB_TRY(h->qhi.reserve(sizeof(float) * (size_t)(n_pairs + 128) * 128));
         VSB_TRY(h->qlo.reserve(sizeof(float) * (size_t)(n_pairs + 128) * 128));
-        VSB_TRY(h->part_key.reserve(sizeof(float) * (size_t)n_lists * nq * ktop));
-        VSB_TRY(h->part_id.reserve(sizeof(int32_t) * (size_t)n_lists * nq * ktop));
+        // candidates: what the (query, probe slot, epilogue group) lists kept, appended per query (<= cap by construction)
+        const int cap = n_lists * ktop;
+        VSB_TRY(h->part_key.reserve(sizeof(uint2) * (size_t)nq * cap));
+        VSB_TRY(h->part_id.reserve(sizeof(int32_t) * (size_t)nq));
         VSB_TRY(h->gthr.reserve(sizeof(int32_t) * (size_t)nq));
+        VSB_CUDA(cudaMemsetAsync(h->part_id.p, 0, sizeof(int32_t) * (size_t)nq, st));
         const int4* items;
         const int32_t *n_items, *pairs;
         int32_t* q_cand;
@@ -215,15 +218,14 @@ static int ivf_search_core(vs_ivf* h, const float* q_dev, int64_t nq, int k, int
         VSB_TRY(make_tmap_2d(&tmQhi, h->qhi.p, (uint64_t)(n_pairs + 128), 128, 4, 128));
         VSB_TRY(make_tmap_2d(&tmQlo, h->qlo.p, (uint64_t)(n_pairs + 128), 128, 4, 128));
         VSB_TRY(launch_exact_tc_ivf(tmQhi, tmQlo, h->tmVhi, h->tmVlo, items, n_items, pairs, nprobe, h->gthr.as<int32_t>(), (int)nq, ktop,
-                                    split3, h->part_key.as<float>(), h->part_id.as<int32_t>(), h->num_sms, st));
+                                    split3, h->part_id.as<int32_t>(), h->part_key.p, cap, h->num_sms, st));
         VSB_TRY(launch_ivf_counts(q_cand, nq, k, out_counts, h->total.as<unsigned long long>(), st));
         if (h->profile) {
             VSB_CUDA(cudaEventRecord(h->ev1, st));
             h->ev_valid = true;
         }
-        VSB_TRY(launch_merge_lists(h->part_key.as<float>(), h->part_id.as<int32_t>(), n_lists, nq, ktop, ktop, k, 0, 0, 1, out_scores,
-                                   out_ids, k, 0, nullptr, nullptr, h->d_vectors, nullptr, q_dev, nullptr, st, nullptr, nullptr, nullptr, 0,
-                                   nullptr, nullptr, h->d_idmap));
+        VSB_TRY(launch_filter_merge_ivf(h->part_key.p, h->part_id.as<int32_t>(), cap, nq, k, out_scores, out_ids, h->d_vectors, q_dev,
+                                        h->d_idmap, st));
         h->last_launches = 10;
         return VS_OK;
     }

@@ -99,11 +99,12 @@ static int launch_ivf_one(int grid, const CUtensorMap& tmA_hi, const CUtensorMap
 
 int launch_exact_tc_ivf(const CUtensorMap& tmA_hi, const CUtensorMap& tmA_lo, const CUtensorMap& tmB_hi, const CUtensorMap& tmB_lo,
                         const int4* items, const int32_t* n_items, const int32_t* pairs, int nprobe, int32_t* gthr, int nq, int ktop,
-                        bool split3, float* part_key, int32_t* part_id, int num_sms, cudaStream_t st) {
+                        bool split3, int32_t* cand_cnt, void* cand, int cand_cap, int num_sms, cudaStream_t st) {
     TcParams p{};
     p.gthr = gthr;
-    p.part_key = part_key;
-    p.part_id = part_id;
+    p.cand_cnt = cand_cnt;
+    p.cand = reinterpret_cast<uint2*>(cand);
+    p.cand_cap = cand_cap;
     p.nq = nq;
     p.items = items;
     p.n_items = n_items;

@@ -42,7 +42,13 @@ constexpr int TC_THREADS_Q = TC_THREADS + 128;
 constexpr int TC_REGS_CTRL_Q = 40, TC_REGS_KEEP_Q = 64, TC_REGS_EPI_Q = 120;
 constexpr int TC_SAMPLE_SUB = 8;                                  // sample pass: running minima per thread and unit
 constexpr int TC_SAMPLE_GROUPS = TC_EPI_GROUPS * TC_SAMPLE_SUB;  // groups of sampled rows per unit
-constexpr int TC_QN = 128;            // candidate-queue entries per quadrant
+#ifndef VSB_TC_QN
+#define VSB_TC_QN 128
+#endif
+#ifndef VSB_TC_F16_STAGES
+#define VSB_TC_F16_STAGES 3
+#endif
+constexpr int TC_QN = VSB_TC_QN;      // candidate-queue entries per quadrant
 constexpr int TC_QBATCH = 24;         // queued rows that make a batch worth folding
 constexpr int TC_QUANT_REFRESH = 16;  // tiles of one group between reads of the finished units' quantile posts (power of two)
 constexpr int TC_QENTRY = 144;        // bytes per entry: 32 keys + {row in quadrant, first column, threshold, -}
@@ -72,7 +78,7 @@ struct TcSmem {
     static constexpr int THREADS = SMEM_LIST ? TC_THREADS_Q : TC_THREADS;
     // ring of base operand stages: TC_F16 one whole tile per stage (two k-blocks + the norm block, 36 KB), the TF32 modes one
     // k-block per stage
-    static constexpr int NSTAGE = MODE == TC_F16 ? 3 : (SPLIT3 ? 5 : 8);
+    static constexpr int NSTAGE = MODE == TC_F16 ? VSB_TC_F16_STAGES : (SPLIT3 ? 5 : 8);
     static constexpr int BSTAGE = MODE == TC_F16 ? 2 * TC_KB_BYTES + TC_FOLD_BYTES : TC_KB_BYTES;
     static constexpr int B_BYTES = NSTAGE * BSTAGE;
     static constexpr int NORM_BYTES = FOLD ? 0 : TC_NACC * TC_BN * 4;
@@ -887,9 +893,23 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
                 if (lane == 0) mbar_arrive(&acc_empty[acc]);
             }
             tcount += n_t;
-            if (valid) {
+            if (IVF && valid) {
+                // what this (query, list, group) kept goes to the query's candidate array (at most KTOP per thread, so
+                // nprobe * TC_EPI_GROUPS * KTOP slots per query can never overflow)
                 if (cap < INF) atomicMin(p.gthr + q, float_to_ordered(cap));
-                const size_t list = (size_t)(IVF ? slot : split) * TC_EPI_GROUPS + grp;
+                int n_kept = 0;
+#pragma unroll
+                for (int i = 0; i < KTOP; ++i) n_kept += top.id[i] >= 0 ? 1 : 0;
+                if (n_kept > 0) {
+                    const int at = atomicAdd(p.cand_cnt + q, n_kept);
+                    uint2* dst = p.cand + (size_t)q * p.cand_cap + at;
+#pragma unroll
+                    for (int i = 0; i < KTOP; ++i)
+                        if (i < n_kept) __stcg(dst + i, make_uint2(__float_as_uint(top.key[i]), (uint32_t)top.id[i]));
+                }
+            } else if (valid) {
+                if (cap < INF) atomicMin(p.gthr + q, float_to_ordered(cap));
+                const size_t list = (size_t)split * TC_EPI_GROUPS + grp;
                 float* pk = p.part_key + (list * p.nq + q) * KTOP;
                 int32_t* pi = p.part_id + (list * p.nq + q) * KTOP;
 #pragma unroll

@@ -353,6 +353,22 @@ __device__ __forceinline__ float dot_neon4_128(const float* __restrict__ q, cons
     return __fadd_rn(__fadd_rn(a0, a1), __fadd_rn(a2, a3));
 }
 
+// The same dot product with the row staged in shared memory (16-byte aligned)
+__device__ __forceinline__ float dot_neon4_128_smem(const float* __restrict__ q, const float* x_smem) {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 8
+    for (int c4 = 0; c4 < 32; ++c4) {
+        const float4 qv = __ldg(reinterpret_cast<const float4*>(q) + c4);
+        const float4 xv = *reinterpret_cast<const float4*>(x_smem + 4 * c4);
+        a0 = fmaf(qv.x, xv.x, a0);
+        a1 = fmaf(qv.y, xv.y, a1);
+        a2 = fmaf(qv.z, xv.z, a2);
+        a3 = fmaf(qv.w, xv.w, a3);
+    }
+    return __fadd_rn(__fadd_rn(a0, a1), __fadd_rn(a2, a3));
+}
+constexpr int kRowPitch = 132;  // floats per staged row: 528 B, so that eight lanes' 16-byte reads hit distinct bank groups
+
 // Exact fp32 dot products q . x_id of a warp's (up to 32) candidates, lane r holding candidate r's local row id (or -1).
 // Every row is read COOPERATIVELY — lane i takes components 4i .. 4i+3 (one coalesced 512-byte request per row) — and the
 // 32 partial sums are added in a FIXED tree (lane i + lane i+16, then +8, +4, +2, +1), so the value of a (query, row) pair
@@ -391,14 +407,30 @@ __device__ __forceinline__ float warp_refine_dots(const float* __restrict__ q_ro
 __device__ __forceinline__ void merge_tail(float myk, int32_t myid, float lastk, int32_t lasti, int64_t q, int lane, int nsel, int k,
                                            int64_t id_base, int neg_out, float* __restrict__ out_key, int32_t* __restrict__ out_id,
                                            int out_stride, int out_off, float* __restrict__ lb_key_out,
-                                           int32_t* __restrict__ lb_id_out, const RefineArgs& rf) {
+                                           int32_t* __restrict__ lb_id_out, const RefineArgs& rf,
+                                           float* row_scratch = nullptr /* per-warp shared memory, nsel x kRowPitch floats */) {
     const float INF = __int_as_float(0x7f800000);
     if (lb_key_out && lane == 0) {  // exclusive lower bound for the next pass (local ids, candidate-ranking keys)
         lb_key_out[q] = lasti >= 0 ? lastk : INF;
         lb_id_out[q] = lasti >= 0 ? lasti : 0x7fffffff;
     }
     if (rf.ivf_idmap) {
-        if (myid >= 0) {
+        if (row_scratch) {
+            // the candidates' rows come in with coalesced 512-byte loads (lane i takes components 4i .. 4i+3 of every row); each
+            // lane then walks ITS row in the reference's order out of shared memory
+            __syncwarp();
+            for (int r = 0; r < nsel; ++r) {
+                const int32_t id = __shfl_sync(0xffffffffu, myid, r);
+                if (id >= 0)
+                    *reinterpret_cast<float4*>(row_scratch + r * kRowPitch + 4 * lane) =
+                        __ldg(reinterpret_cast<const float4*>(rf.base + (size_t)id * 128) + lane);
+            }
+            __syncwarp();
+            if (myid >= 0) {
+                myk = -dot_neon4_128_smem(rf.q + (size_t)q * 128, row_scratch + lane * kRowPitch);
+                myid = __ldg(rf.ivf_idmap + myid);
+            }
+        } else if (myid >= 0) {
             myk = -dot_neon4_128(rf.q + (size_t)q * 128, rf.base + (size_t)myid * 128);
             myid = __ldg(rf.ivf_idmap + myid);
         }
@@ -541,8 +573,8 @@ __global__ void __launch_bounds__(128) merge_small_kernel(const float* __restric
                                                           int neg_in, int neg_out, float* __restrict__ out_key,
                                                           int32_t* __restrict__ out_id, int out_stride, int out_off,
                                                           float* __restrict__ lb_key_out, int32_t* __restrict__ lb_id_out,
-                                                          RefineArgs rf, BlockArgs ba) {
-    extern __shared__ float sm_lists[];  // per warp: keys [n_lists][32] then ids [n_lists][32]
+                                                          RefineArgs rf, BlockArgs ba, int warp_floats) {
+    extern __shared__ float sm_lists[];  // per warp (warp_floats each): keys [n_lists][32] then ids [n_lists][32]
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
     const int64_t q = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
@@ -554,17 +586,37 @@ __global__ void __launch_bounds__(128) merge_small_kernel(const float* __restric
     if (q >= nq) return;
     const float INF = __int_as_float(0x7f800000);
     const size_t lstride = ba.list_stride ? ba.list_stride : (size_t)nq * list_len;
-    float* sk = sm_lists + (size_t)wib * n_lists * 64;
+    float* sk = sm_lists + (size_t)wib * warp_floats;
     int32_t* si = reinterpret_cast<int32_t*>(sk + n_lists * 32);
-    for (int l = 0; l < n_lists; ++l) {
-        float kk = INF;
-        int32_t ii = -1;
-        if (lane < list_len) {
-            kk = part_key[(size_t)l * lstride + (size_t)q * list_len + lane];
-            ii = part_id[(size_t)l * lstride + (size_t)q * list_len + lane];
+    // staging: element e = l * list_len + i of the query's n_lists * list_len entries; eight independent loads per lane in
+    // flight (a serial load -> store loop is latency-bound: 96 lists took ~0.3 ms per 10 K queries)
+    {
+        const int total = n_lists * list_len;
+        for (int e0 = 0; e0 < total; e0 += 8 * 32) {
+            float kk[8];
+            int32_t ii[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int e = e0 + u * 32 + lane;
+                kk[u] = INF;
+                ii[u] = -1;
+                if (e < total) {
+                    const int l = e / list_len, i = e - l * list_len;
+                    kk[u] = part_key[(size_t)l * lstride + (size_t)q * list_len + i];
+                    ii[u] = part_id[(size_t)l * lstride + (size_t)q * list_len + i];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int e = e0 + u * 32 + lane;
+                if (e < total) {
+                    const int l = e / list_len, i = e - l * list_len;
+                    sk[l * 32 + i] = ii[u] >= 0 ? (neg_in ? -kk[u] : kk[u]) : INF;
+                    si[l * 32 + i] = ii[u];
+                }
+            }
         }
-        sk[l * 32 + lane] = ii >= 0 ? (neg_in ? -kk : kk) : INF;
-        si[l * 32 + lane] = ii;
+        // (slots [list_len, 32) of a list stay unwritten: the cursors stop at list_len)
     }
     __syncwarp();
     // lane j walks lists j, j + 32, j + 64 (n_lists <= 96) with one cursor each
@@ -615,8 +667,9 @@ __global__ void __launch_bounds__(128) merge_small_kernel(const float* __restric
                 }
         }
     }
+    // IVF re-score: the lists are consumed; their shared memory (>= nsel x kRowPitch floats per warp, see the launch) takes the rows
     merge_tail(myk, myid, lastk, lasti, q, lane, nsel, k, id_base, neg_out, out_key, out_id, out_stride, out_off, lb_key_out,
-               lb_id_out, rf);
+               lb_id_out, rf, rf.ivf_idmap ? sm_lists + (size_t)wib * warp_floats : nullptr);
 }
 
 // ---- threshold-filter candidate pass (exact_tc.cuh, TC_F16) ----------------------------------------------------------
@@ -630,16 +683,33 @@ __global__ void __launch_bounds__(256) tc_select_thr_kernel(const float* __restr
     const int q = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (q >= nq) return;
     const float INF = __int_as_float(0x7f800000);
-    float pk = -INF;  // the previous pick (value, group); picks ascend lexicographically
+    constexpr int NV = 12;  // group minima held per lane (n_groups <= 384: read once); more are re-read every round
+    float v[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        const int g = lane + 32 * j;
+        v[j] = g < n_groups ? smin[(size_t)g * nq + q] : INF;
+    }
+    // m rounds of "smallest (value, group) after the previous pick"; (INF, .) entries stand for missing groups
+    float pk = -INF;
     int pg = -1;
     for (int r = 0; r < m; ++r) {
         float bk = INF;
         int bg = 0x7fffffff;
-        for (int g = lane; g < n_groups; g += 32) {
-            const float v = smin[(size_t)g * nq + q];
-            const bool after = v > pk || (v == pk && g > pg);
-            if (after && (v < bk || (v == bk && g < bg))) {
-                bk = v;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            const int g = lane + 32 * j;
+            const bool after = v[j] > pk || (v[j] == pk && g > pg);
+            if (after && v[j] < INF && (v[j] < bk || (v[j] == bk && g < bg))) {
+                bk = v[j];
+                bg = g;
+            }
+        }
+        for (int g = lane + 32 * NV; g < n_groups; g += 32) {
+            const float x = smin[(size_t)g * nq + q];
+            const bool after = x > pk || (x == pk && g > pg);
+            if (after && x < INF && (x < bk || (x == bk && g < bg))) {
+                bk = x;
                 bg = g;
             }
         }
@@ -654,7 +724,7 @@ __global__ void __launch_bounds__(256) tc_select_thr_kernel(const float* __restr
         }
         pk = bk;
         pg = bg;
-        if (bg == 0x7fffffff) {  // fewer than m groups
+        if (bg == 0x7fffffff) {  // fewer than m groups with a finite minimum
             pk = INF;
             break;
         }
@@ -693,10 +763,11 @@ __device__ __forceinline__ float u32_to_key(uint32_t u) { return __uint_as_float
 
 // A pivot P over the warp's NPER x 32 keys u[] (0xffffffff = empty slot) with at most 32 keys below it, found by a radix
 // descent from the highest bit in which the keys differ.  *n_below = keys < P.  The descent stops early once >= 24 keys lie
-// below the current bucket (any P with <= 32 keys below it is a valid bound; a few candidates fewer cost nothing); a descent
+// below the current bucket, min_keep = 24 in the certified search (any P with <= 32 keys below it is a valid bound; a few
+// candidates fewer cost nothing); a descent
 // that runs through bit 0 returns the exact 32nd smallest key and *n_ties = how many keys == P complete the 32.
 template <int NPER>
-__device__ __forceinline__ uint32_t warp_pivot32(const uint32_t (&u)[NPER], int* n_below, int* n_ties) {
+__device__ __forceinline__ uint32_t warp_pivot32(const uint32_t (&u)[NPER], int* n_below, int* n_ties, int min_keep) {
     uint32_t lo = 0xffffffffu, hi = 0u;
 #pragma unroll
     for (int j = 0; j < NPER; ++j) {
@@ -726,7 +797,7 @@ __device__ __forceinline__ uint32_t warp_pivot32(const uint32_t (&u)[NPER], int*
         if (need > c0) {  // the whole 0-branch lies below the pivot
             need -= c0;
             prefix |= 1u << bit;
-            if (32 - need >= 24) {
+            if (32 - need >= min_keep) {
                 *n_below = 32 - need;
                 *n_ties = 0;
                 return prefix;
@@ -742,10 +813,15 @@ __device__ __forceinline__ uint32_t warp_pivot32(const uint32_t (&u)[NPER], int*
 // key < thr[q], unordered, cnt of them) are cut down to <= 32 by key, then merge_tail refines them in exact fp32, ranks,
 // certifies against the bound B (= thr[q] when all candidates were kept, else the pivot key: no row outside the kept
 // ones has a key below it) and writes the k results.
+// Also the merge of the tensor-core IVF scan (rf.ivf_idmap: candidates = what the (query, probe slot) lists kept, thr ==
+// nullptr, at least min_keep = k + 2 of them survive the cut and are re-scored in the reference's order out of rows staged
+// in dynamic shared memory).  More than 1536 candidates (IVF with k > 14 only, rare): the same descent with the keys re-read from memory.
+template <bool BIG>  // BIG: register-resident selection up to 1536 candidates (IVF), else up to 512
 __global__ void __launch_bounds__(128) filter_merge_kernel(const uint2* __restrict__ cand, const int32_t* __restrict__ cand_cnt,
                                                            int cap, const float* __restrict__ thr, int64_t nq, int k, int64_t id_base,
-                                                           float* __restrict__ out_key, int32_t* __restrict__ out_id, int out_stride,
-                                                           RefineArgs rf) {
+                                                           int neg_out, int min_keep, float* __restrict__ out_key,
+                                                           int32_t* __restrict__ out_id, int out_stride, RefineArgs rf) {
+    extern __shared__ __align__(16) float fm_rows[];  // IVF re-score only: [4][32 x kRowPitch]
     __shared__ uint32_t s_key[4][32];
     __shared__ int32_t s_id[4][32];
     const int lane = threadIdx.x & 31;
@@ -756,15 +832,16 @@ __global__ void __launch_bounds__(128) filter_merge_kernel(const uint2* __restri
     const int c_raw = __ldg(cand_cnt + q);
     const int c = min(c_raw, cap);
     const uint2* src = cand + (size_t)q * cap;
-    float myk = INF, bound = __ldg(thr + q);
+    float myk = INF, bound = thr ? __ldg(thr + q) : INF;
     int32_t myid = -1;
+    const unsigned lt_mask = (1u << lane) - 1u;
     if (c <= 32) {
         if (lane < c) {
             const uint2 e = __ldcg(src + lane);
             myk = __uint_as_float(e.x);
             myid = (int32_t)e.y;
         }
-    } else {
+    } else if (c <= (BIG ? 1536 : 512)) {
         uint32_t pivot;
         int n_below, n_ties;
         auto run = [&](auto tag) {
@@ -782,9 +859,8 @@ __global__ void __launch_bounds__(128) filter_merge_kernel(const uint2* __restri
                     id[j] = (int32_t)e.y;
                 }
             }
-            pivot = warp_pivot32<NPER>(u, &n_below, &n_ties);
+            pivot = warp_pivot32<NPER>(u, &n_below, &n_ties, min_keep);
             int base = 0;
-            const unsigned lt_mask = (1u << lane) - 1u;
 #pragma unroll
             for (int j = 0; j < NPER; ++j) {
                 const bool lt = u[j] < pivot;
@@ -821,13 +897,65 @@ __global__ void __launch_bounds__(128) filter_merge_kernel(const uint2* __restri
             run(std::integral_constant<int, 4>{});
         else if (c <= 256)
             run(std::integral_constant<int, 8>{});
-        else
+        else if (c <= 512)
             run(std::integral_constant<int, 16>{});
+        else if constexpr (BIG) {
+            if (c <= 1024)
+                run(std::integral_constant<int, 32>{});
+            else
+                run(std::integral_constant<int, 48>{});
+        }
         bound = fminf(bound, u32_to_key(pivot));
+    } else {
+        // exact 32nd smallest key by a full radix descent over the keys in memory, then the same compaction
+        uint32_t prefix = 0u;
+        int need = 32;
+        for (int bit = 31; bit >= 0; --bit) {
+            const uint32_t m = (bit == 31 ? 0u : ~((2u << bit) - 1u)) | (1u << bit);
+            int c0 = 0;
+            for (int i = lane; i < c; i += 32) c0 += (((key_to_u32(__uint_as_float(__ldcg(&src[i].x))) ^ prefix) & m) == 0u) ? 1 : 0;
+            c0 = __reduce_add_sync(0xffffffffu, c0);
+            if (need > c0) {
+                need -= c0;
+                prefix |= 1u << bit;
+            }
+        }
+        int base = 0, ties = 32 - need;  // keys < prefix land in [0, 32 - need), ties behind them
+        for (int i0 = 0; i0 < c; i0 += 32) {
+            const int i = i0 + lane;
+            uint32_t u = 0xffffffffu;
+            int32_t id = -1;
+            if (i < c) {
+                const uint2 e = __ldcg(src + i);
+                u = key_to_u32(__uint_as_float(e.x));
+                id = (int32_t)e.y;
+            }
+            const bool lt = u < prefix, eq = u == prefix && i < c;
+            const unsigned bl = __ballot_sync(0xffffffffu, lt), be = __ballot_sync(0xffffffffu, eq);
+            if (lt) {
+                const int pos = base + __popc(bl & lt_mask);
+                s_key[wib][pos] = u;
+                s_id[wib][pos] = id;
+            }
+            if (eq) {
+                const int pos = ties + __popc(be & lt_mask);
+                if (pos < 32) {
+                    s_key[wib][pos] = u;
+                    s_id[wib][pos] = id;
+                }
+            }
+            base += __popc(bl);
+            ties = min(32, ties + __popc(be));
+        }
+        __syncwarp();
+        myk = u32_to_key(s_key[wib][lane]);  // c > 1536 >= 32: all 32 slots are filled
+        myid = s_id[wib][lane];
+        bound = fminf(bound, u32_to_key(prefix));
     }
     rf.filter = true;
     rf.overflow = c_raw > cap;
-    merge_tail(myk, myid, bound, 0, q, lane, 32, k, id_base, 0, out_key, out_id, out_stride, 0, nullptr, nullptr, rf);
+    merge_tail(myk, myid, bound, 0, q, lane, 32, k, id_base, neg_out, out_key, out_id, out_stride, 0, nullptr, nullptr, rf,
+               rf.ivf_idmap ? fm_rows + (size_t)wib * 32 * kRowPitch : nullptr);
 }
 
 // cand [nq][cap] {key bits, local id}, cand_cnt [nq], thr [nq] -> out [nq][out_stride] (k written per query).  rf_base == nullptr:
@@ -840,8 +968,24 @@ int launch_filter_merge(const void* cand, const int32_t* cand_cnt, int cap, cons
     if (k > 32 || cap > 512 || cap < 32) return fail(VS_ERR_INVALID, "filter merge: need k <= 32 and 32 <= cap <= 512");
     if (cert_qp && (!rf_base || !uncert_count || !uncert_list)) return fail(VS_ERR_INVALID, "merge: certification needs the refine");
     RefineArgs rf{rf_base, rf_bnorm, rf_q, rf_qnorm, cert_qp, uncert_count, uncert_list, nullptr};
-    filter_merge_kernel<<<(unsigned)ceil_div64(nq, 4), 128, 0, st>>>(reinterpret_cast<const uint2*>(cand), cand_cnt, cap, thr, nq, k, id_base,
-                                                                    out_key, out_id, out_stride, rf);
+    filter_merge_kernel<false><<<(unsigned)ceil_div64(nq, 4), 128, 0, st>>>(reinterpret_cast<const uint2*>(cand), cand_cnt, cap, thr, nq, k, id_base,
+                                                                    0, 24, out_key, out_id, out_stride, rf);
+    VSB_CUDA(cudaGetLastError());
+    return VS_OK;
+}
+
+// The merge of the tensor-core IVF scan: candidates {key = -2 q.x as the tensor core saw it, row position}, at most cap per
+// query by construction (no overflow); the best >= k + 2 are re-scored in the reference's order (vectors = list-contiguous
+// rows, ivf_idmap = position -> original id) and the k best written, scores descending
+int launch_filter_merge_ivf(const void* cand, const int32_t* cand_cnt, int cap, int64_t nq, int k, float* out_scores, int32_t* out_ids,
+                            const float* vectors, const float* q, const int32_t* ivf_idmap, cudaStream_t st) {
+    if (nq <= 0) return VS_OK;
+    if (k > 30) return fail(VS_ERR_INVALID, "ivf filter merge: need k <= 30");
+    RefineArgs rf{vectors, nullptr, q, nullptr, nullptr, nullptr, nullptr, ivf_idmap};
+    const int smem = 4 * 32 * kRowPitch * (int)sizeof(float);
+    VSB_CUDA(cudaFuncSetAttribute(filter_merge_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));  // per device
+    filter_merge_kernel<true><<<(unsigned)ceil_div64(nq, 4), 128, smem, st>>>(reinterpret_cast<const uint2*>(cand), cand_cnt, cap, nullptr, nq, k, 0,
+                                                                       1, k + 2, out_scores, out_ids, k, rf);
     VSB_CUDA(cudaGetLastError());
     return VS_OK;
 }
@@ -860,11 +1004,13 @@ int launch_merge_lists(const float* part_key, const int32_t* part_id, int n_list
     BlockArgs ba{list_stride, trailer, trailer_total_out};
     if (ivf_idmap && (!rf_base || !rf_q || n_lists > 96)) return fail(VS_ERR_INVALID, "merge: IVF re-score needs vectors, queries and <= 96 lists");
     if (n_lists <= 96 && round_up_ktop(list_len) != 0) {
-        const size_t smem = (size_t)4 * n_lists * 64 * sizeof(float);  // <= 96 KB
+        // per warp: the staged lists, reused for the candidates' rows by the IVF re-score
+        const int warp_floats = std::max(n_lists * 64, ivf_idmap ? ((nsel * kRowPitch + 3) & ~3) : 0);
+        const size_t smem = (size_t)4 * warp_floats * sizeof(float);  // <= 96 KB
         if (smem > 48 * 1024)  // per device, hence not cached in a static
             VSB_CUDA(cudaFuncSetAttribute(merge_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 96 * 64 * (int)sizeof(float)));
         merge_small_kernel<<<blocks, 128, smem, st>>>(part_key, part_id, n_lists, nq, list_len, nsel, k, id_base, neg_in, neg_out,
-                                                     out_key, out_id, out_stride, out_off, lb_key_out, lb_id_out, rf, ba);
+                                                     out_key, out_id, out_stride, out_off, lb_key_out, lb_id_out, rf, ba, warp_floats);
         VSB_CUDA(cudaGetLastError());
         return VS_OK;
     }

@@ -69,7 +69,7 @@ int launch_exact_tc(const CUtensorMap& tmA_hi, const CUtensorMap& tmA_lo, const 
                     int32_t* part_id, cudaStream_t st);
 int launch_exact_tc_ivf(const CUtensorMap& tmA_hi, const CUtensorMap& tmA_lo, const CUtensorMap& tmB_hi, const CUtensorMap& tmB_lo,
                         const int4* items, const int32_t* n_items, const int32_t* pairs, int nprobe, int32_t* gthr, int nq, int ktop,
-                        bool split3, float* part_key, int32_t* part_id, int num_sms, cudaStream_t st);
+                        bool split3, int32_t* cand_cnt, void* cand, int cand_cap, int num_sms, cudaStream_t st);
 // the fp16 threshold-filter candidate pass: sample pass -> thresholds -> filter pass -> filter merge
 int launch_exact_tc_f16(const CUtensorMap& tmA, const CUtensorMap& tmA_fold, const TcBaseMaps& tmB, int nq, int64_t n_rows,
                         const TcPlan& plan, bool sample, int tile_stride, int tile_off, float* smin, const float* thr,
@@ -81,6 +81,8 @@ int launch_filter_merge(const void* cand, const int32_t* cand_cnt, int cap, cons
                         float* out_key, int32_t* out_id, int out_stride, const float* rf_base, const float* rf_bnorm, const float* rf_q,
                         const float* rf_qnorm, const TcQueryParams* cert_qp, int32_t* uncert_count, int32_t* uncert_list,
                         cudaStream_t st);
+int launch_filter_merge_ivf(const void* cand, const int32_t* cand_cnt, int cap, int64_t nq, int k, float* out_scores, int32_t* out_ids,
+                            const float* vectors, const float* q, const int32_t* ivf_idmap, cudaStream_t st);
 int tc_lists_per_split(int mode);  // partial lists written per (split, query): 1 (TC_F16, mode 2) or 3
 int tc_set_attributes();  // opt-in to > 48 KB dynamic shared memory for every instantiation
 
