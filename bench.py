@@ -4,9 +4,10 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
 One "step" = one pass of the hot path over one batch: 10 000 queries against the whole base, top-10, fp32-faithful.
-Default precision AUTO = certified fp16 tcgen05 candidate pass + exact fp32 refine of the candidates + per-query
-certificate (uncertified queries are redone in 3xTF32); the pure 3xTF32 tcgen05 path is timed in the same run and
-printed beside it (`fp32_3xtf32_path`).
+Default precision AUTO = certified fp16 tcgen05 candidate generation (sample pass over 1/16 of the base tiles ->
+per-query key threshold -> threshold-filter pass over the whole base) + exact fp32 refine of the <= 32 best
+candidates + per-query certificate (uncertified queries are redone in 3xTF32); the pure 3xTF32 tcgen05 path is timed
+in the same run and printed beside it (`fp32_3xtf32_path`).
 N > 1 (torchrun, one rank per GPU): base rows sharded across ranks, queries replicated (every rank uploads 1/N of
 them, one all-gather replicates the slices over NVLink), per-rank local top-k written in place into the rank's slot
 of the gathered buffer, ONE in-place NCCL all-gather of the exchange blocks (ids | dists | uncertified count) + merge
@@ -15,7 +16,8 @@ kernel — strong scaling on the fixed 1M x 128 problem.
 Prints ONE JSON line (rank 0):
   value        whole-job QPS, queries already resident in HBM when the timed region starts
   e2e          the same through the host-buffer C-ABI call (H2D of queries + D2H of results inside the timing)
-  roofline     dominant kernel (fused distance+top-k) timed live with CUDA events on its launching stream
+  roofline     dominant kernel (the fused distance + filter pass over the whole base) timed live with CUDA events on its
+               launching stream; `prepass_ms` = the sample pass + threshold selection that run before it
   cpu_baseline the UNMODIFIED reference (oracle/_ref) timed on this box's host cores on a bounded query sample
 --impl reference times that reference as the main metric (rank 0 only).
 """
@@ -306,7 +308,7 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    kernel_ms = []
+    kernel_ms, prepass_ms = [], []
 
     def dev_fn(after_enqueue=None):
         device_step(q_dev.data_ptr(), after_enqueue)
@@ -315,6 +317,7 @@ def main():
     for _ in range(args.steps):
         t_dev += timed(dev_fn, 1)
         kernel_ms.append(index.last_kernel_ms())
+        prepass_ms.append(index.last_prepass_ms())
     launches, prec_used = index.last_launches()
     fallbacks = index.last_fallbacks()
     t_e2e = timed(e2e_step, args.steps, use_events=False)  # wall clock: the host-buffer call blocks the host
@@ -329,6 +332,7 @@ def main():
     ms_dev = max_over_ranks(float(np.sum(t_dev))) / args.steps
     ms_e2e = max_over_ranks(float(np.sum(t_e2e))) / args.steps
     ms_kernel = max_over_ranks(float(np.mean(kernel_ms)))
+    ms_prepass = max_over_ranks(float(np.mean(prepass_ms)))
 
     # the pure fp32-faithful tensor-core path (3xTF32 split, no fp16 candidate pass) timed in the same run, for reference
     alt = None
@@ -365,8 +369,12 @@ def main():
             # one fp16 product per (query, row, dim): 2*Q*N*128 flop on the f16/bf16 tensor pipe (DESIGN.md "Roofline")
             flops = 2.0 * nq * n_local * DIM
             roof = {"bound": "tensor", "achieved": flops / (ms_kernel * 1e-3) / 1e12, "peak": pk["bf16"],
-                    "unit": "TFLOP/s", "traffic": None, "kernel": "exact_tc_kernel<32, F16>", "tf32_products": 0,
-                    "algorithmic_fp32_tflops": flops / (ms_kernel * 1e-3) / 1e12,
+                    "unit": "TFLOP/s", "traffic": None, "kernel": "exact_tc_kernel<32, F16> (threshold-filter pass)",
+                    "tf32_products": 0, "algorithmic_fp32_tflops": flops / (ms_kernel * 1e-3) / 1e12,
+                    "prepass_ms": ms_prepass,
+                    "frac_incl_prepass": flops / ((ms_kernel + ms_prepass) * 1e-3) / 1e12 / pk["bf16"],
+                    "prepass_note": "exact_tc_kernel<1, F16> sample pass over one base tile in 16 + tc_select_thr_kernel "
+                                    "(per-query thresholds); their flops are not counted as algorithmic work",
                     "peak_note": f"fp16/bf16 dense = MEASURED_PEAKS bf16 burst ({pk['src']})"}
         else:
             # tensor work issued by the fused kernel for this rank's shard: 2*Q*N*128 flop per TF32 product, 3
@@ -379,7 +387,7 @@ def main():
                     "peak_note": f"TF32 dense = MEASURED_PEAKS bf16 burst / 2 ({pk['src']})"}
         if world == 1 and nq == N_QUERY:
             # DRAM bytes of one launch of this kernel from the committed `ncu --set full` capture of the same command
-            prof = {vsb.PREC_F16_CERT: "r1f_ncu_full_exact_tc_f16.txt", vsb.PREC_3XTF32: "r1f_ncu_full_exact_tc_3xtf32.txt"}.get(prec_used)
+            prof = {vsb.PREC_F16_CERT: "r2_ncu_full_exact_tc_f16_filter.txt", vsb.PREC_3XTF32: "r1f_ncu_full_exact_tc_3xtf32.txt"}.get(prec_used)
             roof["traffic"] = ncu_dram_bytes(os.path.join(ROOT, "profiles", prof)) if prof else None
             roof["traffic_unit"] = "bytes/launch (dram__bytes_read.sum + dram__bytes_write.sum, profiles/%s)" % prof if prof else None
         roof["frac"] = roof["achieved"] / roof["peak"]
@@ -390,9 +398,10 @@ def main():
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{N_BASE}x{DIM} fp32 base, {nq} queries/step, exact L2 top-{k}, law={LAW}",
                        "precision": vsb.PREC_NAMES[prec_used], "uncertified_queries_redone_in_fp32": fallbacks,
-                       "precision_note": "fp16 tensor-core pass only proposes 32 candidates per query; every returned distance is "
-                                         "recomputed in fp32 and the top-k is certified complete per query (else redone in "
-                                         "3xTF32): results equal the fp32 path's (tests/test_exact_gpu.py)" if prec_used == vsb.PREC_F16_CERT else "",
+                       "precision_note": "the fp16 tensor-core passes only PROPOSE candidates (every row whose fp16 key lies below a "
+                                         "per-query threshold; the <= 32 best are kept); every returned distance is recomputed in "
+                                         "fp32 and the top-k is certified complete per query against the bound actually used (else "
+                                         "redone in 3xTF32): results equal the fp32 path's (tests/test_exact_gpu.py)" if prec_used == vsb.PREC_F16_CERT else "",
                        "base_rows_per_gpu": n_local,
                        "parallelism": f"base rows sharded x{world}, queries replicated, one in-place all-gather of (ids|dists|count) blocks + merge" if world > 1 else "single GPU",
                        "cache": "L2 flushed (256 MB write) between timed steps; operands (0.5-1 GB) exceed the 126 MB L2"},

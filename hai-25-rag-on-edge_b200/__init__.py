@@ -146,6 +146,11 @@ class ExactIndex:
         _check(lib().vs_exact_last_kernel_ms(self._h, C.byref(ms)))
         return float(ms.value)
 
+    def last_prepass_ms(self) -> float:
+        ms = C.c_float(0)
+        _check(lib().vs_exact_last_prepass_ms(self._h, C.byref(ms)))
+        return float(ms.value)
+
     def last_launches(self):
         a, b = C.c_int(0), C.c_int(0)
         _check(lib().vs_exact_last_launches(self._h, C.byref(a), C.byref(b)))

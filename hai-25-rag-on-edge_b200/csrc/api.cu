@@ -99,6 +99,7 @@ int exact_free(vs_exact* h) {
     if (h->h_flag) cudaFreeHost(h->h_flag);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->ev_pre) cudaEventDestroy(h->ev_pre);
     if (h->ev_cert) cudaEventDestroy(h->ev_cert);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -285,7 +286,11 @@ static int exact_f16_candidate_pass(vs_exact* h, const float* q_dev, int64_t nq,
     CUtensorMap tmA, tmAe;
     VSB_TRY(make_tmap_2d(&tmA, h->qf16.p, (uint64_t)nq, 128, 2, 128));
     VSB_TRY(make_tmap_fold(&tmAe, h->qfold.p, 128, 128));
-    if (h->profile) VSB_CUDA(cudaEventRecord(h->ev0, st));
+    h->ev_pre_valid = false;
+    if (h->profile && h->n > kF16CandCap) {
+        VSB_CUDA(cudaEventRecord(h->ev_pre, st));
+        h->ev_pre_valid = true;
+    }
     if (h->n <= kF16CandCap) {
         VSB_TRY(launch_tc_fill_thr((int)nq, h->f_thr.as<float>(), h->f_cnt.as<int32_t>(), st));
     } else {
@@ -300,6 +305,7 @@ static int exact_f16_candidate_pass(vs_exact* h, const float* q_dev, int64_t nq,
         VSB_TRY(launch_tc_select_thr(h->f_smin.as<float>(), n_groups, (int)nq, m, h->f_thr.as<float>(), h->f_cnt.as<int32_t>(), st));
     }
     const TcPlan plan = tc_make_plan(h->n, nq, h->num_sms, 2);
+    if (h->profile) VSB_CUDA(cudaEventRecord(h->ev0, st));  // the dominant kernel alone: the filter pass
     VSB_TRY(launch_exact_tc_f16(tmA, tmAe, h->tmB16, (int)nq, h->n, plan, false, 1, 0, nullptr, h->f_thr.as<float>(),
                                 h->f_cnt.as<int32_t>(), h->f_cand.p, kF16CandCap, st));
     if (h->profile) {
@@ -455,6 +461,7 @@ int exact_search_core(vs_exact* h, const float* q_dev, int64_t nq, int k, int pr
             if (h->profile && pass == 0) {
                 VSB_CUDA(cudaEventRecord(h->ev1, st));
                 h->ev_valid = true;
+                h->ev_pre_valid = false;
             }
             VSB_TRY(launch_merge_lists(h->part_key.as<float>(), h->part_id.as<int32_t>(), n_lists, nq, ktop,
                                        passes == 1 ? ktop : kk, passes == 1 ? k : kk, h->id_base, 0, 0, out_dists,
@@ -490,6 +497,7 @@ int exact_search_core(vs_exact* h, const float* q_dev, int64_t nq, int k, int pr
             if (h->profile && pass == 0 && q0 == 0) {
                 VSB_CUDA(cudaEventRecord(h->ev1, st));
                 h->ev_valid = true;
+                h->ev_pre_valid = false;
             }
             VSB_TRY(launch_merge_lists(h->part_key.as<float>(), h->part_id.as<int32_t>(), n_ctas, g, ktop,
                                        passes == 1 ? ktop : kk, passes == 1 ? k : kk, h->id_base, 0, 0,
@@ -716,6 +724,7 @@ int vs_exact_set_profile(vs_exact_t* h, int enable) {
     if (enable && !h->ev0) {
         VSB_CUDA(cudaEventCreate(&h->ev0));
         VSB_CUDA(cudaEventCreate(&h->ev1));
+        VSB_CUDA(cudaEventCreate(&h->ev_pre));
     }
     h->profile = enable != 0;
     h->ev_valid = false;
@@ -727,6 +736,16 @@ int vs_exact_last_kernel_ms(vs_exact_t* h, float* ms) {
     if (!h->ev_valid) return fail(VS_ERR_INVALID, "no profiled search yet (vs_exact_set_profile)");
     VSB_CUDA(cudaEventSynchronize(h->ev1));
     VSB_CUDA(cudaEventElapsedTime(ms, h->ev0, h->ev1));
+    return VS_OK;
+}
+
+int vs_exact_last_prepass_ms(vs_exact_t* h, float* ms) {
+    if (!h || !ms) return fail(VS_ERR_INVALID, "NULL argument");
+    *ms = 0.f;
+    if (!h->ev_valid) return fail(VS_ERR_INVALID, "no profiled search yet (vs_exact_set_profile)");
+    if (!h->ev_pre_valid) return VS_OK;
+    VSB_CUDA(cudaEventSynchronize(h->ev0));
+    VSB_CUDA(cudaEventElapsedTime(ms, h->ev_pre, h->ev0));
     return VS_OK;
 }
 

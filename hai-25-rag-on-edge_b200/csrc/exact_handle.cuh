@@ -55,8 +55,8 @@ struct vs_exact {
     int last_fallback = 0;
     // optional CUDA-event timing of the dominant kernel (bench.py's roofline line)
     bool profile = false;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    bool ev_valid = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_pre = nullptr;  // ev_pre .. ev0: sample pass + thresholds (fp16 path)
+    bool ev_valid = false, ev_pre_valid = false;
     // certified search split in two (vs_exact_search_dev_begin / _finish): what finish needs to redo uncertified queries
     cudaEvent_t ev_cert = nullptr;
     bool cert_pending = false;

@@ -120,6 +120,9 @@ VSB_API int vs_exact_last_fallbacks(const vs_exact_t* h, int* n_queries);
  * stream) with CUDA events on the launching stream; vs_exact_last_kernel_ms waits for and returns that duration. */
 VSB_API int vs_exact_set_profile(vs_exact_t* h, int enable);
 VSB_API int vs_exact_last_kernel_ms(vs_exact_t* h, float* ms);
+/* VS_PREC_F16_CERTIFIED only: device time of what runs before the dominant (filter) kernel to produce the per-query
+ * thresholds — the sample pass over one base tile in 16 and the threshold selection.  0 for the other paths. */
+VSB_API int vs_exact_last_prepass_ms(vs_exact_t* h, float* ms);
 
 /* Test hook for the certification bound of VS_PREC_F16_CERTIFIED: runs ONLY the fp16 tensor-core candidate pass and
  * returns, per query, its 32 candidates as the kernel ranked them — out_ids[nq x 32] (local row ids, -1 padded),
