@@ -10,8 +10,9 @@ candidates + per-query certificate (uncertified queries are redone in 3xTF32); t
 in the same run and printed beside it (`fp32_3xtf32_path`).
 N > 1 (torchrun, one rank per GPU): base rows sharded across ranks, queries replicated (every rank uploads 1/N of
 them, one all-gather replicates the slices over NVLink), per-rank local top-k written in place into the rank's slot
-of the gathered buffer, ONE in-place NCCL all-gather of the exchange blocks (ids | dists | uncertified count) + merge
-kernel — strong scaling on the fixed 1M x 128 problem.
+of the gathered buffer, ONE exchange of the blocks (ids | dists | uncertified count) — by default every rank pushes its
+block into the peers' symmetric-memory buffers with one kernel over NVLink and a device-side barrier follows
+(VSB_EXCHANGE=nccl: one in-place NCCL all-gather) — + merge kernel: strong scaling on the fixed 1M x 128 problem.
 
 Prints ONE JSON line (rank 0):
   value        whole-job QPS, queries already resident in HBM when the timed region starts
@@ -403,12 +404,15 @@ def main():
                                          "fp32 and the top-k is certified complete per query against the bound actually used (else "
                                          "redone in 3xTF32): results equal the fp32 path's (tests/test_exact_gpu.py)" if prec_used == vsb.PREC_F16_CERT else "",
                        "base_rows_per_gpu": n_local,
-                       "parallelism": f"base rows sharded x{world}, queries replicated, one in-place all-gather of (ids|dists|count) blocks + merge" if world > 1 else "single GPU",
+                       "parallelism": (f"base rows sharded x{world}, queries replicated, ONE exchange of the (ids|dists|count) blocks ["
+                                       + ("push: every rank stores its block into the peers' symmetric-memory buffers over NVLink "
+                                          "(vs_push_block_dev) + device-side barrier" if searcher.exchange_kind == "push"
+                                          else "in-place NCCL all-gather: " + searcher.exchange_kind) + "] + merge") if world > 1 else "single GPU",
                        "cache": "L2 flushed (256 MB write) between timed steps; operands (0.5-1 GB) exceed the 126 MB L2"},
             "e2e": {"value": nq / (ms_e2e * 1e-3), "unit": "queries/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": int(q_host.numel() * 4),
                     "d2h_bytes_per_step": int(nq * k * 8),
-                    "api": "vs_exact_search_f32 (host buffers)" if world == 1 else "H2D of 1/N of the queries per rank + all-gather of the slices + vs_exact_group_begin + ONE in-place NCCL all-gather of the exchange blocks + vs_exact_group_merge + D2H + vs_exact_group_finish"},
+                    "api": "vs_exact_search_f32 (host buffers)" if world == 1 else "H2D of 1/N of the queries per rank + all-gather of the slices + vs_exact_group_begin + ONE exchange of the blocks (see config.parallelism) + vs_exact_group_merge + D2H + vs_exact_group_finish"},
             "gpu_launches": int(launches + (1 if world > 1 else 0)) * args.steps,
             "roofline": roof,
             "clocks": clocks,

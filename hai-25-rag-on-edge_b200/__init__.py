@@ -174,6 +174,21 @@ def topk_block_bytes(nq: int, k: int) -> int:
     return int(lib().vs_topk_block_bytes(C.c_int64(nq), C.c_int(k)))
 
 
+def push_block_dev(src_ptr: int, dst_ptrs, nbytes: int, flag_ptrs, epoch: int, counter_ptr: int, stream: int = 0) -> None:
+    """one kernel: `nbytes` from src_ptr to the same bytes at every pointer of dst_ptrs (peer-mapped device memory), then
+    `epoch` into every flag word of flag_ptrs"""
+    n = len(flag_ptrs)
+    arr = (C.c_void_p * n)(*[int(p) for p in dst_ptrs]) if nbytes else (C.c_void_p * n)()
+    flg = (C.c_void_p * n)(*[int(p) for p in flag_ptrs])
+    _check(lib().vs_push_block_dev(_ptr(src_ptr), arr, C.c_int(n), C.c_size_t(nbytes), flg, C.c_uint32(epoch & 0xffffffff),
+                                   _ptr(counter_ptr), C.c_void_p(stream)))
+
+
+def wait_flags_dev(flags_ptr: int, n: int, self_index: int, epoch: int, stream: int = 0) -> None:
+    _check(lib().vs_wait_flags_dev(_ptr(flags_ptr), C.c_int(n), C.c_int(self_index), C.c_uint32(epoch & 0xffffffff),
+                                   C.c_void_p(stream)))
+
+
 def merge_blocks_dev(blocks_ptr: int, n_shards: int, stride: int, nq: int, k: int, smallest: bool, out_ids_ptr: int,
                      out_keys_ptr: int, total_ptr: int = 0, stream: int = 0) -> None:
     _check(lib().vs_merge_blocks_dev(_ptr(blocks_ptr), C.c_int(n_shards), C.c_size_t(stride), C.c_int64(nq), C.c_int(k),

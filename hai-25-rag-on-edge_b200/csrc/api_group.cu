@@ -364,7 +364,72 @@ static int mgpu_allgather(vs_exact_mgpu* m, const std::function<uint8_t*(DevCtx&
     return VS_OK;
 }
 
+namespace {
+struct PushDst {
+    void* p[16];
+};
+// every 16-byte unit of the source goes to the same offset of every destination (peer GPUs over NVLink); the block that
+// finishes last (all stores of all blocks fenced at system scope) raises this sender's flag word on every peer
+__global__ void __launch_bounds__(256) push_block_kernel(const uint4* __restrict__ src, PushDst dst, int n_dst, size_t n16,
+                                                         PushDst flag, uint32_t epoch, uint32_t* __restrict__ counter) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) {
+        const uint4 v = src[i];
+        for (int d = 0; d < n_dst; ++d) reinterpret_cast<uint4*>(dst.p[d])[i] = v;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned prev = atomicAdd(counter, 1u);
+        if (prev == gridDim.x - 1) {
+            atomicExch(counter, 0u);
+            __threadfence_system();
+            for (int d = 0; d < n_dst; ++d)
+                asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag.p[d]), "r"(epoch) : "memory");
+        }
+    }
+}
+__global__ void wait_flags_kernel(const uint32_t* flags, int n, int self, uint32_t epoch) {
+    const int t = threadIdx.x;
+    if (t < n && t != self) {
+        uint32_t v;
+        do {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + t) : "memory");
+            if ((int32_t)(v - epoch) >= 0) break;
+            __nanosleep(40);
+        } while (true);
+    }
+}
+}  // namespace
+
 extern "C" {
+
+int vs_push_block_dev(const void* src_dev, void* const* dst_dev, int n_dst, size_t bytes, void* const* flag_dst, uint32_t epoch,
+                      uint32_t* counter_dev, void* stream) {
+    if (n_dst < 0 || n_dst > 16) return fail(VS_ERR_INVALID, "push: at most 16 destinations");
+    if (n_dst == 0) return VS_OK;
+    if (!flag_dst || !counter_dev || (bytes > 0 && (!src_dev || !dst_dev))) return fail(VS_ERR_INVALID, "NULL buffer");
+    if (bytes % 16 != 0 || ((uintptr_t)src_dev & 15)) return fail(VS_ERR_INVALID, "push: 16-byte granularity");
+    PushDst d{}, f{};
+    for (int i = 0; i < n_dst; ++i) {
+        if (bytes > 0 && (!dst_dev[i] || ((uintptr_t)dst_dev[i] & 15))) return fail(VS_ERR_INVALID, "push: bad destination pointer");
+        if (!flag_dst[i] || ((uintptr_t)flag_dst[i] & 3)) return fail(VS_ERR_INVALID, "push: bad flag pointer");
+        d.p[i] = bytes > 0 ? dst_dev[i] : nullptr;
+        f.p[i] = flag_dst[i];
+    }
+    const size_t n16 = bytes / 16;
+    const unsigned blocks = (unsigned)std::max<size_t>(1, std::min<size_t>((n16 + 255) / 256, 148 * 4));
+    push_block_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint4*>(src_dev), d, n_dst, n16, f, epoch,
+                                                               counter_dev);
+    VSB_CUDA(cudaGetLastError());
+    return VS_OK;
+}
+
+int vs_wait_flags_dev(const uint32_t* flags_dev, int n, int self, uint32_t epoch, void* stream) {
+    if (!flags_dev || n < 1 || n > 32) return fail(VS_ERR_INVALID, "wait: 1 .. 32 flag words");
+    wait_flags_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(flags_dev, n, self, epoch);
+    VSB_CUDA(cudaGetLastError());
+    return VS_OK;
+}
 
 size_t vs_topk_block_bytes(int64_t nq, int k) { return (nq > 0 && k > 0) ? block_bytes(nq, k) : 0; }
 

@@ -46,7 +46,10 @@ class ShardedExact:
                total of the uncertified counts and, when some shard had to redo queries, exchanges and merges again.
     """
 
-    def __init__(self, vsb, index, nq_max: int, k: int, device: torch.device, group=None, exchange=None):
+    def __init__(self, vsb, index, nq_max: int, k: int, device: torch.device, group=None, exchange=None, push=None):
+        """exchange: callable replacing the collective (tests).  push: True = exchange by peer stores into symmetric memory
+        (vs_push_block_dev + a cross-GPU barrier), False = in-place NCCL all-gather, None = push when torch's symmetric
+        memory can be set up for the group (one node, NVLink peers), else NCCL; VSB_EXCHANGE=nccl|push overrides."""
         self.vsb, self.k, self.group = vsb, k, group
         self.shards = list(index) if isinstance(index, (list, tuple)) else [index]
         self.index = self.shards[0]
@@ -60,14 +63,80 @@ class ShardedExact:
         self.ids_loc = torch.empty((nq_max, k), dtype=torch.int32, device=device)
         self.d_loc = torch.empty((nq_max, k), dtype=torch.float32, device=device)
         self._exchange = exchange if exchange is not None else self._allgather
+        self.exchange_kind = "none" if self.world == 1 else "nccl"
+        self._sym = None
         if self.n_slots > 1:
             self.block = vsb.topk_block_bytes(nq_max, k)
-            self.gathered = torch.zeros(self.n_slots * self.block, dtype=torch.uint8, device=device)  # [slot][block]
+            size = self.n_slots * self.block
+            import os
+
+            env = os.environ.get("VSB_EXCHANGE", "")
+            want_push = (push if push is not None else True) if env == "" else env == "push"
+            if exchange is None and self.world > 1 and want_push and device.type == "cuda":
+                err = None
+                try:
+                    self._setup_push(size, device)
+                except Exception as e:  # no symmetric memory on this platform
+                    err = e
+                # every rank must take the same exchange: push only when ALL of them could set it up
+                ok = torch.tensor([0 if err is not None else 1], dtype=torch.int32, device=device)
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+                if int(ok.item()) == 1:
+                    self._exchange = self._push_exchange
+                    self.exchange_kind = "push"
+                else:
+                    if err is not None and (push or env == "push"):
+                        raise err
+                    self._sym = None
+                    self.exchange_kind = "nccl (symmetric memory unavailable%s)" % (": " + type(err).__name__ if err else " on a peer")
+            if self._sym is None:
+                self.gathered = torch.zeros(size, dtype=torch.uint8, device=device)  # [slot][block]
             self.grp = vsb.ExactGroup(self.shards, self.n_slots, self.first_slot)
 
     def close(self):
         if self.n_slots > 1:
             self.grp.close()
+
+    # ---- push exchange: the gathered buffers of all ranks are ONE symmetric allocation (two halves used alternately), every rank
+    # stores its slots straight into the peers' buffers over NVLink (one kernel, vs_push_block_dev) and a device-side barrier
+    # on the symmetric memory's signal pad replaces the NCCL all-gather.  Half h is written again two exchanges later; the
+    # barrier in between guarantees that every peer has finished merging it.
+    def _setup_push(self, size: int, device):
+        import torch.distributed._symmetric_memory as symm_mem
+
+        grp = self.group if self.group is not None else dist.group.WORLD
+        self._half = (size + 255) // 256 * 256
+        # [half 0 | half 1 | flag words: one per sender]
+        self._sym = symm_mem.empty(2 * self._half + 256, dtype=torch.uint8, device=device)
+        self._sym.zero_()
+        self._hdl = symm_mem.rendezvous(self._sym, grp)
+        self._peer_ptrs = [int(p) for p in self._hdl.buffer_ptrs]
+        if len(self._peer_ptrs) != self.world:
+            raise RuntimeError("symmetric memory: unexpected number of peers")
+        self._peers = [r for r in range(self.world) if r != self.rank]
+        self._flag_dst = [self._peer_ptrs[r] + 2 * self._half + 4 * self.rank for r in self._peers]  # my word on every peer
+        self._flags = self._peer_ptrs[self.rank] + 2 * self._half
+        self._counter = torch.zeros(1, dtype=torch.int32, device=device)
+        self._epoch = 0
+        self._parity = 0
+        self._stream = 0
+        self.gathered = self._sym[: self._half]
+        torch.cuda.synchronize(device)
+        self._hdl.barrier(channel=0)  # every rank's flags are zero before anybody pushes
+        torch.cuda.synchronize(device)
+
+    def _push(self, nbytes: int):
+        self._epoch += 1
+        off = self._parity * self._half + self.first_slot * self.block
+        dst = [self._peer_ptrs[r] + off for r in self._peers]
+        self.vsb.push_block_dev(self._peer_ptrs[self.rank] + off, dst, nbytes, self._flag_dst, self._epoch,
+                                self._counter.data_ptr(), self._stream)
+        self.vsb.wait_flags_dev(self._flags, self.world, self.rank, self._epoch, self._stream)
+
+    def _push_exchange(self, redo: bool = False):
+        if redo:  # the same half is pushed twice in one step: the peers must be done merging the first version
+            self._push(0)
+        self._push(self.n_local * self.block)
 
     def _allgather(self):
         if self.world > 1:
@@ -81,6 +150,10 @@ class ShardedExact:
         if self.n_slots == 1:
             self.index.search_dev(q_ptr, nq, self.k, precision, self.ids_loc.data_ptr(), self.d_loc.data_ptr(), stream)
             return self.ids_loc, self.d_loc
+        if self._sym is not None:  # next half of the symmetric buffer
+            self._parity ^= 1
+            self._stream = stream
+            self.gathered = self._sym[self._parity * self._half:(self._parity + 1) * self._half]
         self.grp.begin(q_ptr, nq, self.k, precision, self.gathered.data_ptr(), stream)
         self._exchange()
         self.exchanges = 1
@@ -92,7 +165,10 @@ class ShardedExact:
         extra = 0
         if self.n_slots > 1:
             while self.grp.finish():
-                self._exchange()
+                if self._sym is not None:
+                    self._push_exchange(redo=True)
+                else:
+                    self._exchange()
                 self.grp.merge(self.ids_loc.data_ptr(), self.d_loc.data_ptr())
                 extra += 1
                 self.exchanges += 1

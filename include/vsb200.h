@@ -152,6 +152,18 @@ VSB_API size_t vs_topk_block_bytes(int64_t nq, int k);
 VSB_API int vs_merge_blocks_dev(const void* blocks_dev, int n_shards, size_t block_stride, int64_t nq, int k, int smallest,
                                 int32_t* out_ids_dev, float* out_keys_dev, int32_t* total_dev, void* stream);
 
+/* Push form of the exchange step over NVLink peer memory (one process per GPU whose gathered buffers are mapped into each
+ * other's address space: CUDA IPC / symmetric memory).  vs_push_block_dev: ONE kernel stores `bytes` (a multiple of 16; this
+ * participant's slots; 0 = signal only) from src_dev to the same offset of every peer's gathered buffer — dst_dev is a HOST
+ * array of n_dst (<= 16) device pointers — and, once every store is fenced at system scope, writes `epoch` into each peer's
+ * flag word flag_dst[i] (peer-mapped, one word per sender).  counter_dev: a zeroed 4-byte scratch word on this device.
+ * vs_wait_flags_dev: a one-block kernel that returns when the n flag words at flags_dev (skipping index `self`) have all
+ * reached `epoch` — the receiving half of the barrier.  Both are asynchronous on `stream`; together they replace the NCCL
+ * all-gather (hai-25-rag-on-edge_b200/sharded.py).  Epochs must increase by one per exchange on every participant. */
+VSB_API int vs_push_block_dev(const void* src_dev, void* const* dst_dev, int n_dst, size_t bytes, void* const* flag_dst,
+                              uint32_t epoch, uint32_t* counter_dev, void* stream);
+VSB_API int vs_wait_flags_dev(const uint32_t* flags_dev, int n, int self, uint32_t epoch, void* stream);
+
 /* The shards that live on ONE device, as one participant of the exchange (one process per GPU: bench.py / torchrun;
  * or several shards on one GPU).  The group does not own the shard handles.  Slots first_slot .. first_slot+n_local-1
  * of the gathered buffer [n_slots][vs_topk_block_bytes(nq, k)] belong to this group.

@@ -1,5 +1,5 @@
 """Where the time of one sharded step goes (run under torchrun, one rank per GPU): CUDA events on the launching stream
-around (1) the local fused search (vs_exact_group_begin), (2) the ONE in-place NCCL all-gather of the exchange blocks,
+around (1) the local fused search (vs_exact_group_begin), (2) the ONE exchange of the blocks (push over NVLink peer memory + flag barrier, or VSB_EXCHANGE=nccl: in-place all-gather),
 (3) the merge kernel + the 4-byte total, and the host-side wall time of finish().  Prints one JSON line (rank 0, max over
 ranks).  Usage: torchrun --nproc-per-node N tools/exchange_timing.py [--nq 10000] [--rows 1000000] [--steps 20]"""
 import argparse
@@ -51,9 +51,13 @@ def main():
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         ev[0].record(stream)
         if world > 1:
+            if s._sym is not None:  # push exchange: next half of the symmetric buffer (what ShardedExact.enqueue does)
+                s._parity ^= 1
+                s._stream = stream.cuda_stream
+                s.gathered = s._sym[s._parity * s._half:(s._parity + 1) * s._half]
             s.grp.begin(q.data_ptr(), a.nq, a.k, vsb.PREC_AUTO, s.gathered.data_ptr(), stream.cuda_stream)
             ev[1].record(stream)
-            s._allgather()
+            s._exchange()
             ev[2].record(stream)
             s.grp.merge(s.ids_loc.data_ptr(), s.d_loc.data_ptr())
             ev[3].record(stream)
@@ -76,7 +80,8 @@ def main():
     if rank == 0:
         v = t.cpu().numpy()
         print(json.dumps({"n_gpus": world, "rows_per_gpu": r1 - r0, "nq": a.nq, "k": a.k,
-                          "ms_local_search_begin": v[0], "ms_allgather_blocks": v[1], "ms_merge_and_total": v[2],
+                          "exchange": s.exchange_kind,
+                          "ms_local_search_begin": v[0], "ms_exchange_blocks": v[1], "ms_merge_and_total": v[2],
                           "ms_step_device": v[3], "ms_finish_host_wall": v[4],
                           "block_bytes_per_rank": vsb.topk_block_bytes(a.nq, a.k),
                           "note": "CUDA events on the launching stream, max over ranks, L2 flushed between steps"}))
