@@ -43,12 +43,12 @@ constexpr int TC_REGS_CTRL_Q = 40, TC_REGS_KEEP_Q = 64, TC_REGS_EPI_Q = 120;
 constexpr int TC_SAMPLE_SUB = 8;                                  // sample pass: running minima per thread and unit
 constexpr int TC_SAMPLE_GROUPS = TC_EPI_GROUPS * TC_SAMPLE_SUB;  // groups of sampled rows per unit
 #ifndef VSB_TC_QN
-#define VSB_TC_QN 128
+#define VSB_TC_QN 32
 #endif
 #ifndef VSB_TC_F16_STAGES
 #define VSB_TC_F16_STAGES 3
 #endif
-constexpr int TC_QN = VSB_TC_QN;      // candidate-queue entries per quadrant
+constexpr int TC_QN = VSB_TC_QN;      // candidate-queue entries per EPILOGUE WARP (one queue per (quadrant, group): no slot atomics)
 constexpr int TC_QBATCH = 24;         // queued rows that make a batch worth folding
 constexpr int TC_QUANT_REFRESH = 16;  // tiles of one group between reads of the finished units' quantile posts (power of two)
 constexpr int TC_QENTRY = 144;        // bytes per entry: 32 keys + {row in quadrant, first column, threshold, -}
@@ -83,8 +83,8 @@ struct TcSmem {
     static constexpr int B_BYTES = NSTAGE * BSTAGE;
     static constexpr int NORM_BYTES = FOLD ? 0 : TC_NACC * TC_BN * 4;
     static constexpr int PUB_BYTES = SMEM_LIST ? 0 : TC_EPI_GROUPS * TC_BM * 8;  // per (group, query row): {key, unit tag}
-    static constexpr int STAGE_BYTES = SMEM_LIST ? 4 * TC_QN * TC_QENTRY : 0;       // candidate queues, one per quadrant
-    static constexpr int AUX_BYTES = SMEM_LIST ? TC_BM * 8 + 4 * TC_QN * 4 + 64 : 0;  // worst kept key per row, entry mask per row, ready words, tail/head
+    static constexpr int STAGE_BYTES = SMEM_LIST ? 4 * TC_EPI_GROUPS * TC_QN * TC_QENTRY : 0;  // candidate queues, one per epilogue warp
+    static constexpr int AUX_BYTES = SMEM_LIST ? 4 * TC_EPI_GROUPS * TC_QN * 4 + 128 : 0;  // ready words, final tails, heads
     static constexpr int BAR_BYTES = 1024;
     static constexpr int TOTAL = A_BYTES + B_BYTES + NORM_BYTES + PUB_BYTES + STAGE_BYTES + AUX_BYTES + BAR_BYTES +
                                  1024;  // + slack for 1024-B alignment
@@ -123,7 +123,8 @@ struct TcParams {
     const int32_t* n_items;
     const int32_t* pairs;
     int nprobe;
-    int dbg;             // timing experiments only (VSB_TC_DBG): 1 no epilogue work, 2 no inserts, 4 no MMA, 8 no B loads,
+    int dbg;             // timing experiments only (VSB_TC_DBG): 1 no epilogue work, 2 no hand-off, 4 no MMA, 8 no B loads,
+                         // 64 keeper consumes without scanning, 128 hand-off writes the header only,
                          // 16 epilogue = TMEM loads only, 32 epilogue = math only (no TMEM loads)
 };
 
@@ -231,12 +232,10 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
     uint8_t* sB = smem + S::A_BYTES;
     float* sN = (float*)(sB + S::B_BYTES);      // [TC_NACC][128] base norms of the tile in accumulator slot i
     uint2* sPub = (uint2*)((uint8_t*)sN + S::NORM_BYTES);  // [TC_EPI_GROUPS][TC_BM]
-    uint8_t* sQueue = (uint8_t*)sPub + S::PUB_BYTES;              // [4][TC_QN] entries of TC_QENTRY bytes   (SMEM_LIST)
-    float* sWorst = (float*)(sQueue + S::STAGE_BYTES);            // [TC_BM] 32nd best key of the row's list (+inf until full)
-    int* sWpos = (int*)(sWorst + (S::SMEM_LIST ? TC_BM : 0));     // [TC_BM] scratch of a batch: the entries that belong to the row
-    int* sReady = sWpos + (S::SMEM_LIST ? TC_BM : 0);             // [4][TC_QN] sequence number + 1 of the entry in the slot
-    int* sTail = sReady + (S::SMEM_LIST ? 4 * TC_QN : 0);         // [4] entries reserved so far (monotonic)
-    int* sHead = sTail + 4;                                       // [4] entries consumed so far
+    uint8_t* sQueue = (uint8_t*)sPub + S::PUB_BYTES;              // [4][TC_EPI_GROUPS][TC_QN] entries of TC_QENTRY bytes   (SMEM_LIST)
+    int* sReady = (int*)(sQueue + S::STAGE_BYTES);                // [4][TC_EPI_GROUPS][TC_QN] sequence number + 1 of the entry in the slot
+    int* sTail = sReady + (S::SMEM_LIST ? 4 * TC_EPI_GROUPS * TC_QN : 0);  // [4][TC_EPI_GROUPS] entries produced (written once, at the end)
+    int* sHead = sTail + 16;                                      // [4][TC_EPI_GROUPS] entries consumed so far
     uint64_t* bars = (uint64_t*)(sQueue + S::STAGE_BYTES + S::AUX_BYTES);
     uint64_t* full = bars;                    // [NSTAGE]  TMA -> MMA
     uint64_t* empty = full + NSTAGE;          // [NSTAGE]  MMA -> TMA
@@ -271,12 +270,8 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         mbar_init(u_done, 4 * TC_EPI_GROUPS);
         mbar_init(u_flushed, 4);
         if (S::SMEM_LIST) {
-            for (int i = 0; i < TC_BM; ++i) {
-                sWorst[i] = __int_as_float(0x7f800000);
-                sWpos[i] = 0;
-            }
-            for (int i = 0; i < 4 * TC_QN; ++i) sReady[i] = 0;
-            for (int i = 0; i < 8; ++i) sTail[i] = 0;  // tails and heads
+            for (int i = 0; i < 4 * TC_EPI_GROUPS * TC_QN; ++i) sReady[i] = 0;
+            for (int i = 0; i < 32; ++i) sTail[i] = 0;  // tails and heads
         }
         fence_barrier_init();
     }
@@ -548,37 +543,67 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TC_REGS_KEEP_Q));
         if constexpr (!SAMPLE) {
         const int quad = warp & 3;
-        const int* ready = sReady + quad * TC_QN;
-        const uint32_t queue_u = smem_u32(sQueue + quad * TC_QN * TC_QENTRY);
         const int qbatch = p.qbatch > 0 ? p.qbatch : TC_QBATCH;
-        int next = 0;         // entries consumed so far
-        int final_tail = -1;  // total number of entries, known once every epilogue warp has finished its last unit
+        // the quadrant's three queues (one per epilogue group); a batch takes entries from all of them
+        int next[TC_EPI_GROUPS], final_tail[TC_EPI_GROUPS];
+#pragma unroll
+        for (int g = 0; g < TC_EPI_GROUPS; ++g) {
+            next[g] = 0;         // entries consumed so far
+            final_tail[g] = -1;  // entries produced in total, known once every epilogue warp has finished its last unit
+        }
+        bool done = false;
         while (true) {
-            const int my = next + lane;
-            const unsigned rm = __ballot_sync(0xffffffffu, (int)ldsv_u32(ready + (my & (TC_QN - 1))) == my + 1);
-            const int n = rm == 0xffffffffu ? 32 : __ffs(~rm) - 1;  // consecutive ready entries
-            if (n == 0) {
-                if (final_tail < 0) {
-                    if (mbar_try_wait(u_done, 0u)) final_tail = (int)ldsv_u32(sTail + quad);
-                    else __nanosleep(64);
-                } else if (next == final_tail) {
-                    break;
-                }
-                continue;
+            int n[TC_EPI_GROUPS], total = 0;
+            bool half_full = false;
+#pragma unroll
+            for (int g = 0; g < TC_EPI_GROUPS; ++g) {
+                const int my = next[g] + lane;
+                const int* ready = sReady + (quad * TC_EPI_GROUPS + g) * TC_QN;
+                const unsigned rm = __ballot_sync(0xffffffffu, lane < TC_QN && (int)ldsv_u32(ready + (my & (TC_QN - 1))) == my + 1);
+                n[g] = rm == 0xffffffffu ? 32 : __ffs(~rm) - 1;  // consecutive ready entries
+                total += n[g];
+                half_full |= n[g] >= TC_QN / 2;
             }
-            // a batch has a (mostly) fixed cost: wait for a worthwhile one unless the queue fills up or the kernel ends
-            if (n < qbatch && final_tail < 0 && (int)ldsv_u32(sTail + quad) - next < TC_QN / 2) {
-                if (mbar_try_wait(u_done, 0u)) final_tail = (int)ldsv_u32(sTail + quad);
-                else __nanosleep(100);
-                continue;
+            if (total == 0 || (total < qbatch && !done && !half_full)) {
+                // nothing, or not yet a worthwhile batch (a batch has a mostly fixed cost) and no queue is filling up
+                if (!done) {
+                    if (mbar_try_wait(u_done, 0u)) {
+                        done = true;
+#pragma unroll
+                        for (int g = 0; g < TC_EPI_GROUPS; ++g) final_tail[g] = (int)ldsv_u32(sTail + quad * TC_EPI_GROUPS + g);
+                    } else {
+                        __nanosleep(total == 0 ? 64 : 100);
+                    }
+                    continue;
+                }
+                if (total == 0) {
+                    bool all = true;
+#pragma unroll
+                    for (int g = 0; g < TC_EPI_GROUPS; ++g) all &= next[g] == final_tail[g];
+                    if (all) break;
+                    continue;
+                }
             }
             asm volatile("fence.acq_rel.cta;" ::: "memory");
-            const bool act = lane < n;
-            const uint32_t e = queue_u + (uint32_t)(my & (TC_QN - 1)) * TC_QENTRY;
+            // lanes [0, t0) take queue 0, [t0, t0 + t1) queue 1, ...
+            int take[TC_EPI_GROUPS], left = 32, first = 0, my_g = -1, my_idx = 0;
+#pragma unroll
+            for (int g = 0; g < TC_EPI_GROUPS; ++g) {
+                take[g] = min(n[g], left);
+                left -= take[g];
+                if (my_g < 0 && lane < first + take[g]) {
+                    my_g = g;
+                    my_idx = next[g] + lane - first;
+                }
+                first += take[g];
+            }
+            const bool act = my_g >= 0;
+            const uint32_t e = smem_u32(sQueue) + (uint32_t)(((quad * TC_EPI_GROUPS + (act ? my_g : 0)) * TC_QN + (my_idx & (TC_QN - 1))) * TC_QENTRY);
             int qg = 0, col0 = 0, pad_;
             float thr_e = -__int_as_float(0x7f800000);
             if (act) asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(qg), "=r"(col0), "=f"(thr_e), "=r"(pad_) : "r"(e + 128u) : "memory");
             unsigned qm = 0;
+            if (!(p.dbg & 64)) {  // (timing experiment 64: consume without looking)
 #pragma unroll
             for (int j0 = 0; j0 < 32; j0 += 8) {  // eight loads in flight, then their tests
                 float v[8];
@@ -586,6 +611,7 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
                 for (int u = 0; u < 8; ++u) v[u] = lds_f32(e + (uint32_t)((j0 + u + lane) & 31) * 4u);
 #pragma unroll
                 for (int u = 0; u < 8; ++u) qm |= (v[u] < thr_e) ? (1u << ((j0 + u + lane) & 31)) : 0u;
+            }
             }
             int pos = 0;
             if (qm != 0) pos = atomicAdd(p.cand_cnt + qg, __popc(qm));
@@ -598,10 +624,13 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
                 ++pos;
             }
             __syncwarp();
-            next += n;
-            if (lane == 0) stsv_u32(sHead + quad, (uint32_t)next);  // the slots may be reused
+#pragma unroll
+            for (int g = 0; g < TC_EPI_GROUPS; ++g) {
+                next[g] += take[g];
+                if (lane == 0 && take[g] > 0) stsv_u32(sHead + quad * TC_EPI_GROUPS + g, (uint32_t)next[g]);  // the slots may be reused
+            }
             if (p.stats && lane == 0) {
-                atomicAdd(p.stats + 4, (unsigned long long)n);
+                atomicAdd(p.stats + 4, (unsigned long long)(32 - left));
                 atomicAdd(p.stats + 5, 1ull);
             }
         }
@@ -621,7 +650,12 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         const int row = quad * 32 + lane;
         const float INF = __int_as_float(0x7f800000);
         constexpr int CH = TC_BN / 32;
-        const uint32_t queue_u = smem_u32(sQueue + quad * TC_QN * TC_QENTRY);
+        // this warp's own queue: slots are handed out from a register counter, the consumer's head is re-read only when the
+        // queue looks full
+        const uint32_t queue_u = smem_u32(sQueue + (quad * TC_EPI_GROUPS + grp) * TC_QN * TC_QENTRY);
+        const uint32_t ready_u = smem_u32(sReady + (quad * TC_EPI_GROUPS + grp) * TC_QN);
+        const int* my_head = sHead + quad * TC_EPI_GROUPS + grp;
+        int qtail = 0, head_seen = 0;
         int tcount = 0;
         for (int unit = worker; unit < n_units; unit += n_workers) {
             const int m_tile = (unit % n_mt) * CL + cta_rank;
@@ -679,28 +713,29 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
                     const bool hit = m[0] < thr;
                     const unsigned todo = __ballot_sync(0xffffffffu, hit);
                     if (todo != 0 && !(p.dbg & 2)) {
-                        int base = 0;
-                        if (lane == 0) {
-                            base = atomicAdd(sTail + quad, __popc(todo));
-                            if (p.stats) {
-                                atomicAdd(p.stats + 0, 1ull);
-                                atomicAdd(p.stats + 1, (unsigned long long)__popc(todo));
-                            }
+                        if (p.stats && lane == 0) {
+                            atomicAdd(p.stats + 0, 1ull);
+                            atomicAdd(p.stats + 1, (unsigned long long)__popc(todo));
                         }
-                        base = __shfl_sync(0xffffffffu, base, 0);
                         if (hit) {
-                            const int idx = base + __popc(todo & ((1u << lane) - 1u));
-                            while (idx - (int)ldsv_u32(sHead + quad) >= TC_QN) __nanosleep(100);  // queue full: leave the issue slots to the keeper
+                            const int idx = qtail + __popc(todo & ((1u << lane) - 1u));
+                            while (idx - head_seen >= TC_QN) {  // looks full: refresh the head; really full: leave the issue slots to the keeper
+                                head_seen = (int)ldsv_u32(my_head);
+                                if (idx - head_seen >= TC_QN) __nanosleep(100);
+                            }
                             const uint32_t e = queue_u + (uint32_t)(idx & (TC_QN - 1)) * TC_QENTRY;
+                            if (!(p.dbg & 128)) {  // (timing experiment 128: header only)
 #pragma unroll
                             for (int j4 = 0; j4 < 8; ++j4)
                                 asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(e + (uint32_t)(j4 << 4)),
                                              "f"(d[4 * j4 + 0]), "f"(d[4 * j4 + 1]), "f"(d[4 * j4 + 2]), "f"(d[4 * j4 + 3]) : "memory");
+                            }
                             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(e + 128u), "r"(q), "r"(t * TC_BN + c * 32),
                                          "f"(thr), "r"(0) : "memory");
-                            asm volatile("fence.acq_rel.cta;" ::: "memory");
-                            stsv_u32(sReady + quad * TC_QN + (idx & (TC_QN - 1)), (uint32_t)(idx + 1));
+                            // release: the entry is complete before its sequence number shows
+                            asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(ready_u + (uint32_t)(idx & (TC_QN - 1)) * 4u), "r"(idx + 1) : "memory");
                         }
+                        qtail += __popc(todo);
                         __syncwarp();
                     }
                 }
@@ -722,7 +757,10 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
             }
         }
         __syncwarp();
-        if (!SAMPLE && lane == 0) mbar_arrive(u_done);  // every candidate of this warp is in the queue (release)
+        if (!SAMPLE && lane == 0) {
+            stsv_u32(sTail + quad * TC_EPI_GROUPS + grp, (uint32_t)qtail);
+            mbar_arrive(u_done);  // every candidate of this warp is in its queue, the final count is published (release)
+        }
        }
       } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(TC_REGS_EPI));
