@@ -53,7 +53,7 @@ typedef enum vs_status {
 /* Arithmetic of the exact path's dot products (distances are always combined in fp32 as
  * (qn + bn) - 2*dot, cpu_baseline.cpp:241). */
 typedef enum vs_precision {
-    VS_PREC_AUTO = 0,        /* <= 8 queries -> FFMA stream; >= 449 queries and k <= 16 -> certified fp16 candidate pass
+    VS_PREC_AUTO = 0,        /* <= 8 queries -> FFMA stream; >= 449 queries, k <= 16, base >= ~13 K rows -> certified fp16 pass
                                 (below); otherwise 1xTF32 when every operand is exactly representable in TF32 (integer
                                 SIFT data: bit-identical to fp32), else 3xTF32.  Thresholds measured on B200. */
     VS_PREC_FP32_3XTF32 = 1, /* tcgen05 kind::tf32, hi/lo split, 3 products, fp32 accumulate in TMEM.  The tensor-core keys
@@ -63,10 +63,12 @@ typedef enum vs_precision {
     VS_PREC_FP32_FFMA = 2,   /* CUDA-core FFMA streaming kernel (HBM-bound; any batch, slow for large ones) */
     VS_PREC_TF32_1X = 3,     /* single TF32 product; exact only for TF32-representable data */
     VS_PREC_F16_CERTIFIED = 4 /* fp32-faithful results from a cheaper tensor-core pass: tcgen05 kind::f16 on power-of-two
-                                scaled fp16 copies keeps the 32 best keys per query (key error rigorously bounded), those
-                                32 distances are recomputed in exact fp32 and the top k is certified complete per query
-                                (every excluded row is provably farther than the k-th result); queries that cannot be
-                                certified are redone with 3xTF32 / FFMA.  k <= 16.  Synchronises the stream once. */
+                                scaled fp16 copies collects every row whose key lies below a per-query threshold (taken
+                                from a sample pass over 1/16 of the base; key error rigorously bounded), the <= 32 best
+                                are recomputed in exact fp32 and the top k is certified complete per query (every
+                                excluded row is provably farther than the k-th result); queries that cannot be certified
+                                are redone with 3xTF32 / FFMA.  k <= 16; bases of 513 .. ~13 K rows take 3xTF32 instead
+                                (no meaningful sample).  Synchronises the stream once. */
 } vs_precision;
 
 VSB_API const char* vs_last_error(void);
