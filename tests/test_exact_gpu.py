@@ -203,6 +203,34 @@ def test_certified_path_falls_back_when_it_cannot_certify(gpu_vsb, oracle):
         idx.close()
 
 
+def test_f16_unrepresentative_sample_overflows_and_falls_back(gpu_vsb, oracle):
+    """The per-query threshold of the certified fp16 path comes from a sample (one base tile in 16, tiles 3, 19, 35, ...).
+    Any threshold is legal — the certificate is evaluated against it — so an UNREPRESENTATIVE sample must only cost time:
+    here every sampled tile holds far-away rows, the thresholds come out huge, every near row becomes a candidate, the
+    candidate arrays overflow (512) and every query is redone on the fp32 path.  And the mirror case: the sampled tiles
+    hold the ONLY near rows (thresholds far too tight for the rest: fewer than k candidates can happen)."""
+    vsb = gpu_vsb
+    n, nq, k = 60_000, 96, 10
+    tiles = np.arange(n) // 128
+    sampled = (tiles % 16) == 3
+    qry = vsb.synth.make("cont", 52, nq)
+    for far_rows in (sampled, ~sampled):
+        base = vsb.synth.make("cont", 51, n)
+        base[far_rows] += 500.0
+        oi, od = oracle.exact_search(base, qry, k, mode=1)
+        idx = vsb.ExactIndex(base)
+        try:
+            ids, d = idx.search(qry, k, vsb.PREC_F16_CERT)
+            assert idx.last_launches()[1] == vsb.PREC_F16_CERT
+            nfb = idx.last_fallbacks()
+            if far_rows is sampled:
+                assert nfb == nq, nfb          # every candidate array overflowed
+            rec = oracle.exact_distances_at(base, qry, ids)
+            assert_topk_matches(ids, d, oi, od, rec, exact=False, what=f"unrepresentative sample, {nfb} fallbacks")
+        finally:
+            idx.close()
+
+
 @pytest.mark.parametrize("g,k,smallest", [(2, 33, True), (5, 100, True), (8, 100, True), (8, 257, False), (3, 64, False)])
 def test_merge_topk_dev_any_k(gpu_vsb, g, k, smallest):
     """vs_merge_topk_dev for k > 32 (the exchange step of config 5: top-100 over 8 shards): per-shard lists in

@@ -30,6 +30,7 @@ def _set_scan(monkeypatch, scan):
 @pytest.mark.parametrize("law", ["mix", "cont"])
 @pytest.mark.parametrize("n,nlist,nq,k,nprobe", [(20000, 64, 50, 10, 8), (5000, 16, 33, 5, 16), (3000, 300, 7, 10, 3),
                                                  (100000, 256, 200, 10, 32), (2000, 8, 5, 32, 100), (30000, 40, 700, 16, 5),
+                                                 (120000, 64, 400, 30, 32),   # up to 3 x 32 x 32 candidates per query (K9)
                                                  (9000, 700, 65, 1, 9)])
 def test_search_matches_restatement(scan, law, n, nlist, nq, k, nprobe, gpu_vsb, oracle, monkeypatch):
     """Both fine-scan kernels (K6 query-major, K8 list-major) against the CPU restatement: same probe sets, bit-identical
