@@ -11,6 +11,8 @@
 #include <new>
 #include <string>
 
+#include <cstdlib>
+
 #include "kernels.cuh"
 #include "vsb_common.cuh"
 
@@ -156,8 +158,13 @@ static int int8_search_core(vs_int8* h, const float* q_dev, int64_t nq, int k, i
     for (int c = 1; c < rep; ++c)
         VSB_CUDA(cudaMemcpyAsync(h->q_u8.as<uint8_t>() + (size_t)c * (128 / rep) * 128, h->q_u8.p, (size_t)nq * 128,
                                  cudaMemcpyDeviceToDevice, st));
-    const TcPlan plan = tc_make_plan(h->n, nq, h->num_sms, 2);  // independent CTAs (no pair mode in this kernel)
-    const int n_lists = plan.n_splits * int8_lists_per_split() * rep;
+    // batches of more than one query tile: two query tiles per unit share every base tile (int8_tc_pair_kernel; the plan then
+    // counts tile PAIRS as its columns); VSB_INT8_PAIR=0 keeps one tile per unit
+    const char* pe = getenv("VSB_INT8_PAIR");
+    const bool pair = nq > 128 && !(pe && atoi(pe) == 0);
+    const int64_t n_mt = ceil_div64(nq, 128);
+    const TcPlan plan = tc_make_plan(h->n, pair ? ceil_div64(n_mt, 2) * 128 : nq, h->num_sms, 2);
+    const int n_lists = pair ? plan.n_splits : plan.n_splits * int8_lists_per_split() * rep;
     VSB_TRY(h->part_key.reserve(sizeof(float) * (size_t)n_lists * nq * ktop));
     VSB_TRY(h->part_id.reserve(sizeof(int32_t) * (size_t)n_lists * nq * ktop));
     VSB_TRY(h->gthr.reserve(sizeof(int32_t) * (size_t)nq));
@@ -166,7 +173,7 @@ static int int8_search_core(vs_int8* h, const float* q_dev, int64_t nq, int k, i
     CUtensorMap tmA;
     VSB_TRY(make_tmap_2d(&tmA, h->q_u8.p, (uint64_t)(rep > 1 ? 128 : nq), 128, 1, 128));
     if (h->profile) VSB_CUDA(cudaEventRecord(h->ev0, st));
-    VSB_TRY(launch_int8_tc(tmA, h->tmB, h->gthr.as<int32_t>(), h->m, (int)nq, h->n, plan, ktop, rep, h->part_key.as<float>(),
+    VSB_TRY(launch_int8_tc(tmA, h->tmB, h->gthr.as<int32_t>(), h->m, (int)nq, h->n, plan, ktop, pair ? 0 : rep, h->part_key.as<float>(),
                            h->part_id.as<int32_t>(), st));
     if (h->profile) {
         VSB_CUDA(cudaEventRecord(h->ev1, st));

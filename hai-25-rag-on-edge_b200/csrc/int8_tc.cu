@@ -281,6 +281,218 @@ int8_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 // ------------------------------------------------------------------------------------------------
+// K5, large batches: TWO query tiles per unit share every base tile.  With one query tile per CTA a 16 KB base tile feeds only
+// four MMAs (~256 tensor cycles): the TMA fill rate of an SM (~64 B/clk, profiles/r2_sm_limits_tmem_tma.txt) equals the MMA
+// rate and the two contend for shared-memory bandwidth.  With a pair, a tile feeds eight MMAs; epilogue group g owns query
+// tile g of the pair (all 128 columns of its accumulator), TMEM holds two pair-buffers of 2 x 128 columns, and a unit writes
+// ONE list per query instead of two.
+// ------------------------------------------------------------------------------------------------
+constexpr int I8P_NSTAGE = 8;
+constexpr int I8P_SMEM = I8_TILE_BYTES * (2 + I8P_NSTAGE) + 1024 + 1024;
+
+template <int KTOP>
+__global__ void __launch_bounds__(I8_THREADS, 1)
+int8_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const I8Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* sA = smem;  // two query tiles
+    uint8_t* sB = smem + 2 * I8_TILE_BYTES;
+    uint64_t* bars = (uint64_t*)(sB + I8P_NSTAGE * I8_TILE_BYTES);
+    uint64_t* full = bars;
+    uint64_t* empty = full + I8P_NSTAGE;
+    uint64_t* acc_full = empty + I8P_NSTAGE;   // [2] pair-buffers
+    uint64_t* acc_empty = acc_full + 2;
+    uint64_t* a_full = acc_empty + 2;
+    uint64_t* a_empty = a_full + 1;
+    uint32_t* tmem_slot = (uint32_t*)(a_empty + 1);
+
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const int lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < I8P_NSTAGE; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&acc_full[i], 1);
+            mbar_init(&acc_empty[i], 4 * I8_EPI_GROUPS);
+        }
+        mbar_init(a_full, 1);
+        mbar_init(a_empty, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int n_pairs = p.n_mtiles;  // the plan counts tile PAIRS as its query-tile columns
+    const int n_units = n_pairs * p.n_splits;
+
+    if (warp == 0) {
+        const bool leader = elect_one();
+        if (leader) {
+            tma_prefetch_desc(&tmA);
+            tma_prefetch_desc(&tmB);
+        }
+        int stage = 0;
+        uint32_t phase = 0;
+        int it = 0;
+        for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++it) {
+            const int pair = unit % n_pairs;
+            const int split = unit / n_pairs;
+            mbar_wait(a_empty, (uint32_t)((it & 1) ^ 1));
+            if (leader) {
+                mbar_expect_tx(a_full, (uint32_t)(2 * I8_TILE_BYTES));
+                tma_load_2d(sA, &tmA, a_full, 0, (2 * pair) * I8_BM);
+                tma_load_2d(sA + I8_TILE_BYTES, &tmA, a_full, 0, (2 * pair + 1) * I8_BM);  // beyond nq: zero fill
+            }
+            const int t0 = split * p.tiles_per_split;
+            const int t1 = min(t0 + p.tiles_per_split, p.n_tiles);
+            for (int t = t0; t < t1; ++t) {
+                mbar_wait(&empty[stage], phase ^ 1);
+                if (leader) {
+                    mbar_expect_tx(&full[stage], (uint32_t)I8_TILE_BYTES);
+                    tma_load_2d(sB + stage * I8_TILE_BYTES, &tmB, &full[stage], 0, t * I8_BN);
+                }
+                if (++stage == I8P_NSTAGE) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        const bool leader = elect_one();
+        constexpr uint32_t idesc = umma_idesc(kIdescCS32, kIdescU8, I8_BM, I8_BN);
+        const uint64_t a0_desc = umma_desc_sw128(smem_u32(sA));
+        const uint64_t a1_desc = umma_desc_sw128(smem_u32(sA + I8_TILE_BYTES));
+        const uint32_t sB_u = smem_u32(sB);
+        int stage = 0, buf = 0;
+        uint32_t phase = 0, buf_phase = 0;
+        int it = 0;
+        for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++it) {
+            const int split = unit / n_pairs;
+            const int t0 = split * p.tiles_per_split;
+            const int t1 = min(t0 + p.tiles_per_split, p.n_tiles);
+            mbar_wait(a_full, (uint32_t)(it & 1));
+            tc_fence_after();
+            for (int t = t0; t < t1; ++t) {
+                mbar_wait(&acc_empty[buf], buf_phase ^ 1);
+                mbar_wait(&full[stage], phase);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(buf * 2 * I8_BN);
+                const uint64_t b_desc = umma_desc_sw128(sB_u + stage * I8_TILE_BYTES);
+                if (leader) {
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) tc_mma_i8(d_tmem, a0_desc + 2 * ks, b_desc + 2 * ks, idesc, ks > 0 ? 1u : 0u);
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) tc_mma_i8(d_tmem + I8_BN, a1_desc + 2 * ks, b_desc + 2 * ks, idesc, ks > 0 ? 1u : 0u);
+                    tc_commit(&empty[stage]);
+                    tc_commit(&acc_full[buf]);
+                }
+                if (++stage == I8P_NSTAGE) { stage = 0; phase ^= 1; }
+                if (++buf == 2) { buf = 0; buf_phase ^= 1; }
+            }
+            if (leader) tc_commit(a_empty);
+        }
+    } else {
+        const int quad = warp & 3;
+        const int grp = (warp - 2) >> 2;  // = which query tile of the pair
+        const int row = quad * 32 + lane;
+        const float INF = __int_as_float(0x7f800000);
+        constexpr int CH = I8_BN / 32;
+        int buf = 0;
+        uint32_t buf_phase = 0;
+        for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+            const int pair = unit % n_pairs;
+            const int split = unit / n_pairs;
+            const int t0 = split * p.tiles_per_split;
+            const int t1 = min(t0 + p.tiles_per_split, p.n_tiles);
+            const int m_tile = 2 * pair + grp;
+            const int q = m_tile * I8_BM + row;
+            const bool valid = q < p.nq;
+            const bool quad_live = m_tile * I8_BM + quad * 32 < p.nq;  // idle quadrants only handshake
+            RegTopK<KTOP> top;
+            top.init();
+            float cap = INF, thr = INF;
+            int32_t bound = 0;
+            for (int t = t0; t < t1; ++t) {
+                const int rel = (t - t0) & (I8_THR_REFRESH - 1);
+                if (rel == 0 && valid) {
+                    cap = fminf(cap, ordered_to_float(__ldcg(p.gthr + q)));
+                    thr = fminf(top.threshold(), cap + 1.0f);  // keys are integers: next key above cap
+                    if (!(cap < 1e30f)) thr = top.threshold();
+                    bound = acc_bound_for_thr(thr, p.m);
+                }
+                mbar_wait(&acc_full[buf], buf_phase);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * 2 * I8_BN + grp * I8_BN);
+                uint32_t r[2][32];
+                auto fold = [&](const uint32_t (&rr)[32], const int col0) {
+                    int32_t a[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) a[j] = (int32_t)rr[j];
+                    int32_t mx[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) mx[j] = max(a[j], a[j + 16]);
+#pragma unroll
+                    for (int w = 8; w >= 1; w >>= 1)
+#pragma unroll
+                        for (int j = 0; j < w; ++j) mx[j] = max(mx[j], mx[j + w]);
+                    if (mx[0] >= bound) {
+                        uint32_t mask = 0;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) mask |= (a[j] >= bound) ? (1u << j) : 0u;
+                        while (mask) {
+                            const int j = __ffs(mask) - 1;
+                            mask &= mask - 1;
+                            const int32_t av = select32(a, j);
+                            if (av >= bound && (int64_t)(col0 + j) < p.n) {
+                                const float key = -(float)requant_u8(av, p.m);
+                                if (key < thr) {
+                                    top.insert(key, col0 + j);
+                                    thr = fminf(thr, top.threshold());
+                                    bound = acc_bound_for_thr(thr, p.m);
+                                }
+                            }
+                        }
+                    }
+                };
+                if (quad_live) tmem_ld32(taddr, r[0]);
+#pragma unroll
+                for (int c = 0; c < CH; ++c) {
+                    if (!quad_live) break;
+                    tc_wait_ld();
+                    if (c + 1 < CH) tmem_ld32(taddr + (c + 1) * 32, r[(c + 1) & 1]);
+                    fold(r[c & 1], t * I8_BN + c * 32);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[buf]);
+                if (++buf == 2) { buf = 0; buf_phase ^= 1; }
+                if (valid && rel == I8_THR_REFRESH - 1 && top.threshold() < cap) {
+                    atomicMin(p.gthr + q, float_to_ordered(top.threshold()));
+                    cap = top.threshold();
+                }
+            }
+            if (valid) {
+                if (top.threshold() < cap) atomicMin(p.gthr + q, float_to_ordered(top.threshold()));
+                float* pk = p.part_key + ((size_t)split * p.nq + q) * KTOP;  // one list per (split, query)
+                int32_t* pi = p.part_id + ((size_t)split * p.nq + q) * KTOP;
+#pragma unroll
+                for (int i = 0; i < KTOP; ++i) {
+                    pk[i] = top.key[i];
+                    pi[i] = top.id[i];
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------------
 // K4 quantiser, float->u8 score conversion, raw score matrix (tests), max reduction (weight scale)
 // ------------------------------------------------------------------------------------------------
 __global__ void quantize_u8_kernel(const float* __restrict__ src, int64_t count, float inv_scale, uint8_t* __restrict__ dst) {
@@ -367,6 +579,7 @@ static int int8_set_attr_k() {
     VSB_CUDA(cudaFuncSetAttribute(int8_tc_kernel<KTOP, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM));
     VSB_CUDA(cudaFuncSetAttribute(int8_tc_kernel<KTOP, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM));
     VSB_CUDA(cudaFuncSetAttribute(int8_tc_kernel<KTOP, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM));
+    VSB_CUDA(cudaFuncSetAttribute(int8_tc_pair_kernel<KTOP>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8P_SMEM));
     return VS_OK;
 }
 int int8_set_attributes() {
@@ -379,8 +592,25 @@ int int8_set_attributes() {
 }
 int int8_lists_per_split() { return I8_EPI_GROUPS; }
 
+// pair mode (rep == 0): plan.n_mtiles counts PAIRS of query tiles; one list per (split, query)
 int launch_int8_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, int32_t* gthr, float m, int nq, int64_t n, const TcPlan& plan,
                    int ktop, int rep, float* part_key, int32_t* part_id, cudaStream_t st) {
+    if (rep == 0) {
+        I8Params pp{gthr, part_key, part_id, m, nq, n, plan.n_tiles, plan.n_mtiles, plan.n_splits, plan.tiles_per_split, 1};
+#define VSB_I8P_LAUNCH(KT) \
+    case KT: int8_tc_pair_kernel<KT><<<plan.grid, I8_THREADS, I8P_SMEM, st>>>(tmA, tmB, pp); break;
+        switch (ktop) {
+            VSB_I8P_LAUNCH(1)
+            VSB_I8P_LAUNCH(5)
+            VSB_I8P_LAUNCH(10)
+            VSB_I8P_LAUNCH(16)
+            VSB_I8P_LAUNCH(32)
+            default: return fail(VS_ERR_UNSUPPORTED, "INT8 search: k > 32 is not implemented");
+        }
+#undef VSB_I8P_LAUNCH
+        VSB_CUDA(cudaGetLastError());
+        return VS_OK;
+    }
     if (rep != 1 && rep != 2 && rep != 4) return fail(VS_ERR_INVALID, "int8: replication must be 1, 2 or 4");
     if (rep > 1 && nq > I8_BM / rep) return fail(VS_ERR_INVALID, "int8: too many queries for the replication factor");
     I8Params p{gthr, part_key, part_id, m, nq, n, plan.n_tiles, plan.n_mtiles, plan.n_splits, plan.tiles_per_split, rep};
