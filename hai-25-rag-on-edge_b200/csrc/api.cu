@@ -304,7 +304,8 @@ static int exact_f16_candidate_pass(vs_exact* h, const float* q_dev, int64_t nq,
                                     nullptr, nullptr, 0, st));
         VSB_TRY(launch_tc_select_thr(h->f_smin.as<float>(), n_groups, (int)nq, m, h->f_thr.as<float>(), h->f_cnt.as<int32_t>(), st));
     }
-    const TcPlan plan = tc_make_plan(h->n, nq, h->num_sms, 2);
+    // the filter pass holds two query tiles per unit (every base tile feeds both): its plan counts tile PAIRS as columns
+    const TcPlan plan = tc_make_plan(h->n, ceil_div64(ceil_div64(nq, 128), 2) * 128, h->num_sms, 2);
     if (h->profile) VSB_CUDA(cudaEventRecord(h->ev0, st));  // the dominant kernel alone: the filter pass
     VSB_TRY(launch_exact_tc_f16(tmA, tmAe, h->tmB16, (int)nq, h->n, plan, false, 1, 0, nullptr, h->f_thr.as<float>(),
                                 h->f_cnt.as<int32_t>(), h->f_cand.p, kF16CandCap, st));

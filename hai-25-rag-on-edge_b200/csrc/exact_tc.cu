@@ -48,13 +48,17 @@ TcPlan tc_make_plan(int64_t n, int64_t nq, int num_sms, int mode) {
     return pl;
 }
 
+// shared-memory layout of an instantiation (the fp16 filter pass, KTOP == 32, holds two query tiles per unit)
+template <int KTOP, int MODE>
+using TcS = TcSmem<MODE, MODE == TC_F16 && KTOP == 32>;
+
 template <int KTOP, int MODE, bool HAS_LB>
 static int set_attr_one() {
     VSB_CUDA(cudaFuncSetAttribute(exact_tc_kernel<KTOP, MODE, HAS_LB, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  TcSmem<MODE>::TOTAL));
+                                  TcS<KTOP, MODE>::TOTAL));
     if constexpr (MODE != TC_F16)
         VSB_CUDA(cudaFuncSetAttribute(exact_tc_kernel<KTOP, MODE, HAS_LB, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      TcSmem<MODE>::TOTAL));
+                                      TcS<KTOP, MODE>::TOTAL));
     return VS_OK;
 }
 
@@ -64,8 +68,8 @@ static int launch_one(const TcPlan& plan, const CUtensorMap& tmA_hi, const CUten
                       const CUtensorMap& tmB_lo, const TcParams& p, cudaStream_t st) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)plan.grid);
-    cfg.blockDim = dim3((unsigned)TcSmem<MODE>::THREADS);
-    cfg.dynamicSmemBytes = TcSmem<MODE>::TOTAL;
+    cfg.blockDim = dim3((unsigned)TcS<KTOP, MODE>::THREADS);
+    cfg.dynamicSmemBytes = TcS<KTOP, MODE>::TOTAL;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;

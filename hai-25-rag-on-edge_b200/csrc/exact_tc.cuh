@@ -48,6 +48,9 @@ constexpr int TC_SAMPLE_GROUPS = TC_EPI_GROUPS * TC_SAMPLE_SUB;  // groups of sa
 #ifndef VSB_TC_F16_STAGES
 #define VSB_TC_F16_STAGES 3
 #endif
+#ifndef VSB_TC_F16_PAIR_STAGES
+#define VSB_TC_F16_PAIR_STAGES 2
+#endif
 constexpr int TC_QN = VSB_TC_QN;      // candidate-queue entries per EPILOGUE WARP (one queue per (quadrant, group): no slot atomics)
 constexpr int TC_QBATCH = 24;         // queued rows that make a batch worth folding
 constexpr int TC_QUANT_REFRESH = 16;  // tiles of one group between reads of the finished units' quantile posts (power of two)
@@ -64,13 +67,16 @@ enum TcMode : int { TC_TF32X1 = 0, TC_TF32X3 = 1, TC_F16 = 2 };
 
 constexpr int TC_FOLD_BYTES = 128 * 32;  // the K = 16 norm block of a 128-row operand tile: 128 rows x 32 B (SWIZZLE_32B)
 
-template <int MODE>
+// PAIR (TC_F16 filter pass): two query tiles per unit share every base tile.  With one, a 36 KB base tile feeds 9 MMAs (576
+// tensor cycles): the SM's TMA fill rate (~64 B/clk, profiles/r2_sm_limits_tmem_tma.txt) equals the MMA rate and the two
+// contend for shared-memory bandwidth; with a pair it feeds 18.
+template <int MODE, bool PAIR = false>
 struct TcSmem {
     static constexpr bool SPLIT3 = MODE == TC_TF32X3;
     static constexpr int NKB = MODE == TC_F16 ? 2 : 4;  // 128-byte k-blocks per row (128 fp16 = 256 B, 128 fp32 = 512 B)
     // TC_F16 folds the norm term into the MMA: one extra K = 16 block on both operands (kernels.cuh, TC_FOLD_COLS)
     static constexpr bool FOLD = MODE == TC_F16;
-    static constexpr int A_BYTES = (SPLIT3 ? 2 : 1) * NKB * TC_KB_BYTES + (FOLD ? TC_FOLD_BYTES : 0);
+    static constexpr int A_BYTES = (SPLIT3 || PAIR ? 2 : 1) * NKB * TC_KB_BYTES + (FOLD ? TC_FOLD_BYTES : 0);
     // TC_F16 keeps ONE candidate list per query row in the registers of dedicated list-keeper warps that are fed
     // through per-quadrant shared-memory queues; the other modes keep three per-thread register lists per row in the
     // epilogue warps themselves (their query tile leaves no room for the queues: 64 / 128 KB)
@@ -78,7 +84,7 @@ struct TcSmem {
     static constexpr int THREADS = SMEM_LIST ? TC_THREADS_Q : TC_THREADS;
     // ring of base operand stages: TC_F16 one whole tile per stage (two k-blocks + the norm block, 36 KB), the TF32 modes one
     // k-block per stage
-    static constexpr int NSTAGE = MODE == TC_F16 ? VSB_TC_F16_STAGES : (SPLIT3 ? 5 : 8);
+    static constexpr int NSTAGE = MODE == TC_F16 ? (PAIR ? VSB_TC_F16_PAIR_STAGES : VSB_TC_F16_STAGES) : (SPLIT3 ? 5 : 8);
     static constexpr int BSTAGE = MODE == TC_F16 ? 2 * TC_KB_BYTES + TC_FOLD_BYTES : TC_KB_BYTES;
     static constexpr int B_BYTES = NSTAGE * BSTAGE;
     static constexpr int NORM_BYTES = FOLD ? 0 : TC_NACC * TC_BN * 4;
@@ -219,7 +225,8 @@ __global__ void __launch_bounds__(TcSmem<MODE>::THREADS, 1)
 exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                 const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                 const TcParams p) {
-    using S = TcSmem<MODE>;
+    constexpr bool PAIR = MODE == TC_F16 && KTOP == 32;  // the filter pass; p.n_mtiles then counts PAIRS of query tiles
+    using S = TcSmem<MODE, PAIR>;
     constexpr int NSTAGE = S::NSTAGE;
     constexpr bool SPLIT3 = S::SPLIT3;
     constexpr int TC_NKB = S::NKB;
@@ -326,9 +333,17 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
                   mbar_wait(a_empty, (uint32_t)((it & 1) ^ 1));
                   if (leader) {
                       mbar_expect_tx(a_full, (uint32_t)S::A_BYTES);
-                      tma_load_2d(sA, &tmA_hi, a_full, 0, m_tile * TC_BM);
-                      tma_load_2d(sA + TC_KB_BYTES, &tmA_hi, a_full, 64, m_tile * TC_BM);
-                      tma_load_2d(sA + 2 * TC_KB_BYTES, &tmA_lo, a_full, 0, 0);  // the same 128 x 16 constants for every tile
+                      if constexpr (PAIR) {  // query tiles 2 m and 2 m + 1 (the latter may lie beyond nq: zero fill)
+                          tma_load_2d(sA, &tmA_hi, a_full, 0, 2 * m_tile * TC_BM);
+                          tma_load_2d(sA + TC_KB_BYTES, &tmA_hi, a_full, 64, 2 * m_tile * TC_BM);
+                          tma_load_2d(sA + 2 * TC_KB_BYTES, &tmA_hi, a_full, 0, (2 * m_tile + 1) * TC_BM);
+                          tma_load_2d(sA + 3 * TC_KB_BYTES, &tmA_hi, a_full, 64, (2 * m_tile + 1) * TC_BM);
+                          tma_load_2d(sA + 4 * TC_KB_BYTES, &tmA_lo, a_full, 0, 0);
+                      } else {
+                          tma_load_2d(sA, &tmA_hi, a_full, 0, m_tile * TC_BM);
+                          tma_load_2d(sA + TC_KB_BYTES, &tmA_hi, a_full, 64, m_tile * TC_BM);
+                          tma_load_2d(sA + 2 * TC_KB_BYTES, &tmA_lo, a_full, 0, 0);  // the same 128 x 16 constants for every tile
+                      }
                   }
                   const int t0 = split * p.tiles_per_split;
                   const int t1 = min(t0 + p.tiles_per_split, p.n_tiles);
@@ -438,7 +453,8 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
             if constexpr (MODE == TC_F16) {
               // 9 instructions per tile: 2 k-blocks x 4 (K = 16 each) of  (-s_q q) . (s_b x)  and the norm block
               // (2^rho constants) . (pieces of s_b^2 ||x||^2 / 2):  acc = (s_q s_b / 2) (||x||^2 - 2 q.x)
-              const uint64_t a_e = umma_desc_sw32(sA_u + 2 * TC_KB_BYTES);
+              constexpr int NH = PAIR ? 2 : 1;  // query tiles per unit
+              const uint64_t a_e = umma_desc_sw32(sA_u + NH * 2 * TC_KB_BYTES);
               for (int unit = worker; unit < n_units; unit += n_workers, ++it) {
                   const int split = unit / n_mt;
                   const int t0 = split * p.tiles_per_split;
@@ -446,27 +462,28 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
                   mbar_wait(a_full, (uint32_t)(it & 1));
                   tc_fence_after();
                   for (int t = t0; t < t1; ++t) {
-                      mbar_wait(&acc_empty[acc], acc_phase ^ 1);
                       mbar_wait(&full[stage], phase);
-                      tc_fence_after();
-                      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TC_BN);
                       const uint32_t b_u = sB_u + stage * S::BSTAGE;
-                      if (!(p.dbg & 4) && leader) {
 #pragma unroll
-                          for (int kb = 0; kb < 2; ++kb) {
-                              const uint64_t a = umma_desc_sw128(sA_u + kb * TC_KB_BYTES);
-                              const uint64_t b = umma_desc_sw128(b_u + kb * TC_KB_BYTES);
+                      for (int h = 0; h < NH; ++h) {  // one accumulator per query tile of the unit
+                          mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+                          tc_fence_after();
+                          const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TC_BN);
+                          if (!(p.dbg & 4) && leader) {
 #pragma unroll
-                              for (int ks = 0; ks < 4; ++ks) tc_mma_f16(d_tmem, a + 2 * ks, b + 2 * ks, idesc, (kb | ks) ? 1u : 0u);
+                              for (int kb = 0; kb < 2; ++kb) {
+                                  const uint64_t a = umma_desc_sw128(sA_u + (2 * h + kb) * TC_KB_BYTES);
+                                  const uint64_t b = umma_desc_sw128(b_u + kb * TC_KB_BYTES);
+#pragma unroll
+                                  for (int ks = 0; ks < 4; ++ks) tc_mma_f16(d_tmem, a + 2 * ks, b + 2 * ks, idesc, (kb | ks) ? 1u : 0u);
+                              }
+                              tc_mma_f16(d_tmem, a_e, umma_desc_sw32(b_u + 2 * TC_KB_BYTES), idesc, 1u);
                           }
-                          tc_mma_f16(d_tmem, a_e, umma_desc_sw32(b_u + 2 * TC_KB_BYTES), idesc, 1u);
+                          if (leader) tc_commit(&acc_full[acc]);
+                          if (++acc == TC_NACC) { acc = 0; acc_phase ^= 1; }
                       }
-                      if (leader) {
-                          tc_commit(&empty[stage]);
-                          tc_commit(&acc_full[acc]);
-                      }
+                      if (leader) tc_commit(&empty[stage]);
                       if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
-                      if (++acc == TC_NACC) { acc = 0; acc_phase ^= 1; }
                   }
                   if (leader) tc_commit(a_empty);
               }
@@ -658,22 +675,35 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         int qtail = 0, head_seen = 0;
         int tcount = 0;
         for (int unit = worker; unit < n_units; unit += n_workers) {
-            const int m_tile = (unit % n_mt) * CL + cta_rank;
+            constexpr int NH = PAIR ? 2 : 1;  // query tiles per unit: every base tile yields NH accumulator tiles
+            const int m_tile = (unit % n_mt) * NH;
             const int split = unit / n_mt;
             const int t0 = split * p.tiles_per_split;
             const int t1 = min(t0 + p.tiles_per_split, p.n_tiles);
-            const int q = m_tile * TC_BM + row;
-            const bool valid = q < p.nq;
-            const bool quad_live = m_tile * TC_BM + quad * 32 < p.nq;
-            float thr = -INF;  // rows beyond the last query never pass
-            if (!SAMPLE && valid) thr = __ldg(p.thr + q);
+            int qh[NH];
+            bool validh[NH], liveh[NH];
+            float thrh[NH];
+#pragma unroll
+            for (int h = 0; h < NH; ++h) {
+                qh[h] = (m_tile + h) * TC_BM + row;
+                validh[h] = qh[h] < p.nq;
+                liveh[h] = (m_tile + h) * TC_BM + quad * 32 < p.nq;
+                thrh[h] = -INF;  // rows beyond the last query never pass
+                if (!SAMPLE && validh[h]) thrh[h] = __ldg(p.thr + qh[h]);
+            }
             float gmin[TC_SAMPLE_SUB];
 #pragma unroll
             for (int u = 0; u < TC_SAMPLE_SUB; ++u) gmin[u] = INF;
+            const int nv = (t1 - t0) * NH;  // accumulator tiles of the unit, in MMA order: base tile v / NH, query tile v % NH
             int first = (grp - tcount % TC_EPI_GROUPS + TC_EPI_GROUPS) % TC_EPI_GROUPS;
             int j = 0;
-            for (int i = first; i < t1 - t0; i += TC_EPI_GROUPS, ++j) {
-                const int t = (t0 + i) * p.tile_stride + p.tile_off;  // the base tile
+            for (int i = first; i < nv; i += TC_EPI_GROUPS, ++j) {
+                const int hsel = PAIR ? (i & 1) : 0;
+                const int q = PAIR ? (hsel ? qh[NH - 1] : qh[0]) : qh[0];
+                const bool valid = PAIR ? (hsel ? validh[NH - 1] : validh[0]) : validh[0];
+                const bool quad_live = PAIR ? (hsel ? liveh[NH - 1] : liveh[0]) : liveh[0];
+                const float thr = PAIR ? (hsel ? thrh[NH - 1] : thrh[0]) : thrh[0];
+                const int t = (t0 + i / NH) * p.tile_stride + p.tile_off;  // the base tile
                 const int tc = tcount + i;
                 const int acc = tc & (TC_NACC - 1);
                 const uint32_t acc_phase = (uint32_t)(tc / TC_NACC) & 1u;
@@ -747,12 +777,12 @@ exact_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&acc_empty[acc]);
             }
-            tcount += t1 - t0;
+            tcount += nv;
             if constexpr (SAMPLE) {
-                if (valid) {
+                if (validh[0]) {
 #pragma unroll
                     for (int u = 0; u < TC_SAMPLE_SUB; ++u)
-                        p.smin[((size_t)(split * TC_EPI_GROUPS + grp) * TC_SAMPLE_SUB + u) * p.nq + q] = gmin[u];
+                        p.smin[((size_t)(split * TC_EPI_GROUPS + grp) * TC_SAMPLE_SUB + u) * p.nq + qh[0]] = gmin[u];
                 }
             }
         }
