@@ -105,11 +105,24 @@ bool run_benchmark(const std::string& dataset_name, const std::string& base_file
         std::cerr << "Error: " << vs_last_error() << std::endl;
         return false;
     }
-    const double build_s = std::chrono::duration<double>(clock::now() - build_start).count();
-
     std::vector<int32_t> ids(Q_rows * (size_t)k);
     std::vector<float> dists(Q_rows * (size_t)k);
     const int64_t batch = opt.batch > 0 ? opt.batch : (int64_t)std::max<size_t>(Q_rows, 1);
+    // still index build: one untimed search of the first batch, so that the device workspaces, the kernel modules and (multi-GPU)
+    // the NCCL channels exist before the timed region — the GPU counterpart of the reference's precomputed norms
+    if (Q_rows > 0) {
+        const int64_t nb = (int64_t)std::min<size_t>((size_t)batch, Q_rows);
+        const int rc = multi ? vs_exact_mgpu_search_f32(multi, Q.data(), nb, k, opt.precision, ids.data(), dists.data())
+                             : vs_exact_search_f32(index, Q.data(), nb, k, opt.precision, ids.data(), dists.data());
+        if (rc != VS_OK) {
+            std::cerr << "Error: " << vs_last_error() << std::endl;
+            if (multi) vs_exact_mgpu_destroy(multi);
+            else vs_exact_destroy(index);
+            return false;
+        }
+    }
+    const double build_s = std::chrono::duration<double>(clock::now() - build_start).count();
+
     std::vector<double> batch_times;
     int precision_used = 0, launches = 0;
 
