@@ -398,10 +398,11 @@ int exact_search_core(vs_exact* h, const float* q_dev, int64_t nq, int k, int pr
         return fail(VS_ERR_INVALID, "unknown precision");
     if (nq > 0x7fffffff / 128) return fail(VS_ERR_INVALID, "nq too large");
     if (prec == VS_PREC_F16_CERTIFIED && k > 16) return fail(VS_ERR_UNSUPPORTED, "certified fp16 candidate pass needs k <= 16");
-    // AUTO (measured on B200, 1M x 128, top-10, whole call): <= 8 queries: one FFMA pass over the base (0.17-0.29 ms);
-    // 9..448 queries: TF32 tensor-core kernel (0.27-0.45 ms: fewer launches and no host round trip); beyond that the
-    // certified fp16 candidate pass wins (0.49 vs 0.52 ms at 512 queries, 1.7 vs 3.4 ms at 4096)
-    constexpr int64_t kAutoFfmaMax = 8, kAutoF16Min = 449;
+    // AUTO (measured on B200, top-10, whole call, tools/small_batch.py -> profiles/r2_small_batch_sweep.txt): <= 8 queries: one
+    // FFMA pass over the fp32 base (0.17-0.28 ms at 1M rows; host calls replay a CUDA graph); from 9 queries on the certified
+    // fp16 path wins at every batch size — it streams the half-size fp16 base: 0.16 ms up to 256 queries, 0.21 ms at 512,
+    // 0.95 ms at 4096, against 0.27 / 0.54 / 3.5 ms for 3xTF32 (125K rows: 0.10-0.26 ms against 0.13-0.52)
+    constexpr int64_t kAutoFfmaMax = 8, kAutoF16Min = 9;
     if (prec == VS_PREC_AUTO && nq >= kAutoF16Min && k <= 16 && dim == 128 && f16_pass_supported(h->n)) prec = VS_PREC_F16_CERTIFIED;
     // bases too small for a meaningful sample pass (513 .. ~13 K rows) take the 3xTF32 path: same answer, and just as fast there
     if (prec == VS_PREC_F16_CERTIFIED && dim == 128 && !f16_pass_supported(h->n)) prec = VS_PREC_FP32_3XTF32;
