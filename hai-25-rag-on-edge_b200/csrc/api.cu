@@ -400,9 +400,11 @@ int exact_search_core(vs_exact* h, const float* q_dev, int64_t nq, int k, int pr
     if (prec == VS_PREC_F16_CERTIFIED && k > 16) return fail(VS_ERR_UNSUPPORTED, "certified fp16 candidate pass needs k <= 16");
     // AUTO (measured on B200, top-10, whole call, tools/small_batch.py -> profiles/r2_small_batch_sweep.txt): <= 8 queries: one
     // FFMA pass over the fp32 base (0.17-0.28 ms at 1M rows; host calls replay a CUDA graph); from 9 queries on the certified
-    // fp16 path wins at every batch size — it streams the half-size fp16 base: 0.16 ms up to 256 queries, 0.21 ms at 512,
+    // fp16 path wins at every batch size (device-pointer calls) — it streams the half-size fp16 base: 0.16 ms up to 256 queries, 0.21 ms at 512,
     // 0.95 ms at 4096, against 0.27 / 0.54 / 3.5 ms for 3xTF32 (125K rows: 0.10-0.26 ms against 0.13-0.52)
-    constexpr int64_t kAutoFfmaMax = 8, kAutoF16Min = 9;
+    // Host calls: FFMA graph 0.167 / 0.175 / 0.212 / 0.295 ms at batch 1 / 2 / 4 / 8, fp16 path 0.173-0.175 ms at all of them:
+    // the fp16 path takes over from 3 queries (where it applies); otherwise FFMA up to 8 queries, TF32 beyond
+    constexpr int64_t kAutoFfmaMax = 8, kAutoF16Min = 3;
     if (prec == VS_PREC_AUTO && nq >= kAutoF16Min && k <= 16 && dim == 128 && f16_pass_supported(h->n)) prec = VS_PREC_F16_CERTIFIED;
     // bases too small for a meaningful sample pass (513 .. ~13 K rows) take the 3xTF32 path: same answer, and just as fast there
     if (prec == VS_PREC_F16_CERTIFIED && dim == 128 && !f16_pass_supported(h->n)) prec = VS_PREC_FP32_3XTF32;
@@ -661,8 +663,9 @@ int vs_exact_search_f32(vs_exact_t* h, const float* queries, int64_t nq, int k, 
     if (!queries || !out_ids || !out_dists) return fail(VS_ERR_INVALID, "NULL buffer");
     VSB_CUDA(cudaSetDevice(h->device));
     cudaStream_t st = h->stream;
-    if (nq <= 8 && k <= kMaxRegK && h->dim == 128 && (precision == VS_PREC_AUTO || precision == VS_PREC_FP32_FFMA) && !h->profile &&
-        !h->cert_pending && !h->broken && !getenv("VSB_NO_GRAPH"))
+    const bool auto_f16 = precision == VS_PREC_AUTO && nq >= 3 && k <= 16 && f16_pass_supported(h->n);  // exact_search_core's rule
+    if (nq <= 8 && k <= kMaxRegK && h->dim == 128 && ((precision == VS_PREC_AUTO && !auto_f16) || precision == VS_PREC_FP32_FFMA) &&
+        !h->profile && !h->cert_pending && !h->broken && !getenv("VSB_NO_GRAPH"))
         return exact_search_small_graph(h, queries, nq, k, out_ids, out_dists);
     VSB_TRY(h->q.reserve(sizeof(float) * (size_t)nq * h->dim));
     VSB_TRY(h->out_ids.reserve(sizeof(int32_t) * (size_t)nq * k));

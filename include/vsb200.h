@@ -53,7 +53,7 @@ typedef enum vs_status {
 /* Arithmetic of the exact path's dot products (distances are always combined in fp32 as
  * (qn + bn) - 2*dot, cpu_baseline.cpp:241). */
 typedef enum vs_precision {
-    VS_PREC_AUTO = 0,        /* <= 8 queries -> FFMA stream; >= 9 queries, k <= 16, base >= ~13 K rows -> certified fp16 pass
+    VS_PREC_AUTO = 0,        /* <= 2 queries (<= 8 where the fp16 pass does not apply) -> FFMA stream; >= 3 queries, k <= 16, base >= ~13 K rows -> certified fp16 pass
                                 (below); otherwise 1xTF32 when every operand is exactly representable in TF32 (integer
                                 SIFT data: bit-identical to fp32), else 3xTF32.  Thresholds measured on B200. */
     VS_PREC_FP32_3XTF32 = 1, /* tcgen05 kind::tf32, hi/lo split, 3 products, fp32 accumulate in TMEM.  The tensor-core keys
