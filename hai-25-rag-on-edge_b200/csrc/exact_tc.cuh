@@ -1,25 +1,24 @@
-// K1 — fused distance GEMM + top-k on the 5th-generation tensor cores (tcgen05, accumulators in TMEM, operands
+// K1 — fused distance GEMM + selection on the 5th-generation tensor cores (tcgen05, accumulators in TMEM, operands
 // fed by TMA), replacing the reference's per-query  cblas_sgemm(M=1) -> distance loop -> select_topk
 // (cpu/cpu_baseline.cpp:222-248) for a whole batch of queries.  The Q x N distance matrix never exists in
-// memory: each epilogue thread owns one query row of the accumulator tile and folds it into a register-
-// resident candidate list.
+// memory: each epilogue thread owns one query row of the accumulator tile (a TMEM lane), 32 columns at a time.
 //
-// Mapping: queries -> M (TMEM lanes, 128 per CTA), base rows -> N (TMEM columns, 128 per tile), K = dim = 128 as
-// 4 k-blocks of 32 fp32 (one 128-byte swizzle row each).  kind::tf32, K = 8 per instruction.
+// Mapping: queries -> M (TMEM lanes, 128 per CTA), base rows -> N (TMEM columns, 128 per tile), K = dim = 128.
 //   1xTF32 : 16 MMAs per tile (exact when operands are TF32-representable, e.g. integer SIFT data)
 //   3xTF32 : q.x ~= q_lo.x_hi + q_hi.x_hi + q_hi.x_lo per k-block, 48 MMAs per tile, fp32 accumulate
-// Ranking key per (query, base row): bn - 2*dot (the query norm is constant per row of the tile); the merge
-// kernel recomputes the reported distance of the surviving candidates in exact fp32 (kernels.cu, K3).
+//   F16    : 8 kind::f16 MMAs on power-of-two scaled fp16 copies + 1 for the norm block: the accumulator is the key
+// TF32 modes: ranking key bn - 2*dot, a sorted register list per (unit, epilogue group, query), thresholds shared between
+// groups and CTAs; the merge kernel recomputes the reported distances of the survivors in exact fp32 (kernels.cu).
+// F16 mode: a candidate generator built as a threshold filter — sample pass (KTOP == 1: group minima over one base tile in
+// 16), per-query threshold (tc_select_thr_kernel), filter pass (KTOP == 32: every row below the threshold is appended to the
+// query's candidate array, two query tiles per unit), filter merge + certificate (kernels.cu); see DESIGN.md §3 / §4.
 //
-// Work decomposition: unit = (query tile, base split); units are ordered split-major so that the CTAs resident
-// at any moment sweep the same base panel (it streams from HBM once and is re-read from L2 by the other
-// query tiles).  Every unit writes two sorted partial lists per query (one per epilogue warpgroup).
-// Per-query thresholds are shared between CTAs through a global array (atomicMin of each full list's worst kept
-// key — an upper bound of the query's KTOP-th best key), so later units start with a tight filter.
+// Work decomposition: unit = (query tile [pair], base split); units are ordered split-major so that the CTAs resident
+// at any moment sweep the same base panel (it streams from HBM once and is re-read from L2 by the other query tiles).
 //
-// Warp roles (320 threads): warp 0 = TMA producer (one lane), warp 1 = TMEM allocator + MMA issuer (one
-// lane), warps 2..9 = epilogue: warpgroup g = (warp-2)/4 handles columns [64g, 64g+64) of every tile, TMEM
-// lane quadrant = warp % 4.
+// Warp roles: warp 0 = TMA producer (one lane), warp 1 = TMEM allocator + MMA issuer (one lane), warps 2-3 idle,
+// then three epilogue warpgroups that take accumulator tiles round-robin (TMEM lane quadrant = warp % 4), and in F16 mode
+// a fifth warpgroup of four keeper warps (one per quadrant) that drain the epilogue warps' candidate queues.
 #pragma once
 #include <cuda.h>
 
@@ -34,10 +33,9 @@ constexpr int TC_NACC = 4;        // accumulator buffers in TMEM (4 x 128 column
 constexpr int TC_EPI_GROUPS = 3;  // epilogue warpgroups; tiles rotate over them
 constexpr int TC_THREADS = 128 + 128 * TC_EPI_GROUPS;  // warpgroup 0: TMA producer, MMA issuer, two idle warps
 constexpr int TC_REGS_CTRL = 80, TC_REGS_EPI = 144;   // setmaxnreg budgets: 128*80 + 384*144 == 64K registers
-// TC_F16 adds a fifth warpgroup of four list-keeper warps (one per TMEM lane quadrant): 640 threads start with 96
-// registers (61440); control drops to 40, the keepers rise to 104 (a 32-entry register list per lane), the three
-// epilogue warpgroups to 112 (128*40 + 128*104 + 384*112 = 61440: setmaxnreg.inc can only take what the CTA itself
-// released)
+// TC_F16 adds a fifth warpgroup of four keeper warps (one per TMEM lane quadrant): 640 threads start with 96 registers
+// (61440); control drops to 40, the keepers to 64, the three epilogue warpgroups rise to 120 (128*40 + 128*64 + 384*120 <=
+// 61440: setmaxnreg.inc can only take what the CTA itself released)
 constexpr int TC_THREADS_Q = TC_THREADS + 128;
 constexpr int TC_REGS_CTRL_Q = 40, TC_REGS_KEEP_Q = 64, TC_REGS_EPI_Q = 120;
 constexpr int TC_SAMPLE_SUB = 8;                                  // sample pass: running minima per thread and unit
@@ -52,9 +50,8 @@ constexpr int TC_SAMPLE_GROUPS = TC_EPI_GROUPS * TC_SAMPLE_SUB;  // groups of sa
 #define VSB_TC_F16_PAIR_STAGES 2
 #endif
 constexpr int TC_QN = VSB_TC_QN;      // candidate-queue entries per EPILOGUE WARP (one queue per (quadrant, group): no slot atomics)
-constexpr int TC_QBATCH = 24;         // queued rows that make a batch worth folding
-constexpr int TC_QUANT_REFRESH = 16;  // tiles of one group between reads of the finished units' quantile posts (power of two)
-constexpr int TC_QENTRY = 144;        // bytes per entry: 32 keys + {row in quadrant, first column, threshold, -}
+constexpr int TC_QBATCH = 24;         // queued entries that make a keeper batch worthwhile
+constexpr int TC_QENTRY = 144;        // bytes per entry: the 32 keys of a chunk + {query, first column, threshold, -}
 constexpr int TC_THR_REFRESH = 4; // tiles of one group between reads of the shared threshold (power of two)
 
 // Operand arithmetic of the tensor-core pass
@@ -101,8 +98,7 @@ struct TcParams {
     const float* bnorm;  // [n_tiles*128], +inf beyond n
     const float* lb_key; // optional per-query exclusive lower bound (multi-pass k > 32), or nullptr
     const int32_t* lb_id;
-    int32_t* gthr;       // [nq] shared thresholds (order-preserving int encoding), preset to a huge value; TC_F16: followed
-                         // by [2][n_splits][nq] floats, the 8th / 16th best key of every finished (split, query) list
+    int32_t* gthr;       // [nq] shared thresholds (order-preserving int encoding), preset to a huge value (TF32 modes)
     float* part_key;     // [n_splits*TC_EPI_GROUPS][nq][KTOP]
     int32_t* part_id;
     int nq;
@@ -179,31 +175,6 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
-}
-
-// Bound of a query's 32nd best key from the lists of FINISHED units (TC_F16): every finished (split, query) list posts
-// its 8th and its 16th best key.  Units cover disjoint rows, so the 4th smallest posted 8th-key has 4 x 8 = 32 rows at
-// or below it, and so has the 2nd smallest posted 16th-key.  Much tighter than the best single list's 32nd key once a
-// few units are done: that one only knows its own 1/n_splits of the rows.
-__device__ __forceinline__ float tc_quantile_cap(const int32_t* gthr, int nq, int n_splits, int q) {
-    const float* g8 = reinterpret_cast<const float*>(gthr + nq) + q;
-    const float* g16 = g8 + (size_t)n_splits * nq;
-    const float BIG = __int_as_float(0x7f7f7f7f);
-    float a0 = BIG, a1 = BIG;                       // two smallest 16th-keys
-    float b0 = BIG, b1 = BIG, b2 = BIG, b3 = BIG;   // four smallest 8th-keys
-    for (int s = 0; s < n_splits; ++s) {
-        const float v16 = __ldcg(g16 + (size_t)s * nq);
-        float x = __ldcg(g8 + (size_t)s * nq);
-        a1 = fminf(a1, fmaxf(a0, v16));
-        a0 = fminf(a0, v16);
-        float lo;
-        lo = fminf(b0, x); x = fmaxf(b0, x); b0 = lo;
-        lo = fminf(b1, x); x = fmaxf(b1, x); b1 = lo;
-        lo = fminf(b2, x); x = fmaxf(b2, x); b2 = lo;
-        b3 = fminf(b3, x);
-    }
-    const float c = fminf(a1, b3);
-    return c < BIG ? c : __int_as_float(0x7f800000);
 }
 
 // CL = CTAs per cluster (1 or 2).  CL == 2: the two CTAs of a pair work on two DIFFERENT query tiles and the SAME base
