@@ -671,9 +671,16 @@ int vs_exact_search_f32(vs_exact_t* h, const float* queries, int64_t nq, int k, 
     VSB_TRY(h->out_ids.reserve(sizeof(int32_t) * (size_t)nq * k));
     VSB_TRY(h->out_keys.reserve(sizeof(float) * (size_t)nq * k));
     VSB_CUDA(cudaMemcpyAsync(h->q.p, queries, sizeof(float) * (size_t)nq * h->dim, cudaMemcpyHostToDevice, st));
-    VSB_TRY(exact_search_core(h, h->q.as<float>(), nq, k, precision, h->out_ids.as<int32_t>(), h->out_keys.as<float>(), st));
-    VSB_CUDA(cudaMemcpyAsync(out_ids, h->out_ids.p, sizeof(int32_t) * (size_t)nq * k, cudaMemcpyDeviceToHost, st));
-    VSB_CUDA(cudaMemcpyAsync(out_dists, h->out_keys.p, sizeof(float) * (size_t)nq * k, cudaMemcpyDeviceToHost, st));
+    // the download is enqueued BEFORE the host waits for the certification count (no idle gap behind the merge kernel); the rare
+    // redo of uncertified queries rewrites rows, so the copies are then repeated
+    VSB_TRY(exact_search_core(h, h->q.as<float>(), nq, k, precision, h->out_ids.as<int32_t>(), h->out_keys.as<float>(), st, true));
+    int redone = 0;
+    for (int pass = 0; pass < 2; ++pass) {
+        VSB_CUDA(cudaMemcpyAsync(out_ids, h->out_ids.p, sizeof(int32_t) * (size_t)nq * k, cudaMemcpyDeviceToHost, st));
+        VSB_CUDA(cudaMemcpyAsync(out_dists, h->out_keys.p, sizeof(float) * (size_t)nq * k, cudaMemcpyDeviceToHost, st));
+        if (pass == 0) VSB_TRY(exact_certified_finish(h, &redone));
+        if (redone == 0) break;
+    }
     VSB_CUDA(cudaStreamSynchronize(st));
     return VS_OK;
 }
