@@ -126,8 +126,9 @@ VSB_API int vs_exact_last_kernel_ms(vs_exact_t* h, float* ms);
  * thresholds — the sample pass over one base tile in 16 and the threshold selection.  0 for the other paths. */
 VSB_API int vs_exact_last_prepass_ms(vs_exact_t* h, float* ms);
 
-/* Test hook for the certification bound of VS_PREC_F16_CERTIFIED: runs ONLY the fp16 tensor-core candidate pass and
- * returns, per query, its 32 candidates as the kernel ranked them — out_ids[nq x 32] (local row ids, -1 padded),
+/* Test hook for the certification bound of VS_PREC_F16_CERTIFIED: runs ONLY the fp16 tensor-core candidate generation
+ * (sample pass, thresholds, filter pass) and returns, per query, the up to 32 candidates the filter merge keeps (24 .. 32
+ * when more rows lie below the threshold) as the kernel ranked them — out_ids[nq x 32] (local row ids, -1 padded),
  * out_keys[nq x 32] (the kernel's keys  ||x||^2 - 2 q.x  in distance units, ascending) — and out_bound[nq], the bound
  * E_q = cert_a*sqrt(||q||^2) + cert_b the certificate assumes for |key - exact key| (tests/test_exact_gpu.py measures
  * the actual error against float64). Host buffers. */
